@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/src).
+
+Run in the build container only (`python oracle/make_golden.py`); the GPU box has no
+/root/reference, so the vectors are committed.  The reference has no tests or golden vectors of
+its own -- these files are what pins the oracle (oracle/ofri_oracle.py) and, through
+it, the CUDA path.  matplotlib is not installed and is never called on the path, so it is stubbed
+(SURVEY §A.9); TIFFs are read with PIL (identical uint8 arrays to skimage.io.imread).
+"""
+import builtins
+import contextlib
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def import_reference():
+    mpl, pp = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+    for n in ("imshow", "figure", "show"):
+        setattr(pp, n, lambda *a, **k: None)
+    mpl.pyplot = pp
+    sys.modules["matplotlib"] = mpl
+    sys.modules["matplotlib.pyplot"] = pp
+    sys.path.insert(0, os.path.join(REF, "src"))
+    import warnings
+    warnings.simplefilter("ignore")
+    import GenericPyramidalOpticalFlow as GPOF
+    import HornSchunck as HS
+    import PhysicsBasedOpticalFlowLiuShen as LS
+    import gaussian_filter as GF
+    import GaussianKernelBitExact as GKBE
+    import GenericPyramidalOpticalFlowWrapper as WRAP
+    return GPOF, HS, LS, GF, GKBE, WRAP
+
+
+@contextlib.contextmanager
+def quiet():
+    saved = builtins.print
+    builtins.print = lambda *a, **k: None
+    try:
+        yield
+    finally:
+        builtins.print = saved
+
+
+def load_bundled():
+    from PIL import Image
+    base = os.path.join(REF, "examples", "testImages", "Bits08", "Ni06")
+    a = np.array(Image.open(os.path.join(base, "parabolic01_0.tif")))
+    b = np.array(Image.open(os.path.join(base, "parabolic01_1.tif")))
+    assert a.dtype == np.uint8 and a.shape == (512, 512)
+    return a, b
+
+
+def rand_img(rng, H, W):
+    """PIV-like random test image: sparse bright blobs on a dark background, values 0..255."""
+    img = rng.uniform(0, 12, (H, W))
+    n = max(4, H * W // 40)
+    ys = rng.integers(0, H, n)
+    xs = rng.integers(0, W, n)
+    img[ys, xs] += rng.uniform(40, 240, n)
+    return np.clip(np.rint(img), 0, 255).astype(np.float32)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    GPOF, HS, LS, GF, GKBE, WRAP = import_reference()
+    rng = np.random.default_rng(20261018)
+    a8, b8 = load_bundled()
+    np.savez_compressed(os.path.join(OUT, "bundled_pair.npz"), im0=a8, im1=b8)
+    I0 = a8.astype(np.float32)
+    I1 = b8.astype(np.float32)
+
+    st = {}
+    # ---- Gaussian coefficient + filter (GF) ------------------------------------------------
+    for tag, (sg, K) in {"g34_3": (3.4, 3), "g048_5": (0.48, 5), "g20_3": (2.0, 3), "g12_7": (1.2, 7),
+                         "g18_9": (1.8, 9)}.items():
+        st["gk_" + tag] = GF.prepareGaussianKernel(sg, K)
+    gimg = rand_img(rng, 37, 53)
+    st["gauss_in"] = gimg
+    for tag, (sg, K) in {"g34_3": (3.4, 3), "g048_5": (0.48, 5), "g12_7": (1.2, 7), "g18_9": (1.8, 9)}.items():
+        st["gauss_out_" + tag] = GF.gaussian_filterPx(np.copy(gimg), sg, K)
+    st["gauss_trunc_out"] = GF.gaussian_filter(np.copy(gimg), 1.8, 4.0 / 0.6 * 3)     # GPOF:211 parameters
+    gsmall = rand_img(rng, 5, 6)
+    st["gauss_small_in"] = gsmall
+    st["gauss_small_out"] = GF.gaussian_filterPx(np.copy(gsmall), 0.48, 5)
+    # ---- Pillow bicubic down-sample (GPOF:67-68) --------------------------------------------
+    for tag, (H, W) in {"a": (48, 64), "b": (47, 61), "c": (33, 50), "d": (150, 259)}.items():
+        img = rand_img(rng, H, W)
+        w = int(np.int32(np.round(W * 0.5)))
+        h = int(np.int32(np.round(H * 0.5)))
+        st["rs_in_" + tag] = img
+        st["rs_out_" + tag] = GPOF.imresize(img, (w, h))
+    img = rand_img(rng, 64, 96)
+    st["rs_in_q"] = img
+    st["rs_out_q"] = GPOF.imresize(img, (24, 16))          # 4:1, as level 1 of a 3-level pyramid
+    # ---- spline up-sample + warp through updateNextPyramidalLevel (GPOF:118-235) -----------
+    for tag, (h, w, H, W) in {"a": (24, 32, 48, 64), "b": (24, 30, 47, 61), "c": (16, 25, 33, 50),
+                              "d": (16, 24, 64, 96)}.items():
+        yy, xx = np.mgrid[0:h, 0:w]
+        Ua = (1.5 * np.sin(yy / 5.0) + 0.8 * np.cos(xx / 7.0) + rng.normal(0, 0.2, (h, w))).astype(np.float32)
+        Va = (0.9 * np.cos(yy / 4.0) * np.sin(xx / 6.0) + rng.normal(0, 0.2, (h, w))).astype(np.float32)
+        n1 = rand_img(rng, H, W)
+        n2 = rand_img(rng, H, W)
+        prev = np.zeros((h, w), dtype=np.float32)
+        st["up_Ua_" + tag] = Ua.copy()
+        st["up_Va_" + tag] = Va.copy()
+        st["up_n1_" + tag] = n1.copy()
+        st["up_n2_" + tag] = n2.copy()
+        for sc in (False, True):
+            with quiet():
+                w1, w2, Uacc, Vacc, U, V = GPOF.updateNextPyramidalLevel(n1.copy(), prev, n2.copy(), Ua.copy(),
+                                                                         Va.copy(), None, None, True, True, sc)
+            s = "_s1_" if sc else "_s0_"
+            st["up_w1" + s + tag] = w1
+            st["up_w2" + s + tag] = w2
+            st["up_Uacc" + s + tag] = Uacc
+            st["up_Vacc" + s + tag] = Vacc
+    # direct warp with large / out-of-range coordinates (GPOF:70-116)
+    img = rand_img(rng, 29, 41)
+    cy = (np.arange(29, dtype=np.float32)[:, None] + rng.uniform(-6, 6, (29, 41))).astype(np.float32)
+    cx = (np.arange(41, dtype=np.float32)[None, :] + rng.uniform(-6, 6, (29, 41))).astype(np.float32)
+    cy[3, 4] = 7.5
+    cx[3, 4] = 8.5
+    cy[5, 6] = -0.5
+    cx[5, 6] = 40.5          # exact .5 ties -> half-to-even
+    st["warp_img"] = img
+    st["warp_cy"] = cy
+    st["warp_cx"] = cx
+    st["warp_out"] = GPOF.doBiLinearWarping(img, cy.copy(), cx.copy(), 1, "nearest")
+    # ---- Horn-Schunck (HS) ----------------------------------------------------------------
+    f1 = GF.gaussian_filterPx(rand_img(rng, 45, 58), 3.4, 3)
+    f2 = GF.gaussian_filterPx(rand_img(rng, 45, 58), 3.4, 3)
+    st["hs_f1"] = f1
+    st["hs_f2"] = f2
+    fx, fy, ft = HS.computeDerivatives(f2, f1)        # as reached from compute(f1, f2): HS:37, 73, 84
+    st["hs_fx"], st["hs_fy"], st["hs_ft"] = fx, fy, ft
+    U0 = rng.normal(0, 0.5, (45, 58)).astype(np.float32)
+    V0 = rng.normal(0, 0.5, (45, 58)).astype(np.float32)
+    st["hs_U0"], st["hs_V0"] = U0, V0
+    for nit in (1, 2, 7, 50):
+        with quiet():
+            U, V, err = HS.HSOpticalFlowAlgoAdapter([3.0], nit).compute(f1, f2, U0.copy(), V0.copy())
+        st["hs_U_%d" % nit], st["hs_V_%d" % nit], st["hs_err_%d" % nit] = U, V, np.float64(err)
+    # ---- Liu-Shen (LS) ---------------------------------------------------------------------
+    g1 = GF.gaussian_filterPx(rand_img(rng, 40, 52), 0.48, 5)
+    g2 = GF.gaussian_filterPx(rand_img(rng, 40, 52), 0.48, 5)
+    st["ls_g1"], st["ls_g2"] = g1, g2
+    rec = []
+    orig_helper = LS.helper
+
+    def recording_helper(B11, B12, B22, bu, bv, u, v, r, c):
+        out = orig_helper(B11, B12, B22, bu, bv, u, v, r, c)
+        rec.append((B11.copy(), B12.copy(), B22.copy(), bu.copy(), bv.copy(), out[0].copy(), out[1].copy(),
+                    float(out[2])))
+        return out
+
+    LS.helper = recording_helper
+    Uin = rng.normal(0, 0.3, (40, 52)).astype(np.float32)
+    Vin = rng.normal(0, 0.3, (40, 52)).astype(np.float32)
+    st["ls_Uin"], st["ls_Vin"] = Uin, Vin
+    for tag, hpar in {"h5": 5, "h01": 0.1}.items():
+        rec.clear()
+        with quiet():
+            U, V, err = LS.LiuShenOpticalFlowAlgoAdapter(hpar).compute(g1.copy(), g2.copy(), Uin.copy(), Vin.copy())
+        st["ls_U_" + tag], st["ls_V_" + tag], st["ls_err_" + tag] = U, V, np.float64(err)
+        st["ls_niter_" + tag] = np.int64(len(rec))
+        B11, B12, B22, bu, bv, un, vn, e0 = rec[0]
+        st["ls_B11_" + tag], st["ls_B12_" + tag], st["ls_B22_" + tag] = B11, B12, B22
+        st["ls_bu0_" + tag], st["ls_bv0_" + tag] = bu, bv
+        st["ls_u1_" + tag], st["ls_v1_" + tag], st["ls_err0_" + tag] = un, vn, np.float64(e0)
+        st["ls_errs_" + tag] = np.array([r[-1] for r in rec], dtype=np.float64)
+    # zero initial guess: iteration-0 bu/bv are exactly Ixt/Iyt
+    rec.clear()
+    with quiet():
+        LS.LiuShenOpticalFlowAlgoAdapter(5).compute(g1.copy(), g2.copy(), np.zeros_like(Uin), np.zeros_like(Vin))
+    st["ls_Ixt"], st["ls_Iyt"] = rec[0][3], rec[0][4]
+    # early exit: identical frames -> zero flow -> total_error == 0 after the first sweep
+    rec.clear()
+    with quiet():
+        U, V, err = LS.LiuShenOpticalFlowAlgoAdapter(5).compute(g1.copy(), g1.copy(), np.zeros_like(Uin),
+                                                                np.zeros_like(Vin))
+    st["ls_same_niter"] = np.int64(len(rec))
+    st["ls_same_U"], st["ls_same_V"], st["ls_same_err"] = U, V, np.float64(err)
+    LS.helper = orig_helper
+    # ---- getGaussianKernelBitExact (GKBE) ----------------------------------------------------
+    for tag, (n, sg) in {"3_0": (3, 0.0), "5_0": (5, 0.0), "7_0": (7, -0.0), "9_0": (9, 0), "3_34": (3, 3.4),
+                         "5_048": (5, 0.48), "7_15": (7, 1.5), "33_495": (33, 4.95), "4_1": (4, 1.0),
+                         "5_m12": (5, -1.2), "11_0": (11, 0.0)}.items():
+        s, kv = GKBE.getGaussianKernelBitExact(n, sg)
+        st["gkbe_sum_" + tag] = np.float64(s)
+        st["gkbe_k_" + tag] = np.asarray(kv, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "stages.npz"), **st)
+
+    # ---- whole-driver goldens ----------------------------------------------------------------
+    def run(im0, im1, FILTER, main, L=1, k=1, FILTER_OPT=None, opt=None, **kw):
+        with quiet():
+            U, V = GPOF.genericPyramidalOpticalFlow(im0, im1, FILTER, main, L, k, FILTER_OPT, opt, **kw)
+        return np.asarray(U, dtype=np.float32), np.asarray(V, dtype=np.float32)
+
+    cfg = {}
+    U, V = run(I0, I1, 3.4, HS.HSOpticalFlowAlgoAdapter([21], 600), 1, 1)
+    cfg["c1_U"], cfg["c1_V"] = U, V
+    U, V = run(I0, I1, 3.4, HS.HSOpticalFlowAlgoAdapter([21, 45], 600), 2, 1)
+    cfg["c2_U"], cfg["c2_V"] = U, V
+    U, V = run(I0, I1, 3.4, HS.HSOpticalFlowAlgoAdapter([21, 45], 600), 2, 1, 0.48, LS.LiuShenOpticalFlowAlgoAdapter(5))
+    cfg["c3_U"], cfg["c3_V"] = U, V
+    np.savez_compressed(os.path.join(OUT, "configs_bundled.npz"), **cfg)
+
+    # smaller whole-driver cases: BOM rows (BOM:143-194) on a 200x232 crop, odd sizes, 3 levels, kLevels=2,
+    # no-warp, LS as main, FILTER=0
+    sm = {}
+    c0 = np.ascontiguousarray(I0[150:350, 100:332])
+    c1 = np.ascontiguousarray(I1[150:350, 100:332])
+    sm["crop0"], sm["crop1"] = c0, c1
+    for name, fs, L, use_ls in (("HS_Fs0_0", 0.0, 1, False), ("HS_Fs3_4", 3.4, 1, False),
+                                ("HS_Fs3_4_PyrLvls2", 3.4, 2, False), ("LiuSE_HS_Fs3_4_PyrLvls2", 3.4, 2, True)):
+        algo = LS.LiuShenOpticalFlowAlgoAdapter(0.1) if use_ls else HS.HSOpticalFlowAlgoAdapter([1.0] * L, 100)
+        with quiet():
+            U, V = WRAP.GenericPyramidalOpticalFlowWrapper(algo, filter_sigma=fs, pyr_levels=L).calculateFlow(c0, c1)
+        sm["bom_%s_U" % name], sm["bom_%s_V" % name] = np.float32(U), np.float32(V)
+    o0 = np.ascontiguousarray(I0[7:7 + 151, 11:11 + 259])          # odd sizes: 151 x 259 -> 76 x 130 (half-even)
+    o1 = np.ascontiguousarray(I1[7:7 + 151, 11:11 + 259])
+    sm["odd0"], sm["odd1"] = o0, o1
+    U, V = run(o0, o1, 3.4, HS.HSOpticalFlowAlgoAdapter([21, 45], 200), 2, 1, 0.48, LS.LiuShenOpticalFlowAlgoAdapter(5))
+    sm["odd_c3_U"], sm["odd_c3_V"] = U, V
+    U, V = run(c0, c1, 3.4, HS.HSOpticalFlowAlgoAdapter([21, 30, 45], 150), 3, 1, 0.48, LS.LiuShenOpticalFlowAlgoAdapter(5))
+    sm["l3_U"], sm["l3_V"] = U, V
+    U, V = run(c0, c1, 3.4, HS.HSOpticalFlowAlgoAdapter([21, 21, 45, 45], 100), 2, 2, 0.48,
+               LS.LiuShenOpticalFlowAlgoAdapter(5))
+    sm["k2_U"], sm["k2_V"] = U, V
+    U, V = run(c0, c1, 0.8, HS.HSOpticalFlowAlgoAdapter([21, 21, 45, 45], 100), 2, 2)       # k>0 with FILTER<=1
+    sm["k2f08_U"], sm["k2f08_V"] = U, V
+    U, V = run(c0, c1, 3.4, HS.HSOpticalFlowAlgoAdapter([21, 45], 100, False), 2, 1, warping=False,
+               pyramidalIntermediateScaling=True, pyramidalScaling=True)
+    sm["nowarp_U"], sm["nowarp_V"] = U, V
+    U, V = run(c0, c1, 3.4, HS.HSOpticalFlowAlgoAdapter([21, 21, 45, 45], 60, False), 2, 2, warping=False,
+               pyramidalScaling=True)
+    sm["nowarp_k2_U"], sm["nowarp_k2_V"] = U, V
+    U, V = run(c0, c1, 3.4, LS.LiuShenOpticalFlowAlgoAdapter(5), 2, 1, 0.0, HS.HSOpticalFlowAlgoAdapter([30, 30], 40))
+    sm["lsmain_hsopt_U"], sm["lsmain_hsopt_V"] = U, V          # LS main, HS optional, FILTER_OPT = 0 (GPOF:384-386)
+    np.savez_compressed(os.path.join(OUT, "configs_small.npz"), **sm)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
