@@ -1,0 +1,290 @@
+"""Host-side Python API over libofri.so: a `Handle` (one GPU, one stream) with one method per C entry point.
+All arithmetic happens in the CUDA library; this file only marshals numpy arrays and parameters."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ALGO_HS, ALGO_LS, ALGO_NONE, Algo, OfriError, Params
+
+_EXC = {_lib.ERR_INVALID: ValueError, _lib.ERR_ALPHAS: IndexError, _lib.ERR_FILTER_OPT: TypeError,
+        _lib.ERR_TOO_SMALL: ValueError, _lib.ERR_UNSUPPORTED: NotImplementedError, _lib.ERR_OOM: MemoryError}
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _batched(a):
+    a = _f32(a)
+    if a.ndim == 2:
+        return a[None], True
+    if a.ndim != 3:
+        raise ValueError("expected a (H, W) or (batch, H, W) array, got shape %r" % (a.shape,))
+    return a, False
+
+
+def hs_algo(alphas_in_order, niter):
+    a = Algo()
+    a.kind = ALGO_HS
+    a.hs_niter = int(niter)
+    if len(alphas_in_order) > _lib.OFRI_MAX_ALPHAS:
+        raise ValueError("more than %d HS alphas" % _lib.OFRI_MAX_ALPHAS)
+    a.n_alphas = len(alphas_in_order)
+    for i, v in enumerate(alphas_in_order):
+        a.alphas[i] = float(np.float32(v))
+    return a
+
+
+def ls_algo(h, maxiter=60, tol=1e-8):
+    a = Algo()
+    a.kind = ALGO_LS
+    a.ls_h = float(np.float32(h))
+    a.ls_maxiter = int(maxiter)
+    a.ls_tol = float(tol)
+    return a
+
+
+def no_algo():
+    a = Algo()
+    a.kind = ALGO_NONE
+    return a
+
+
+def gaussian_taps(sigma, ksize):
+    """prepareGaussianKernel (gaussian_filter.py:47-52), generated with numpy exactly as the reference does so the
+    coefficients handed to the kernels are bit-identical."""
+    k = np.zeros(ksize, dtype=np.float32)
+    xs = np.arange(-ksize / 2, ksize / 2, 1, dtype=int)
+    k[:] = 1.0 / np.sqrt(2.0 * np.pi * sigma ** 2) * np.exp(-xs ** 2 / (2.0 * sigma ** 2))
+    k /= np.sum(k)
+    return k
+
+
+def make_params(main, optional=None, filter_sigma=0.0, filter_opt_sigma=None, pyramid_levels=1, k_levels=1,
+                warping=True, bilinear=True, intermediate_scaling=True, final_scaling=False,
+                main_taps=3, opt_taps=5):
+    p = Params()
+    p.size = C.sizeof(Params)
+    p.pyramid_levels = int(pyramid_levels)
+    p.k_levels = int(k_levels)
+    p.warping = int(bool(warping))
+    p.bilinear = int(bool(bilinear))
+    p.intermediate_scaling = int(bool(intermediate_scaling))
+    p.final_scaling = int(bool(final_scaling))
+    p.main_algo = main
+    p.opt_algo = optional if optional is not None else no_algo()
+    if filter_sigma > 1e-3:                                         # GPOF:368
+        t = gaussian_taps(filter_sigma, main_taps)
+        p.n_taps_main = len(t)
+        for i, v in enumerate(t):
+            p.taps_main[i] = v
+    p.refilter_k = int(filter_sigma > 1)                            # GPOF:396
+    if optional is not None and optional.kind != ALGO_NONE:
+        if filter_opt_sigma is None:                                # GPOF:380 compares None > 1e-3
+            raise TypeError("'>' not supported between instances of 'NoneType' and 'float'")
+        if filter_opt_sigma > 1e-3:
+            t = gaussian_taps(filter_opt_sigma, opt_taps)
+            p.n_taps_opt = len(t)
+            for i, v in enumerate(t):
+                p.taps_opt[i] = v
+    return p
+
+
+class Handle:
+    """One GPU context of libofri (ofri_create / ofri_destroy)."""
+
+    def __init__(self, device=0):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        rc = self._L.ofri_create(int(device), C.byref(self._h))
+        if rc != 0:
+            msg = self._L.ofri_last_error(None).decode()
+            self._h = None
+            raise OfriError(rc, msg)
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ofri_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing -----------------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._L.ofri_last_error(self._h).decode()
+            raise _EXC.get(rc, OfriError)(msg) if rc in _EXC else OfriError(rc, msg)
+
+    def set_option(self, key, value):
+        self._check(self._L.ofri_set_option(self._h, key.encode(), int(value)))
+
+    def get_option(self, key):
+        v = C.c_int()
+        self._check(self._L.ofri_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._L.ofri_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self._check(self._L.ofri_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._L.ofri_launch_count(self._h))
+
+    def stage_timings(self):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = self._L.ofri_stage_timings(self._h, names, ms, 64)
+        return {names[i].decode(): float(ms[i]) for i in range(n)}
+
+    # -- whole path ---------------------------------------------------------------------------------------------
+    def pyramidal_flow(self, im1, im2, params, want_errors=False):
+        a, single = _batched(im1)
+        b, _ = _batched(im2)
+        if a.shape != b.shape:
+            raise ValueError("im1 and im2 must have the same shape")
+        B, H, W = a.shape
+        U = np.empty((B, H, W), np.float32)
+        V = np.empty((B, H, W), np.float32)
+        ncall = max(params.pyramid_levels * params.k_levels, 1)
+        err = np.zeros((B, ncall, 2), np.float32) if want_errors else None
+        self._check(self._L.ofri_pyramidal_flow(self._h, a.ctypes.data, b.ctypes.data, B, H, W, C.byref(params),
+                                                U.ctypes.data, V.ctypes.data, err.ctypes.data if want_errors else None))
+        if single:
+            U, V = U[0], V[0]
+            err = err[0] if want_errors else None
+        return (U, V, err) if want_errors else (U, V)
+
+    def pyramidal_flow_ptr(self, im1_ptr, im2_ptr, batch, H, W, params, u_ptr, v_ptr, err_ptr=None, device=False):
+        """Raw-pointer form: HOST pointers (device=False; e.g. pinned torch tensors) or DEVICE pointers."""
+        fn = self._L.ofri_pyramidal_flow_dev if device else self._L.ofri_pyramidal_flow
+        self._check(fn(self._h, im1_ptr, im2_ptr, int(batch), int(H), int(W), C.byref(params), u_ptr, v_ptr, err_ptr))
+
+    # -- adapters ------------------------------------------------------------------------------------------------
+    def hs_compute(self, im1, im2, U0, V0, alpha, niter):
+        a, single = _batched(im1)
+        b, _ = _batched(im2)
+        B, H, W = a.shape
+        u0 = _batched(U0)[0] if U0 is not None else None
+        v0 = _batched(V0)[0] if V0 is not None else None
+        U = np.empty((B, H, W), np.float32)
+        V = np.empty((B, H, W), np.float32)
+        err = np.empty(B, np.float32)
+        self._check(self._L.ofri_hs_compute(self._h, _ptr(a), _ptr(b), _ptr(u0) if u0 is not None else None,
+                                            _ptr(v0) if v0 is not None else None, B, H, W, float(np.float32(alpha)),
+                                            int(niter), _ptr(U), _ptr(V), _ptr(err)))
+        return (U[0], V[0], float(err[0])) if single else (U, V, err)
+
+    def ls_compute(self, im1, im2, U0, V0, h, maxiter=60, tol=1e-8):
+        a, single = _batched(im1)
+        b, _ = _batched(im2)
+        B, H, W = a.shape
+        u0 = _batched(U0)[0] if U0 is not None else None
+        v0 = _batched(V0)[0] if V0 is not None else None
+        U = np.empty((B, H, W), np.float32)
+        V = np.empty((B, H, W), np.float32)
+        err = np.empty(B, np.float32)
+        it = np.empty(B, np.int32)
+        self._check(self._L.ofri_ls_compute(self._h, _ptr(a), _ptr(b), _ptr(u0) if u0 is not None else None,
+                                            _ptr(v0) if v0 is not None else None, B, H, W, float(np.float32(h)),
+                                            int(maxiter), float(tol), _ptr(U), _ptr(V), _ptr(err),
+                                            it.ctypes.data_as(C.POINTER(C.c_int32))))
+        return (U[0], V[0], float(err[0]), int(it[0])) if single else (U, V, err, it)
+
+    # -- stages ---------------------------------------------------------------------------------------------------
+    def gauss_px(self, img, taps):
+        a, single = _batched(img)
+        B, H, W = a.shape
+        t = _f32(taps)
+        out = np.empty_like(a)
+        self._check(self._L.ofri_gauss_px(self._h, _ptr(a), B, H, W, _ptr(t), len(t), _ptr(out)))
+        return out[0] if single else out
+
+    def resize_bicubic(self, img, out_h, out_w):
+        a, single = _batched(img)
+        B, H, W = a.shape
+        out = np.empty((B, out_h, out_w), np.float32)
+        self._check(self._L.ofri_resize_bicubic(self._h, _ptr(a), B, H, W, int(out_h), int(out_w), _ptr(out)))
+        return out[0] if single else out
+
+    def level_size(self, n, scale):
+        return int(self._L.ofri_level_size(int(n), float(scale)))
+
+    def spline_upsample(self, a, out_h, out_w, mul=1.0):
+        a, single = _batched(a)
+        B, h, w = a.shape
+        out = np.empty((B, out_h, out_w), np.float32)
+        self._check(self._L.ofri_spline_upsample(self._h, _ptr(a), B, h, w, int(out_h), int(out_w),
+                                                 float(np.float32(mul)), _ptr(out)))
+        return out[0] if single else out
+
+    def warp_bilinear(self, img, cy, cx):
+        a, single = _batched(img)
+        y, _ = _batched(cy)
+        x, _ = _batched(cx)
+        B, H, W = a.shape
+        out = np.empty_like(a)
+        self._check(self._L.ofri_warp_bilinear(self._h, _ptr(a), _ptr(y), _ptr(x), B, H, W, _ptr(out)))
+        return out[0] if single else out
+
+    def warp_pair(self, im1, im2, us, vs):
+        a, single = _batched(im1)
+        b, _ = _batched(im2)
+        u, _ = _batched(us)
+        v, _ = _batched(vs)
+        B, H, W = a.shape
+        o1 = np.empty_like(a)
+        o2 = np.empty_like(a)
+        self._check(self._L.ofri_warp_pair(self._h, _ptr(a), _ptr(b), _ptr(u), _ptr(v), B, H, W, _ptr(o1), _ptr(o2)))
+        return (o1[0], o2[0]) if single else (o1, o2)
+
+    def hs_derivatives(self, im1, im2):
+        a, single = _batched(im1)
+        b, _ = _batched(im2)
+        B, H, W = a.shape
+        fx, fy, ft = np.empty_like(a), np.empty_like(a), np.empty_like(a)
+        self._check(self._L.ofri_hs_derivatives(self._h, _ptr(a), _ptr(b), B, H, W, _ptr(fx), _ptr(fy), _ptr(ft)))
+        return (fx[0], fy[0], ft[0]) if single else (fx, fy, ft)
+
+    def hs_iterate(self, U0, V0, fx, fy, ft, alpha, niter):
+        u, single = _batched(U0)
+        v, _ = _batched(V0)
+        dx, _ = _batched(fx)
+        dy, _ = _batched(fy)
+        dt, _ = _batched(ft)
+        B, H, W = u.shape
+        U, V = np.empty_like(u), np.empty_like(u)
+        self._check(self._L.ofri_hs_iterate(self._h, _ptr(u), _ptr(v), _ptr(dx), _ptr(dy), _ptr(dt), B, H, W,
+                                            float(np.float32(alpha)), int(niter), _ptr(U), _ptr(V)))
+        return (U[0], V[0]) if single else (U, V)
+
+    def ls_coefficients(self, im1, im2, h):
+        a, single = _batched(im1)
+        b, _ = _batched(im2)
+        B, H, W = a.shape
+        coef = np.empty((8, B, H, W), np.float32)
+        self._check(self._L.ofri_ls_coefficients(self._h, _ptr(a), _ptr(b), B, H, W, float(np.float32(h)), _ptr(coef)))
+        return coef[:, 0] if single else coef
+
+
+_default = {}
+
+
+def default_handle(device=0):
+    """Process-wide handle per device (created on first use; raises without a B200)."""
+    h = _default.get(device)
+    if h is None:
+        h = _default[device] = Handle(device)
+    return h

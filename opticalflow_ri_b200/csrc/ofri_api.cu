@@ -1,0 +1,1060 @@
+// ofri_api.cu -- handle, workspace, the coarse-to-fine driver (genericPyramidalOpticalFlow restated for the
+// GPU: GenericPyramidalOpticalFlow.py:238-416) and the extern "C" boundary declared in include/ofri.h.
+// Host-side only; every numeric stage is a kernel in ofri_stages.cu / ofri_hs.cu / ofri_ls.cu.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "ofri_internal.h"
+#include "ofri_pixel.cuh"
+#include "ofri_tables.h"
+
+using namespace ofri;
+
+namespace {
+
+std::mutex g_err_mutex;
+std::string g_last_error;   // errors without a handle (ofri_create)
+
+struct DevResizeTaps { int* xmin = nullptr; int* cnt = nullptr; double* w = nullptr; int kmax = 0; };
+struct DevSplineSys { double* lo = nullptr; double* cp = nullptr; double* den = nullptr; };
+
+struct StageTime { std::string name; cudaEvent_t e0, e1; };
+
+}  // namespace
+
+struct ofri_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  std::string err;
+  // bump arena for per-call workspace (stream-ordered reuse)
+  char* arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0;
+  // staging buffers of the host-pointer entry points (double buffered)
+  char* stage = nullptr;
+  size_t stage_cap = 0;
+  std::map<std::pair<int, int>, DevResizeTaps> taps;
+  std::map<int, DevSplineSys> splines;
+  LaunchCounter lc;
+  // options
+  int hs_fuse = 4, hs_variant = 0, ls_fuse = 2, chunk_pairs = 0, timing = 0;
+  // timings of the last call
+  std::vector<StageTime> times;
+  std::vector<std::pair<std::string, float>> times_ms;
+};
+
+namespace {
+
+int fail(ofri_handle h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else {
+    std::lock_guard<std::mutex> g(g_err_mutex);
+    g_last_error = buf;
+  }
+  return code;
+}
+
+#define OFRI_CUDA(h, call)                                                                             \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess)                                                                             \
+      return fail(h, e_ == cudaErrorMemoryAllocation ? OFRI_ERR_OOM : OFRI_ERR_CUDA, "%s failed: %s", #call, \
+                  cudaGetErrorString(e_));                                                             \
+  } while (0)
+
+inline long round_up(long v, long m) { return (v + m - 1) / m * m; }
+
+// ---- workspace ---------------------------------------------------------------------------------------------------
+int arena_reserve(ofri_handle h, size_t bytes) {
+  if (bytes <= h->arena_cap) return OFRI_OK;
+  OFRI_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->arena) cudaFree(h->arena);
+  h->arena = nullptr;
+  h->arena_cap = 0;
+  size_t want = bytes + (bytes >> 3);
+  cudaError_t e = cudaMalloc(&h->arena, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&h->arena, want);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, OFRI_ERR_OOM, "cudaMalloc of %zu workspace bytes failed: %s", want, cudaGetErrorString(e));
+  }
+  h->arena_cap = want;
+  return OFRI_OK;
+}
+struct Bump {
+  char* base;
+  size_t off = 0, cap;
+  bool dry;
+  Bump(char* b, size_t c, bool d) : base(b), cap(c), dry(d) {}
+  void* take(size_t bytes) {
+    size_t o = (off + 255) & ~(size_t)255;
+    off = o + bytes;
+    return dry ? nullptr : (void*)(base + o);
+  }
+  Img plane(int batch, int H, int W) {
+    Img m;
+    m.H = H; m.W = W; m.batch = batch;
+    m.pitch = round_up(W, 4);
+    m.stride = m.pitch * H;
+    m.p = (float*)take(sizeof(float) * (size_t)m.stride * batch);
+    return m;
+  }
+  ImgD planed(int batch, int H, int W) {
+    ImgD m;
+    m.H = H; m.W = W; m.batch = batch;
+    m.pitch = W;
+    m.stride = (long)W * H;
+    m.p = (double*)take(sizeof(double) * (size_t)m.stride * batch);
+    return m;
+  }
+};
+// view of a plane buffer (allocated for the finest level) at a coarser level's size
+Img view(const Img& base, int H, int W) {
+  Img m = base;
+  m.H = H; m.W = W;
+  m.pitch = round_up(W, 4);
+  m.stride = m.pitch * H;
+  return m;
+}
+ImgD viewd(const ImgD& base, int H, int W) {
+  ImgD m = base;
+  m.H = H; m.W = W; m.pitch = W; m.stride = (long)W * H;
+  return m;
+}
+Img dense(const float* p, int batch, int H, int W) {
+  Img m;
+  m.p = const_cast<float*>(p);
+  m.H = H; m.W = W; m.batch = batch; m.pitch = W; m.stride = (long)W * H;
+  return m;
+}
+
+// ---- cached per-size tables ----------------------------------------------------------------------------------------
+int get_resize_taps(ofri_handle h, int in_size, int out_size, ResizeTaps* out) {
+  auto key = std::make_pair(in_size, out_size);
+  auto it = h->taps.find(key);
+  if (it == h->taps.end()) {
+    HostResizeTaps t = build_resize_taps(in_size, out_size);
+    DevResizeTaps d;
+    d.kmax = t.kmax;
+    OFRI_CUDA(h, cudaMalloc(&d.xmin, sizeof(int) * out_size));
+    OFRI_CUDA(h, cudaMalloc(&d.cnt, sizeof(int) * out_size));
+    OFRI_CUDA(h, cudaMalloc(&d.w, sizeof(double) * t.w.size()));
+    OFRI_CUDA(h, cudaMemcpy(d.xmin, t.xmin.data(), sizeof(int) * out_size, cudaMemcpyHostToDevice));
+    OFRI_CUDA(h, cudaMemcpy(d.cnt, t.cnt.data(), sizeof(int) * out_size, cudaMemcpyHostToDevice));
+    OFRI_CUDA(h, cudaMemcpy(d.w, t.w.data(), sizeof(double) * t.w.size(), cudaMemcpyHostToDevice));
+    it = h->taps.emplace(key, d).first;
+  }
+  out->xmin = it->second.xmin;
+  out->cnt = it->second.cnt;
+  out->w = it->second.w;
+  out->kmax = it->second.kmax;
+  out->in_size = in_size;
+  out->out_size = out_size;
+  return OFRI_OK;
+}
+int get_spline_sys(ofri_handle h, int n, SplineSys* out) {
+  auto it = h->splines.find(n);
+  if (it == h->splines.end()) {
+    HostSplineSys t = build_spline_sys(n);
+    const int m = n - 2;
+    DevSplineSys d;
+    OFRI_CUDA(h, cudaMalloc(&d.lo, sizeof(double) * m));
+    OFRI_CUDA(h, cudaMalloc(&d.cp, sizeof(double) * m));
+    OFRI_CUDA(h, cudaMalloc(&d.den, sizeof(double) * m));
+    OFRI_CUDA(h, cudaMemcpy(d.lo, t.lo.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+    OFRI_CUDA(h, cudaMemcpy(d.cp, t.cp.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+    OFRI_CUDA(h, cudaMemcpy(d.den, t.den.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+    it = h->splines.emplace(n, d).first;
+  }
+  out->lo = it->second.lo;
+  out->cp = it->second.cp;
+  out->den = it->second.den;
+  out->n = n;
+  return OFRI_OK;
+}
+
+int level_size(int n, double scale) { return level_size_half_even(n, scale); }
+
+// ---- timing -----------------------------------------------------------------------------------------------------------
+struct Timed {
+  ofri_handle h;
+  bool on;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  std::string name;
+  Timed(ofri_handle hh, const char* n) : h(hh), on(hh->timing != 0), name(n) {
+    if (on) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, h->stream);
+    }
+  }
+  ~Timed() {
+    if (on) {
+      cudaEventRecord(e1, h->stream);
+      h->times.push_back({name, e0, e1});
+    }
+  }
+};
+void collect_times(ofri_handle h) {
+  h->times_ms.clear();
+  if (h->times.empty()) return;
+  cudaStreamSynchronize(h->stream);
+  std::map<std::string, float> agg;
+  std::vector<std::string> order;
+  for (auto& t : h->times) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t.e0, t.e1);
+    if (!agg.count(t.name)) order.push_back(t.name);
+    agg[t.name] += ms;
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  for (auto& n : order) h->times_ms.emplace_back(n, agg[n]);
+  h->times.clear();
+}
+
+// ---- parameter validation ------------------------------------------------------------------------------------------------
+int check_params(ofri_handle h, const ofri_params* p, int H, int W) {
+  if (!p) return fail(h, OFRI_ERR_INVALID, "params is NULL");
+  if (p->size != sizeof(ofri_params))
+    return fail(h, OFRI_ERR_INVALID, "ofri_params.size = %u, library expects %zu (ABI mismatch)", p->size,
+                sizeof(ofri_params));
+  if (p->pyramid_levels < 1 || p->pyramid_levels > 16) return fail(h, OFRI_ERR_INVALID, "Invalid scale level");
+  if (p->k_levels < 0) return fail(h, OFRI_ERR_INVALID, "k_levels < 0");
+  if (p->warping && !p->bilinear)
+    return fail(h, OFRI_ERR_UNSUPPORTED, "biLinear=False (Liu-Shen warp, GPOF:204-221) is not on the native path");
+  if (p->n_taps_main < 0 || p->n_taps_main > OFRI_MAX_GAUSS_TAPS || p->n_taps_opt < 0 ||
+      p->n_taps_opt > OFRI_MAX_GAUSS_TAPS || (p->n_taps_main && !(p->n_taps_main & 1)) ||
+      (p->n_taps_opt && !(p->n_taps_opt & 1)))
+    return fail(h, OFRI_ERR_INVALID, "bad Gaussian tap count");
+  const ofri_algo* algos[2] = {&p->main_algo, &p->opt_algo};
+  for (int a = 0; a < 2; ++a) {
+    const ofri_algo* g = algos[a];
+    if (a == 0 && g->kind != OFRI_ALGO_HS && g->kind != OFRI_ALGO_LS)
+      return fail(h, OFRI_ERR_INVALID, "main adapter must be HS or LS");
+    if (g->kind == OFRI_ALGO_HS) {
+      if (g->n_alphas < 0 || g->n_alphas > OFRI_MAX_ALPHAS) return fail(h, OFRI_ERR_INVALID, "bad n_alphas");
+      if (g->n_alphas < p->pyramid_levels * p->k_levels)
+        return fail(h, OFRI_ERR_ALPHAS, "pop from empty list");   // IndexError at HornSchunck.py:36
+      if (g->hs_niter < 0) return fail(h, OFRI_ERR_INVALID, "Niter < 0");
+    } else if (g->kind == OFRI_ALGO_LS) {
+      if (g->ls_maxiter < 1 || g->ls_maxiter > 100000) return fail(h, OFRI_ERR_INVALID, "bad ls_maxiter");
+    } else if (g->kind != OFRI_ALGO_NONE) {
+      return fail(h, OFRI_ERR_INVALID, "unknown adapter kind %d", g->kind);
+    }
+  }
+  // every level must have >= 4 samples per axis for the cubic spline (scipy raises otherwise) and the Gaussian
+  // padding needs n >= half kernel
+  double scale = 1.0 / std::pow(2.0, p->pyramid_levels - 1);
+  for (int l = 1; l <= p->pyramid_levels; ++l) {
+    int hl = l == p->pyramid_levels ? H : level_size(H, scale);
+    int wl = l == p->pyramid_levels ? W : level_size(W, scale);
+    if (hl < 1 || wl < 1) return fail(h, OFRI_ERR_TOO_SMALL, "pyramid level %d is empty (%d x %d)", l, hl, wl);
+    if (l < p->pyramid_levels && (hl < 4 || wl < 4))
+      return fail(h, OFRI_ERR_TOO_SMALL, "pyramid level %d is %d x %d; the cubic spline needs >= 4 samples", l, hl, wl);
+    int hk = (p->n_taps_main > p->n_taps_opt ? p->n_taps_main : p->n_taps_opt) / 2;
+    if (hl < hk || wl < hk) return fail(h, OFRI_ERR_TOO_SMALL, "level %d smaller than the Gaussian half-width", l);
+    scale *= 2.0;
+  }
+  return OFRI_OK;
+}
+
+// ---- the driver ------------------------------------------------------------------------------------------------------------
+struct Workspace {
+  Img lvl1, lvl2, warp1, warp2, work1, work2, opt1, opt2, tmp, fx, fy, ft, U[2], V[2], U0, V0, Uacc, Vacc, us, vs;
+  LsPlanes ls;
+  ImgD M1, T1, M2;
+  double* hs_acc = nullptr;
+  double* ls_errs = nullptr;
+  int* ls_state = nullptr;
+  unsigned* ls_max = nullptr;
+};
+
+void plan_workspace(Bump& b, int batch, int H, int W, const ofri_params* p, Workspace* ws) {
+  const bool multi = p->pyramid_levels > 1;
+  const bool has_opt = p->opt_algo.kind != OFRI_ALGO_NONE;
+  const bool has_ls = p->main_algo.kind == OFRI_ALGO_LS || p->opt_algo.kind == OFRI_ALGO_LS;
+  const bool has_hs = p->main_algo.kind == OFRI_ALGO_HS || p->opt_algo.kind == OFRI_ALGO_HS;
+  if (multi) { ws->lvl1 = b.plane(batch, H, W); ws->lvl2 = b.plane(batch, H, W); }
+  if (multi || p->k_levels > 1) { ws->warp1 = b.plane(batch, H, W); ws->warp2 = b.plane(batch, H, W); }
+  ws->work1 = b.plane(batch, H, W);
+  ws->work2 = b.plane(batch, H, W);
+  if (has_opt) { ws->opt1 = b.plane(batch, H, W); ws->opt2 = b.plane(batch, H, W); }
+  ws->tmp = b.plane(batch, H, W);
+  if (has_hs) { ws->fx = b.plane(batch, H, W); ws->fy = b.plane(batch, H, W); ws->ft = b.plane(batch, H, W); }
+  for (int i = 0; i < 2; ++i) { ws->U[i] = b.plane(batch, H, W); ws->V[i] = b.plane(batch, H, W); }
+  ws->U0 = b.plane(batch, H, W);
+  ws->V0 = b.plane(batch, H, W);
+  ws->Uacc = b.plane(batch, H, W);
+  ws->Vacc = b.plane(batch, H, W);
+  if (multi) {
+    ws->us = b.plane(batch, H, W);
+    ws->vs = b.plane(batch, H, W);
+    int hc = (H + 1) / 2 + 1, wc = (W + 1) / 2 + 1;      // the coarser level is at most this big
+    ws->M1 = b.planed(batch, hc, wc);
+    ws->T1 = b.planed(batch, H, wc);
+    ws->M2 = b.planed(batch, H, wc);
+  }
+  if (has_ls) {
+    for (int c = 0; c < 8; ++c) ws->ls.c[c] = b.plane(batch, H, W);
+    int maxit = 1;
+    if (p->main_algo.kind == OFRI_ALGO_LS) maxit = p->main_algo.ls_maxiter;
+    if (p->opt_algo.kind == OFRI_ALGO_LS && p->opt_algo.ls_maxiter > maxit) maxit = p->opt_algo.ls_maxiter;
+    ws->ls_errs = (double*)b.take(sizeof(double) * 2 * (size_t)maxit * batch);
+    ws->ls_state = (int*)b.take(sizeof(int) * 4 * batch);
+    ws->ls_max = (unsigned*)b.take(sizeof(unsigned) * 2 * batch);
+  }
+  ws->hs_acc = (double*)b.take(sizeof(double) * 2 * batch);
+}
+
+GaussTaps make_taps(const float* k, int n) {
+  GaussTaps t;
+  t.K = n;
+  for (int i = 0; i < OFRI_MAX_GAUSS_TAPS; ++i) t.k[i] = i < n ? k[i] : 0.0f;
+  return t;
+}
+
+// one adapter compute() on level planes.  U/V state lives in ws.U[cur] / ws.V[cur]; returns the new cur.
+// uv_zero: the initial guess is identically zero (lets HS skip the copy of U0 for its error norm).
+int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws, const Img& im1, const Img& im2,
+                int Hl, int Wl, int cur, bool uv_zero, float* d_err, int err_stride) {
+  cudaStream_t s = h->stream;
+  Img U[2] = {view(ws.U[0], Hl, Wl), view(ws.U[1], Hl, Wl)};
+  Img V[2] = {view(ws.V[0], Hl, Wl), view(ws.V[1], Hl, Wl)};
+  if (a.kind == OFRI_ALGO_HS) {
+    Img fx = view(ws.fx, Hl, Wl), fy = view(ws.fy, Hl, Wl), ft = view(ws.ft, Hl, Wl);
+    {
+      Timed t(h, "hs_derivs");
+      launch_hs_derivs(im1, im2, fx, fy, ft, s, h->lc);
+    }
+    Img U0, V0;   // null = zero initial guess
+    if (!uv_zero && d_err) {
+      U0 = view(ws.U0, Hl, Wl);
+      V0 = view(ws.V0, Hl, Wl);
+      launch_copy(U0, U[cur], s, h->lc);
+      launch_copy(V0, V[cur], s, h->lc);
+    }
+    int res;
+    {
+      Timed t(h, "hs_iterate");
+      res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], a.hs_niter,
+                              h->hs_fuse, h->hs_variant, s, h->lc);
+    }
+    cur = res ? (cur ^ 1) : cur;
+    if (d_err) {
+      Timed t(h, "hs_error");
+      launch_hs_error(U[cur], V[cur], U0, V0, ws.hs_acc, d_err, err_stride, s, h->lc);
+    }
+    return cur;
+  }
+  // Liu-Shen: inside the solver u = ROW component (our V), v = COLUMN component (our U)  (LS:38-39)
+  LsPlanes co;
+  for (int c = 0; c < 8; ++c) co.c[c] = view(ws.ls.c[c], Hl, Wl);
+  {
+    Timed t(h, "ls_coefficients");
+    launch_ls_coefficients(im1, im2, a.ls_h, co, ws.ls_max, s, h->lc);
+  }
+  {
+    Timed t(h, "ls_iterate");
+    launch_ls_solve(V[cur], U[cur], V[cur ^ 1], U[cur ^ 1], co, a.ls_h, a.ls_maxiter, a.ls_tol, h->ls_fuse, ws.ls_errs,
+                    ws.ls_state, V[cur], U[cur], d_err, err_stride, nullptr, s, h->lc);
+  }
+  return cur;
+}
+
+// Whole pyramid for `batch` pairs resident on the device.  im1/im2/uo/vo may have any pitch.
+int run_pyramid(ofri_handle h, const Img& im1, const Img& im2, const ofri_params* p, const Img& uo, const Img& vo,
+                float* d_err, Workspace& ws) {
+  cudaStream_t s = h->stream;
+  const int H = im1.H, W = im1.W, L = p->pyramid_levels, KL = p->k_levels;
+  const bool has_opt = p->opt_algo.kind != OFRI_ALGO_NONE;
+  const GaussTaps taps_main = make_taps(p->taps_main, p->n_taps_main);
+  const GaussTaps taps_opt = make_taps(p->taps_opt, p->n_taps_opt);
+  const int err_stride = L * KL * 2;
+  double scale = 1.0 / std::pow(2.0, L - 1);
+  int prevH = 0, prevW = 0;
+  int cur = 0;
+  int call_index = 0;
+  Img Uacc = ws.Uacc, Vacc = ws.Vacc, us = ws.us, vs = ws.vs;   // buffers; swapped after a warp
+  for (int level = 1; level <= L; ++level) {
+    const bool last = level == L;
+    const bool local_scaling = last ? p->final_scaling != 0 : p->intermediate_scaling != 0;
+    int Hl = H, Wl = W;
+    Img n1 = im1, n2 = im2;
+    if (scale < 1.0 && !last) {                                           // GPOF:336-343
+      Hl = level_size(H, scale);
+      Wl = level_size(W, scale);
+      n1 = view(ws.lvl1, Hl, Wl);
+      n2 = view(ws.lvl2, Hl, Wl);
+      ResizeTaps tx, ty;
+      int rc = get_resize_taps(h, W, Wl, &tx);
+      if (rc) return rc;
+      rc = get_resize_taps(h, H, Hl, &ty);
+      if (rc) return rc;
+      Timed t(h, "resize");
+      Img tmp = view(ws.tmp, H, Wl);
+      launch_resize(im1, tmp, n1, tx, ty, s, h->lc);
+      launch_resize(im2, tmp, n2, tx, ty, s, h->lc);
+    }
+    Img w1 = n1, w2 = n2;
+    bool uv_zero = true;
+    Img Ucur = view(ws.U[cur], Hl, Wl), Vcur = view(ws.V[cur], Hl, Wl);
+    if (level > 1) {                                                       // GPOF:351-355 -> 118-235
+      Img ua = view(Uacc, prevH, prevW), va = view(Vacc, prevH, prevW);
+      Img un = view(us, Hl, Wl), vn = view(vs, Hl, Wl);
+      if (prevH != Hl || prevW != Wl) {
+        Timed t(h, "spline_upsample");
+        SplineSys sy, sx;
+        int rc = get_spline_sys(h, prevH, &sy);
+        if (rc) return rc;
+        rc = get_spline_sys(h, prevW, &sx);
+        if (rc) return rc;
+        float mx = 1.0f, my = 1.0f;
+        if (local_scaling) {                                               // GPOF:167-172 (f32 division)
+          mx = (float)Wl / (float)prevW;
+          my = (float)Hl / (float)prevH;
+        }
+        ImgD M1 = viewd(ws.M1, prevH, prevW), T1 = viewd(ws.T1, Hl, prevW), M2 = viewd(ws.M2, Hl, prevW);
+        // mul == 1 must still multiply when scaling is on (x * 1.0f is exact), so pass the flag through mul != 1
+        launch_spline(ua, un, mx, sy, sx, M1, T1, M2, s, h->lc);
+        launch_spline(va, vn, my, sy, sx, M1, T1, M2, s, h->lc);
+      } else {
+        launch_copy(un, ua, s, h->lc);
+        launch_copy(vn, va, s, h->lc);
+        if (local_scaling) { /* factor is exactly 1 */ }
+      }
+      if (p->warping) {
+        Timed t(h, "warp");
+        w1 = view(ws.warp1, Hl, Wl);
+        w2 = view(ws.warp2, Hl, Wl);
+        launch_warp_pair(n1, n2, un, vn, w1, w2, s, h->lc);
+        std::swap(Uacc, us);                                               // finalUAccum = usNew (GPOF:226-227)
+        std::swap(Vacc, vs);
+      } else {                                                             // GPOF:228-232
+        launch_copy(Ucur, un, s, h->lc);
+        launch_copy(Vcur, vn, s, h->lc);
+        uv_zero = false;
+      }
+    }
+    Img UaccL = view(Uacc, Hl, Wl), VaccL = view(Vacc, Hl, Wl);
+    if (level == 1 || !p->warping) {
+      // level 1: Uaccum = Vaccum = 0 (GPOF:365-366); no-warp transition: accumulators restart at 0 (GPOF:231-232)
+      cudaMemsetAsync(UaccL.p, 0, sizeof(float) * (size_t)UaccL.stride * UaccL.batch, s);
+      cudaMemsetAsync(VaccL.p, 0, sizeof(float) * (size_t)VaccL.stride * VaccL.batch, s);
+    }
+    if (uv_zero) {
+      cudaMemsetAsync(Ucur.p, 0, sizeof(float) * (size_t)Ucur.stride * Ucur.batch, s);
+      cudaMemsetAsync(Vcur.p, 0, sizeof(float) * (size_t)Vcur.stride * Vcur.batch, s);
+    }
+    // pre-filters (GPOF:368-386)
+    Img work1 = w1, work2 = w2;
+    if (p->n_taps_main > 0) {
+      Timed t(h, "gauss");
+      work1 = view(ws.work1, Hl, Wl);
+      work2 = view(ws.work2, Hl, Wl);
+      Img tmp = view(ws.tmp, Hl, Wl);
+      launch_gauss(w1, tmp, work1, taps_main, s, h->lc);
+      launch_gauss(w2, tmp, work2, taps_main, s, h->lc);
+    }
+    Img o1 = n1, o2 = n2;
+    if (has_opt && p->n_taps_opt > 0) {
+      Timed t(h, "gauss");
+      o1 = view(ws.opt1, Hl, Wl);
+      o2 = view(ws.opt2, Hl, Wl);
+      Img tmp = view(ws.tmp, Hl, Wl);
+      launch_gauss(n1, tmp, o1, taps_opt, s, h->lc);
+      launch_gauss(n2, tmp, o2, taps_opt, s, h->lc);
+    }
+    for (int k = 0; k < KL; ++k) {
+      if (k > 0) {                                                         // GPOF:392-404
+        if (p->warping) {
+          // same-size "transition": usNew = Uaccum (no spline, no scaling), re-warp the level images
+          Timed t(h, "warp");
+          w1 = view(ws.warp1, Hl, Wl);
+          w2 = view(ws.warp2, Hl, Wl);
+          launch_warp_pair(n1, n2, UaccL, VaccL, w1, w2, s, h->lc);
+          cudaMemsetAsync(Ucur.p, 0, sizeof(float) * (size_t)Ucur.stride * Ucur.batch, s);
+          cudaMemsetAsync(Vcur.p, 0, sizeof(float) * (size_t)Vcur.stride * Vcur.batch, s);
+          uv_zero = true;
+          if (p->n_taps_main > 0 && p->refilter_k) {                       // FILTER > 1 (GPOF:396)
+            work1 = view(ws.work1, Hl, Wl);
+            work2 = view(ws.work2, Hl, Wl);
+            Img tmp = view(ws.tmp, Hl, Wl);
+            launch_gauss(w1, tmp, work1, taps_main, s, h->lc);
+            launch_gauss(w2, tmp, work2, taps_main, s, h->lc);
+          } else {
+            work1 = w1;
+            work2 = w2;
+          }
+        } else {
+          // U, V = Uaccum, Vaccum; accumulators restart at zero; work images unchanged (GPOF:403-404)
+          launch_copy(Ucur, UaccL, s, h->lc);
+          launch_copy(Vcur, VaccL, s, h->lc);
+          cudaMemsetAsync(UaccL.p, 0, sizeof(float) * (size_t)UaccL.stride * UaccL.batch, s);
+          cudaMemsetAsync(VaccL.p, 0, sizeof(float) * (size_t)VaccL.stride * VaccL.batch, s);
+          uv_zero = false;
+        }
+      }
+      float* e_main = d_err ? d_err + 2 * call_index : nullptr;
+      cur = run_adapter(h, p->main_algo, call_index, ws, work1, work2, Hl, Wl, cur, uv_zero, e_main, err_stride);
+      if (has_opt) {
+        float* e_opt = d_err ? d_err + 2 * call_index + 1 : nullptr;
+        cur = run_adapter(h, p->opt_algo, call_index, ws, o1, o2, Hl, Wl, cur, false, e_opt, err_stride);
+      }
+      Ucur = view(ws.U[cur], Hl, Wl);
+      Vcur = view(ws.V[cur], Hl, Wl);
+      {
+        Timed t(h, "accumulate");
+        launch_axpy(UaccL, Ucur, s, h->lc);                                // GPOF:413-414
+        launch_axpy(VaccL, Vcur, s, h->lc);
+      }
+      ++call_index;
+    }
+    prevH = Hl;
+    prevW = Wl;
+    scale *= 2.0;
+  }
+  launch_copy(uo, view(Uacc, H, W), s, h->lc);
+  launch_copy(vo, view(Vacc, H, W), s, h->lc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, OFRI_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return OFRI_OK;
+}
+
+size_t workspace_bytes(int batch, int H, int W, const ofri_params* p) {
+  Bump dry(nullptr, 0, true);
+  Workspace ws;
+  plan_workspace(dry, batch, H, W, p, &ws);
+  return dry.off + 4096;
+}
+
+int ensure_stage(ofri_handle h, size_t bytes) {
+  if (bytes <= h->stage_cap) return OFRI_OK;
+  OFRI_CUDA(h, cudaDeviceSynchronize());
+  if (h->stage) cudaFree(h->stage);
+  h->stage = nullptr;
+  h->stage_cap = 0;
+  cudaError_t e = cudaMalloc(&h->stage, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, OFRI_ERR_OOM, "cudaMalloc of %zu staging bytes failed", bytes);
+  }
+  h->stage_cap = bytes;
+  return OFRI_OK;
+}
+
+int pick_chunk(ofri_handle h, int batch, int H, int W, const ofri_params* p, size_t extra_per_pair) {
+  if (h->chunk_pairs > 0) return h->chunk_pairs < batch ? h->chunk_pairs : batch;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  size_t budget = (free_b + h->arena_cap + h->stage_cap) / 2;     // leave half of the device to the caller
+  size_t per_pair = workspace_bytes(1, H, W, p) + extra_per_pair;
+  long n = (long)(budget / (per_pair ? per_pair : 1));
+  if (n < 1) n = 1;
+  if (n > 64) n = 64;          // enough to fill 148 SMs many times over; keeps the working set bounded
+  return (int)(n < batch ? n : batch);
+}
+
+// generic helper for the stage-level host entry points: upload dense host planes into pitched device planes
+struct HostCall {
+  ofri_handle h;
+  Bump b;
+  HostCall(ofri_handle hh) : h(hh), b(hh->arena, hh->arena_cap, false) {}
+};
+int upload(ofri_handle h, const Img& d, const float* src) {
+  OFRI_CUDA(h, cudaMemcpy2DAsync(d.p, sizeof(float) * d.pitch, src, sizeof(float) * d.W, sizeof(float) * d.W,
+                                 (size_t)d.H * d.batch, cudaMemcpyHostToDevice, h->stream));
+  return OFRI_OK;
+}
+int download(ofri_handle h, float* dst, const Img& d) {
+  OFRI_CUDA(h, cudaMemcpy2DAsync(dst, sizeof(float) * d.W, d.p, sizeof(float) * d.pitch, sizeof(float) * d.W,
+                                 (size_t)d.H * d.batch, cudaMemcpyDeviceToHost, h->stream));
+  return OFRI_OK;
+}
+int finish(ofri_handle h) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, OFRI_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(h, OFRI_ERR_CUDA, "execution failed: %s", cudaGetErrorString(e));
+  collect_times(h);
+  return OFRI_OK;
+}
+// NB: planes uploaded with upload() are contiguous over (batch*H) rows only when stride == pitch*H, which Bump::plane
+// guarantees.
+
+#define OFRI_ENTER(h)                                                        \
+  if (!(h)) return fail(nullptr, OFRI_ERR_INVALID, "NULL handle");           \
+  OFRI_CUDA(h, cudaSetDevice((h)->device));                                  \
+  (h)->err.clear();
+
+#define OFRI_DIMS(h, batch, H, W)                                                                      \
+  if ((batch) < 1 || (H) < 1 || (W) < 1) return fail(h, OFRI_ERR_INVALID, "batch, H, W must be >= 1"); \
+  if ((batch) > 65535) return fail(h, OFRI_ERR_INVALID, "batch > 65535 per call");
+
+}  // namespace
+
+// =====================================================================================================================
+// extern "C"
+// =====================================================================================================================
+extern "C" {
+
+int ofri_abi_version(void) { return OFRI_ABI_VERSION; }
+
+int ofri_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    fail(nullptr, OFRI_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return OFRI_ERR_NO_DEVICE;
+  }
+  return n;
+}
+
+int ofri_create(int device, ofri_handle* out) {
+  if (!out) return fail(nullptr, OFRI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int n = ofri_device_count();
+  if (n <= 0) return fail(nullptr, OFRI_ERR_NO_DEVICE, "no CUDA device available (libofri has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(nullptr, OFRI_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(nullptr, OFRI_ERR_NO_DEVICE, "cannot open CUDA device %d", device);
+  }
+  if (prop.major != 10)
+    return fail(nullptr, OFRI_ERR_NO_DEVICE, "device %d is sm_%d%d; libofri is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  ofri_ctx* h = new ofri_ctx();
+  h->device = device;
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, OFRI_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming);
+  }
+  h->stream = h->own_stream;
+  *out = h;
+  return OFRI_OK;
+}
+
+int ofri_destroy(ofri_handle h) {
+  if (!h) return OFRI_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->taps) { cudaFree(kv.second.xmin); cudaFree(kv.second.cnt); cudaFree(kv.second.w); }
+  for (auto& kv : h->splines) { cudaFree(kv.second.lo); cudaFree(kv.second.cp); cudaFree(kv.second.den); }
+  if (h->arena) cudaFree(h->arena);
+  if (h->stage) cudaFree(h->stage);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(h->ev_h2d[i]);
+    cudaEventDestroy(h->ev_comp[i]);
+    cudaEventDestroy(h->ev_d2h[i]);
+  }
+  cudaStreamDestroy(h->own_stream);
+  cudaStreamDestroy(h->s_in);
+  cudaStreamDestroy(h->s_out);
+  delete h;
+  return OFRI_OK;
+}
+
+const char* ofri_last_error(ofri_handle h) {
+  if (h) return h->err.c_str();
+  std::lock_guard<std::mutex> g(g_err_mutex);
+  static thread_local std::string copy;
+  copy = g_last_error;
+  return copy.c_str();
+}
+
+int ofri_set_stream(ofri_handle h, void* cuda_stream) {
+  OFRI_ENTER(h);
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return OFRI_OK;
+}
+
+int ofri_synchronize(ofri_handle h) {
+  OFRI_ENTER(h);
+  OFRI_CUDA(h, cudaStreamSynchronize(h->stream));
+  OFRI_CUDA(h, cudaStreamSynchronize(h->s_in));
+  OFRI_CUDA(h, cudaStreamSynchronize(h->s_out));
+  return OFRI_OK;
+}
+
+static int* option_slot(ofri_handle h, const char* key) {
+  if (!key) return nullptr;
+  if (!strcmp(key, "hs_fuse")) return &h->hs_fuse;
+  if (!strcmp(key, "hs_variant")) return &h->hs_variant;
+  if (!strcmp(key, "ls_fuse")) return &h->ls_fuse;
+  if (!strcmp(key, "chunk_pairs")) return &h->chunk_pairs;
+  if (!strcmp(key, "timing")) return &h->timing;
+  return nullptr;
+}
+int ofri_set_option(ofri_handle h, const char* key, int value) {
+  OFRI_ENTER(h);
+  int* s = option_slot(h, key);
+  if (!s) return fail(h, OFRI_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
+  *s = value;
+  return OFRI_OK;
+}
+int ofri_get_option(ofri_handle h, const char* key, int* value) {
+  OFRI_ENTER(h);
+  int* s = option_slot(h, key);
+  if (!s || !value) return fail(h, OFRI_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
+  *value = *s;
+  return OFRI_OK;
+}
+int64_t ofri_launch_count(ofri_handle h) { return h ? h->lc.n : 0; }
+
+int ofri_stage_timings(ofri_handle h, const char** names, float* ms, int max_entries) {
+  if (!h) return 0;
+  int n = 0;
+  for (auto& kv : h->times_ms) {
+    if (n >= max_entries) break;
+    if (names) names[n] = kv.first.c_str();
+    if (ms) ms[n] = kv.second;
+    ++n;
+  }
+  return n;
+}
+
+// ---- whole path -------------------------------------------------------------------------------------------------------
+int ofri_pyramidal_flow_dev(ofri_handle h, const float* d_im1, const float* d_im2, int batch, int H, int W,
+                            const ofri_params* p, float* d_u_out, float* d_v_out, float* d_err_out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!d_im1 || !d_im2 || !d_u_out || !d_v_out) return fail(h, OFRI_ERR_INVALID, "NULL image / output pointer");
+  int rc = check_params(h, p, H, W);
+  if (rc) return rc;
+  const int chunk = pick_chunk(h, batch, H, W, p, 0);
+  rc = arena_reserve(h, workspace_bytes(chunk, H, W, p));
+  if (rc) return rc;
+  const size_t plane = (size_t)H * W;
+  const int err_stride = p->pyramid_levels * p->k_levels * 2;
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    int nb = batch - b0 < chunk ? batch - b0 : chunk;
+    Bump bump(h->arena, h->arena_cap, false);
+    Workspace ws;
+    plan_workspace(bump, nb, H, W, p, &ws);
+    rc = run_pyramid(h, dense(d_im1 + b0 * plane, nb, H, W), dense(d_im2 + b0 * plane, nb, H, W), p,
+                     dense(d_u_out + b0 * plane, nb, H, W), dense(d_v_out + b0 * plane, nb, H, W),
+                     d_err_out ? d_err_out + (size_t)b0 * err_stride : nullptr, ws);
+    if (rc) return rc;
+  }
+  return OFRI_OK;
+}
+
+int ofri_pyramidal_flow(ofri_handle h, const float* im1, const float* im2, int batch, int H, int W,
+                        const ofri_params* p, float* u_out, float* v_out, float* err_out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!im1 || !im2 || !u_out || !v_out) return fail(h, OFRI_ERR_INVALID, "NULL image / output pointer");
+  int rc = check_params(h, p, H, W);
+  if (rc) return rc;
+  const size_t plane = (size_t)H * W, plane_b = plane * sizeof(float);
+  const int err_stride = p->pyramid_levels * p->k_levels * 2;
+  const size_t err_b = sizeof(float) * err_stride;
+  // per pair staging: 2 inputs + 2 outputs + errors, double buffered
+  const size_t slot_per_pair = 4 * plane_b + ((err_b + 255) & ~(size_t)255);
+  const int chunk = pick_chunk(h, batch, H, W, p, 2 * slot_per_pair);
+  rc = arena_reserve(h, workspace_bytes(chunk, H, W, p));
+  if (rc) return rc;
+  const size_t slot_b = ((slot_per_pair * chunk) + 255) & ~(size_t)255;
+  rc = ensure_stage(h, 2 * slot_b);
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  const int nchunks = (batch + chunk - 1) / chunk;
+  for (int c = 0; c < nchunks; ++c) {
+    const int b0 = c * chunk;
+    const int nb = batch - b0 < chunk ? batch - b0 : chunk;
+    const int slot = c & 1;
+    char* base = h->stage + slot * slot_b;
+    float* d_i1 = (float*)base;
+    float* d_i2 = d_i1 + plane * chunk;
+    float* d_u = d_i2 + plane * chunk;
+    float* d_v = d_u + plane * chunk;
+    float* d_e = d_v + plane * chunk;
+    // H2D on the copy-in stream once the previous user of this slot (compute of chunk c-2) is done
+    if (c >= 2) OFRI_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_comp[slot], 0));
+    OFRI_CUDA(h, cudaMemcpyAsync(d_i1, im1 + b0 * plane, plane_b * nb, cudaMemcpyHostToDevice, h->s_in));
+    OFRI_CUDA(h, cudaMemcpyAsync(d_i2, im2 + b0 * plane, plane_b * nb, cudaMemcpyHostToDevice, h->s_in));
+    OFRI_CUDA(h, cudaEventRecord(h->ev_h2d[slot], h->s_in));
+    OFRI_CUDA(h, cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
+    if (c >= 2) OFRI_CUDA(h, cudaStreamWaitEvent(s, h->ev_d2h[slot], 0));   // output slot drained
+    Bump bump(h->arena, h->arena_cap, false);
+    Workspace ws;
+    plan_workspace(bump, nb, H, W, p, &ws);
+    rc = run_pyramid(h, dense(d_i1, nb, H, W), dense(d_i2, nb, H, W), p, dense(d_u, nb, H, W), dense(d_v, nb, H, W),
+                     err_out ? d_e : nullptr, ws);
+    if (rc) return rc;
+    OFRI_CUDA(h, cudaEventRecord(h->ev_comp[slot], s));
+    OFRI_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
+    OFRI_CUDA(h, cudaMemcpyAsync(u_out + b0 * plane, d_u, plane_b * nb, cudaMemcpyDeviceToHost, h->s_out));
+    OFRI_CUDA(h, cudaMemcpyAsync(v_out + b0 * plane, d_v, plane_b * nb, cudaMemcpyDeviceToHost, h->s_out));
+    if (err_out)
+      OFRI_CUDA(h, cudaMemcpyAsync(err_out + (size_t)b0 * err_stride, d_e, err_b * nb, cudaMemcpyDeviceToHost,
+                                   h->s_out));
+    OFRI_CUDA(h, cudaEventRecord(h->ev_d2h[slot], h->s_out));
+  }
+  OFRI_CUDA(h, cudaStreamSynchronize(h->s_out));
+  rc = finish(h);
+  return rc;
+}
+
+// ---- adapters stand-alone ------------------------------------------------------------------------------------------------
+int ofri_hs_compute(ofri_handle h, const float* im1, const float* im2, const float* u0, const float* v0, int batch,
+                    int H, int W, float alpha, int niter, float* u_out, float* v_out, float* err) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!im1 || !im2 || !u_out || !v_out) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
+  if (niter < 0) return fail(h, OFRI_ERR_INVALID, "Niter < 0");
+  size_t need = (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 11 + sizeof(double) * 2 * batch +
+                sizeof(float) * batch + 4096;
+  int rc = arena_reserve(h, need);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img i1 = b.plane(batch, H, W), i2 = b.plane(batch, H, W), fx = b.plane(batch, H, W), fy = b.plane(batch, H, W),
+      ft = b.plane(batch, H, W);
+  Img U[2] = {b.plane(batch, H, W), b.plane(batch, H, W)}, V[2] = {b.plane(batch, H, W), b.plane(batch, H, W)};
+  Img U0 = b.plane(batch, H, W), V0 = b.plane(batch, H, W);
+  double* acc = (double*)b.take(sizeof(double) * 2 * batch);
+  float* d_err = (float*)b.take(sizeof(float) * batch);
+  if ((rc = upload(h, i1, im1)) || (rc = upload(h, i2, im2))) return rc;
+  const bool zero0 = !u0 || !v0;
+  if (zero0) {
+    cudaMemsetAsync(U[0].p, 0, sizeof(float) * U[0].stride * batch, h->stream);
+    cudaMemsetAsync(V[0].p, 0, sizeof(float) * V[0].stride * batch, h->stream);
+  } else {
+    if ((rc = upload(h, U[0], u0)) || (rc = upload(h, V[0], v0)) || (rc = upload(h, U0, u0)) ||
+        (rc = upload(h, V0, v0)))
+      return rc;
+  }
+  launch_hs_derivs(i1, i2, fx, fy, ft, h->stream, h->lc);
+  int res = launch_hs_iterate(U[0], V[0], U[1], V[1], fx, fy, ft, alpha, niter, h->hs_fuse, h->hs_variant, h->stream,
+                              h->lc);
+  Img nu, nv;
+  launch_hs_error(U[res], V[res], zero0 ? nu : U0, zero0 ? nv : V0, acc, d_err, 1, h->stream, h->lc);
+  if ((rc = download(h, u_out, U[res])) || (rc = download(h, v_out, V[res]))) return rc;
+  if (err) OFRI_CUDA(h, cudaMemcpyAsync(err, d_err, sizeof(float) * batch, cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
+int ofri_ls_compute(ofri_handle h, const float* im1, const float* im2, const float* u0, const float* v0, int batch,
+                    int H, int W, float hpar, int maxiter, double tol, float* u_out, float* v_out, float* err,
+                    int32_t* iters) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!im1 || !im2 || !u_out || !v_out) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
+  if (maxiter < 1 || maxiter > 100000) return fail(h, OFRI_ERR_INVALID, "bad maxiter");
+  size_t need = (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 14 +
+                sizeof(double) * 2 * (size_t)maxiter * batch + 64 * (size_t)batch + 8192;
+  int rc = arena_reserve(h, need);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img i1 = b.plane(batch, H, W), i2 = b.plane(batch, H, W);
+  Img U[2] = {b.plane(batch, H, W), b.plane(batch, H, W)}, V[2] = {b.plane(batch, H, W), b.plane(batch, H, W)};
+  LsPlanes co;
+  for (int c = 0; c < 8; ++c) co.c[c] = b.plane(batch, H, W);
+  double* errs = (double*)b.take(sizeof(double) * 2 * (size_t)maxiter * batch);
+  int* state = (int*)b.take(sizeof(int) * 4 * batch);
+  unsigned* mx = (unsigned*)b.take(sizeof(unsigned) * 2 * batch);
+  float* d_err = (float*)b.take(sizeof(float) * batch);
+  int* d_it = (int*)b.take(sizeof(int) * batch);
+  if ((rc = upload(h, i1, im1)) || (rc = upload(h, i2, im2))) return rc;
+  if (!u0 || !v0) {
+    cudaMemsetAsync(U[0].p, 0, sizeof(float) * U[0].stride * batch, h->stream);
+    cudaMemsetAsync(V[0].p, 0, sizeof(float) * V[0].stride * batch, h->stream);
+  } else if ((rc = upload(h, U[0], u0)) || (rc = upload(h, V[0], v0))) {
+    return rc;
+  }
+  launch_ls_coefficients(i1, i2, hpar, co, mx, h->stream, h->lc);
+  launch_ls_solve(V[0], U[0], V[1], U[1], co, hpar, maxiter, tol, h->ls_fuse, errs, state, V[0], U[0], d_err, 1, d_it,
+                  h->stream, h->lc);
+  if ((rc = download(h, u_out, U[0])) || (rc = download(h, v_out, V[0]))) return rc;
+  if (err) OFRI_CUDA(h, cudaMemcpyAsync(err, d_err, sizeof(float) * batch, cudaMemcpyDeviceToHost, h->stream));
+  if (iters) OFRI_CUDA(h, cudaMemcpyAsync(iters, d_it, sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
+}
+
+// ---- stages ------------------------------------------------------------------------------------------------------------------
+int ofri_gaussian_taps(double sigma, int n_taps, float* taps_out) {
+  if (!taps_out || n_taps < 1 || n_taps > OFRI_MAX_GAUSS_TAPS || !(n_taps & 1)) return OFRI_ERR_INVALID;
+  // gaussian_filter.py:47-52: f64 sample -> f32 store; sum and divide in f32
+  const int hk = n_taps / 2;
+  float sum = 0.0f;
+  for (int i = 0; i < n_taps; ++i) {
+    double x = (double)(i - hk);
+    double v = 1.0 / std::sqrt(2.0 * M_PI * sigma * sigma) * std::exp(-(x * x) / (2.0 * sigma * sigma));
+    taps_out[i] = (float)v;
+  }
+  // numpy's pairwise sum equals a left-to-right sum for fewer than 8 elements; for longer kernels it differs in the
+  // last bit at most -- callers that need bit-identical taps (the Python shim) pass numpy-generated coefficients.
+  for (int i = 0; i < n_taps; ++i) { volatile float t = sum + taps_out[i]; sum = t; }
+  for (int i = 0; i < n_taps; ++i) { volatile float t = taps_out[i] / sum; taps_out[i] = t; }
+  return OFRI_OK;
+}
+
+int ofri_level_size(int n, double scale) { return level_size(n, scale); }
+
+int ofri_gauss_px(ofri_handle h, const float* in, int batch, int H, int W, const float* taps, int n_taps, float* out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!in || !out || !taps || n_taps < 1 || n_taps > OFRI_MAX_GAUSS_TAPS || !(n_taps & 1))
+    return fail(h, OFRI_ERR_INVALID, "bad gauss arguments");
+  if (H < n_taps / 2 || W < n_taps / 2) return fail(h, OFRI_ERR_TOO_SMALL, "image smaller than the kernel half-width");
+  int rc = arena_reserve(h, (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 3 + 4096);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img i = b.plane(batch, H, W), t = b.plane(batch, H, W), o = b.plane(batch, H, W);
+  if ((rc = upload(h, i, in))) return rc;
+  launch_gauss(i, t, o, make_taps(taps, n_taps), h->stream, h->lc);
+  if ((rc = download(h, out, o))) return rc;
+  return finish(h);
+}
+
+int ofri_resize_bicubic(ofri_handle h, const float* in, int batch, int H, int W, int out_h, int out_w, float* out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!in || !out || out_h < 1 || out_w < 1) return fail(h, OFRI_ERR_INVALID, "bad resize arguments");
+  int rc = arena_reserve(h, (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 3 + 4096);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  if (out_w > W || out_h > H) return fail(h, OFRI_ERR_UNSUPPORTED, "only down-sampling is on the path");
+  Img i = b.plane(batch, H, W), t = b.plane(batch, H, out_w), o = b.plane(batch, out_h, out_w);
+  ResizeTaps tx, ty;
+  if ((rc = get_resize_taps(h, W, out_w, &tx)) || (rc = get_resize_taps(h, H, out_h, &ty))) return rc;
+  if ((rc = upload(h, i, in))) return rc;
+  launch_resize(i, t, o, tx, ty, h->stream, h->lc);
+  if ((rc = download(h, out, o))) return rc;
+  return finish(h);
+}
+
+int ofri_spline_upsample(ofri_handle h, const float* in, int batch, int in_h, int in_w, int out_h, int out_w, float mul,
+                         float* out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, in_h, in_w);
+  if (!in || !out || out_h < 1 || out_w < 1) return fail(h, OFRI_ERR_INVALID, "bad spline arguments");
+  if (in_h < 4 || in_w < 4) return fail(h, OFRI_ERR_TOO_SMALL, "the cubic spline needs >= 4 samples per axis");
+  size_t need = sizeof(float) * ((size_t)round_up(in_w, 4) * in_h + (size_t)round_up(out_w, 4) * out_h) * batch +
+                sizeof(double) * ((size_t)in_h * in_w + 2 * (size_t)out_h * in_w) * batch + 8192;
+  int rc = arena_reserve(h, need);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img i = b.plane(batch, in_h, in_w), o = b.plane(batch, out_h, out_w);
+  ImgD M1 = b.planed(batch, in_h, in_w), T1 = b.planed(batch, out_h, in_w), M2 = b.planed(batch, out_h, in_w);
+  SplineSys sy, sx;
+  if ((rc = get_spline_sys(h, in_h, &sy)) || (rc = get_spline_sys(h, in_w, &sx))) return rc;
+  if ((rc = upload(h, i, in))) return rc;
+  launch_spline(i, o, mul, sy, sx, M1, T1, M2, h->stream, h->lc);
+  if ((rc = download(h, out, o))) return rc;
+  return finish(h);
+}
+
+int ofri_warp_bilinear(ofri_handle h, const float* img, const float* cy, const float* cx, int batch, int H, int W,
+                       float* out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!img || !cy || !cx || !out) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
+  int rc = arena_reserve(h, (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 4 + 4096);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img i = b.plane(batch, H, W), y = b.plane(batch, H, W), x = b.plane(batch, H, W), o = b.plane(batch, H, W);
+  if ((rc = upload(h, i, img)) || (rc = upload(h, y, cy)) || (rc = upload(h, x, cx))) return rc;
+  launch_warp_coords(i, y, x, o, h->stream, h->lc);
+  if ((rc = download(h, out, o))) return rc;
+  return finish(h);
+}
+
+int ofri_warp_pair(ofri_handle h, const float* im1, const float* im2, const float* us, const float* vs, int batch, int H,
+                   int W, float* out1, float* out2) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!im1 || !im2 || !us || !vs || !out1 || !out2) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
+  int rc = arena_reserve(h, (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 6 + 4096);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img a = b.plane(batch, H, W), c = b.plane(batch, H, W), u = b.plane(batch, H, W), v = b.plane(batch, H, W),
+      o1 = b.plane(batch, H, W), o2 = b.plane(batch, H, W);
+  if ((rc = upload(h, a, im1)) || (rc = upload(h, c, im2)) || (rc = upload(h, u, us)) || (rc = upload(h, v, vs)))
+    return rc;
+  launch_warp_pair(a, c, u, v, o1, o2, h->stream, h->lc);
+  if ((rc = download(h, out1, o1)) || (rc = download(h, out2, o2))) return rc;
+  return finish(h);
+}
+
+int ofri_hs_derivatives(ofri_handle h, const float* im1, const float* im2, int batch, int H, int W, float* fx,
+                        float* fy, float* ft) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!im1 || !im2 || !fx || !fy || !ft) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
+  int rc = arena_reserve(h, (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 5 + 4096);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img a = b.plane(batch, H, W), c = b.plane(batch, H, W), dx = b.plane(batch, H, W), dy = b.plane(batch, H, W),
+      dt = b.plane(batch, H, W);
+  if ((rc = upload(h, a, im1)) || (rc = upload(h, c, im2))) return rc;
+  launch_hs_derivs(a, c, dx, dy, dt, h->stream, h->lc);
+  if ((rc = download(h, fx, dx)) || (rc = download(h, fy, dy)) || (rc = download(h, ft, dt))) return rc;
+  return finish(h);
+}
+
+int ofri_hs_iterate(ofri_handle h, const float* u0, const float* v0, const float* fx, const float* fy, const float* ft,
+                    int batch, int H, int W, float alpha, int niter, float* u_out, float* v_out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!u0 || !v0 || !fx || !fy || !ft || !u_out || !v_out) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
+  if (niter < 0) return fail(h, OFRI_ERR_INVALID, "Niter < 0");
+  int rc = arena_reserve(h, (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 7 + 4096);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img dx = b.plane(batch, H, W), dy = b.plane(batch, H, W), dt = b.plane(batch, H, W);
+  Img U[2] = {b.plane(batch, H, W), b.plane(batch, H, W)}, V[2] = {b.plane(batch, H, W), b.plane(batch, H, W)};
+  if ((rc = upload(h, dx, fx)) || (rc = upload(h, dy, fy)) || (rc = upload(h, dt, ft)) || (rc = upload(h, U[0], u0)) ||
+      (rc = upload(h, V[0], v0)))
+    return rc;
+  int res = launch_hs_iterate(U[0], V[0], U[1], V[1], dx, dy, dt, alpha, niter, h->hs_fuse, h->hs_variant, h->stream,
+                              h->lc);
+  if ((rc = download(h, u_out, U[res])) || (rc = download(h, v_out, V[res]))) return rc;
+  return finish(h);
+}
+
+int ofri_ls_coefficients(ofri_handle h, const float* im1, const float* im2, int batch, int H, int W, float hpar,
+                         float* coef) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!im1 || !im2 || !coef) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
+  int rc = arena_reserve(h, (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 10 + 64 * (size_t)batch + 4096);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img a = b.plane(batch, H, W), c = b.plane(batch, H, W);
+  LsPlanes co;
+  for (int i = 0; i < 8; ++i) co.c[i] = b.plane(batch, H, W);
+  unsigned* mx = (unsigned*)b.take(sizeof(unsigned) * 2 * batch);
+  if ((rc = upload(h, a, im1)) || (rc = upload(h, c, im2))) return rc;
+  launch_ls_coefficients(a, c, hpar, co, mx, h->stream, h->lc);
+  for (int i = 0; i < 8; ++i)
+    if ((rc = download(h, coef + (size_t)i * batch * H * W, co.c[i]))) return rc;
+  return finish(h);
+}
+
+}  // extern "C"

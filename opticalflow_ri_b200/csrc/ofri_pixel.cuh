@@ -1,0 +1,259 @@
+// ofri_pixel.cuh -- per-pixel arithmetic of every stage, shared by the simple kernels, the fused (temporally
+// blocked) kernels and the test-only host harness (tests/hostcheck), so that index rules and rounding order are
+// written exactly once.  All functions are __host__ __device__; nothing here touches memory spaces or threads.
+//
+// Rounding discipline: wherever the reference's result depends on separate rounding of each operation
+// (numba f32 loops without FMA contraction, numpy f64 expressions) the explicit *_rn helpers are used so the
+// compiler cannot contract.  The two iterative solvers use explicit fmaf() chains instead (fast path; within
+// the 1e-4 px tolerance) -- explicit, so the simple and fused kernels are bit-identical.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define OFRI_HD __host__ __device__ __forceinline__
+#else
+#define OFRI_HD inline
+#endif
+
+namespace ofri {
+
+// ---- exactly-rounded scalar ops -------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+OFRI_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+OFRI_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+OFRI_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
+OFRI_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+OFRI_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+OFRI_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+OFRI_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+OFRI_HD double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+#else   // host build (tests/hostcheck is compiled with -ffp-contract=off)
+OFRI_HD float fmul(float a, float b) { volatile float r = a * b; return r; }
+OFRI_HD float fadd(float a, float b) { volatile float r = a + b; return r; }
+OFRI_HD float fsub(float a, float b) { volatile float r = a - b; return r; }
+OFRI_HD float fdiv(float a, float b) { volatile float r = a / b; return r; }
+OFRI_HD double dmul(double a, double b) { volatile double r = a * b; return r; }
+OFRI_HD double dadd(double a, double b) { volatile double r = a + b; return r; }
+OFRI_HD double dsub(double a, double b) { volatile double r = a - b; return r; }
+OFRI_HD double ddiv(double a, double b) { volatile double r = a / b; return r; }
+#endif
+
+OFRI_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// scipy 'mirror' for a radius-1 stencil: -1 -> 1, n -> n-2 (degenerate n == 1 -> 0)
+OFRI_HD int mirror1(int i, int n) {
+  if (n == 1) return 0;
+  return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i);
+}
+
+// ---- Gaussian pre-filter (gaussian_filter.py:54-85) ------------------------------------------------------
+// Source index, in the unpadded line of n samples, of padded position p in [0, n+2h):
+//   left/top  P[h-1-j] = a[j]        (mirror including the edge sample)
+//   right/bot P[n+2h-1-j] = a[n-1-j] (forward copy of the last h samples -- reference quirk)
+OFRI_HD int gauss_src_index(int p, int n, int h) {
+  if (p < h) return h - 1 - p;
+  if (p < h + n) return p - h;
+  return p - 2 * h;
+}
+// out[x] = (((0 + P[x+2h] k0) + P[x+2h-1] k1) + ... + P[x] k[K-1]); separate f32 multiply and add
+// (gaussian_filter.py:37-40).  `line` is addressed as line[idx*stride].
+template <typename Taps>
+OFRI_HD float gauss_point(const float* line, long stride, int x, int n, const Taps& k, int K) {
+  const int h = K >> 1;
+  float acc = 0.0f;
+  for (int j = 0; j < K; ++j) {
+    int src = gauss_src_index(x + 2 * h - j, n, h);
+    acc = fadd(acc, fmul(line[(long)src * stride], k[j]));
+  }
+  return acc;
+}
+
+// ---- Pillow BICUBIC resample (libImaging/Resample.c, mode F) ---------------------------------------------
+OFRI_HD double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0;
+  if (x < 2.0) return (((x - 5.0) * x + 8.0) * x - 4.0) * a;
+  return 0.0;
+}
+// one output sample: f64 accumulate, ascending taps, f32 store
+OFRI_HD float resample_point(const float* line, long stride, int xmin, int cnt, const double* w) {
+  double ss = 0.0;
+  for (int t = 0; t < cnt; ++t) ss = dadd(ss, dmul((double)line[(long)(xmin + t) * stride], w[t]));
+  return (float)ss;
+}
+
+// ---- not-a-knot cubic spline evaluation (FITPACK bispev restated) ------------------------------
+// position of output sample k of N over n input samples: i = floor(k n / N), s = frac, clamped to the last knot
+OFRI_HD void spline_locate(int k, int n, int N, int* i_out, double* s_out) {
+  long long num = (long long)k * (long long)n;
+  long long i = num / N;
+  double s = ddiv((double)(num - i * N), (double)N);
+  if (i >= n - 1) { i = n - 2; s = 1.0; }
+  *i_out = (int)i;
+  *s_out = s;
+}
+OFRI_HD double spline_eval(double yi, double yj, double Mi, double Mj, double s) {
+  double t = dsub(1.0, s);
+  double t3 = dmul(dmul(t, t), t);
+  double s3 = dmul(dmul(s, s), s);
+  double a = ddiv(dmul(Mi, t3), 6.0);
+  double b = ddiv(dmul(Mj, s3), 6.0);
+  double c = dmul(dsub(yi, ddiv(Mi, 6.0)), t);
+  double d = dmul(dsub(yj, ddiv(Mj, 6.0)), s);
+  return dadd(dadd(dadd(a, b), c), d);
+}
+
+// ---- bilinear warp (GenericPyramidalOpticalFlow.py:70-116) --------------------------------------------------
+// coordinate of GPOF:200-201: f32( f64(idx) -/+ f64(f32(flow/2)) )
+OFRI_HD float warp_coord(int idx, float flow, float sign) {
+  float half = fmul(flow, 0.5f);
+  double c = sign < 0.0f ? dsub((double)idx, (double)half) : dadd((double)idx, (double)half);
+  return (float)c;
+}
+OFRI_HD float warp_sample(const float* img, long pitch, int H, int W, float cy, float cx) {
+  // np.int32(np.round(c)): half-to-even.  Clamp first so absurd / NaN coordinates saturate instead of trapping
+  // (the reference's behaviour there is undefined; inside +-1e9 the result is identical).
+  int iy = (int)fminf(fmaxf(rintf(cy), -1.0e9f), 1.0e9f);
+  int ix = (int)fminf(fmaxf(rintf(cx), -1.0e9f), 1.0e9f);
+  double dy = dsub((double)cy, (double)iy);
+  double dx = dsub((double)cx, (double)ix);
+  int ny = dy < 0.0 ? iy - 1 : iy + 1;
+  int nx = dx < 0.0 ? ix - 1 : ix + 1;
+  dy = fabs(dy);
+  dx = fabs(dx);
+  iy = clampi(iy, 0, H - 1);
+  ix = clampi(ix, 0, W - 1);
+  ny = clampi(ny, 0, H - 1);
+  nx = clampi(nx, 0, W - 1);
+  double i00 = (double)img[(long)iy * pitch + ix];
+  double i01 = (double)img[(long)iy * pitch + nx];
+  double i10 = (double)img[(long)ny * pitch + ix];
+  double i11 = (double)img[(long)ny * pitch + nx];
+  double oy = dsub(1.0, dy), ox = dsub(1.0, dx);
+  double r = dmul(dmul(oy, ox), i00);
+  r = dadd(r, dmul(dmul(oy, dx), i01));
+  r = dadd(r, dmul(dmul(dy, ox), i10));
+  r = dadd(r, dmul(dmul(dy, dx), i11));
+  return (float)r;
+}
+
+// ---- Horn-Schunck derivatives (HornSchunck.py:107-127 through the swaps of :37/:73/:84) ---------------------
+// a.. = 2x2 block of frame1 (im1 of compute), b.. = same block of frame2; index i+1 / j+1 mirrored (n -> n-2).
+OFRI_HD void hs_deriv_point(float a00, float a01, float a10, float a11, float b00, float b01, float b10, float b11,
+                            float* fx, float* fy, float* ft) {
+  // each scipy convolve: f64 accumulate (exact for these magnitudes), one rounding to f32; then f32 adds
+  float gxa = (float)(dadd(dadd(dadd(dmul(a00, 0.25), dmul(a01, -0.25)), dmul(a10, 0.25)), dmul(a11, -0.25)));
+  float gxb = (float)(dadd(dadd(dadd(dmul(b00, 0.25), dmul(b01, -0.25)), dmul(b10, 0.25)), dmul(b11, -0.25)));
+  float gya = (float)(dadd(dadd(dadd(dmul(a00, 0.25), dmul(a01, 0.25)), dmul(a10, -0.25)), dmul(a11, -0.25)));
+  float gyb = (float)(dadd(dadd(dadd(dmul(b00, 0.25), dmul(b01, 0.25)), dmul(b10, -0.25)), dmul(b11, -0.25)));
+  float bxa = (float)(dadd(dadd(dadd(dmul(a00, 0.25), dmul(a01, 0.25)), dmul(a10, 0.25)), dmul(a11, 0.25)));
+  float bxb = (float)(dadd(dadd(dadd(dmul(b00, -0.25), dmul(b01, -0.25)), dmul(b10, -0.25)), dmul(b11, -0.25)));
+  *fx = fadd(gxb, gxa);
+  *fy = fadd(gyb, gya);
+  *ft = fadd(bxa, bxb);
+}
+
+// ---- Horn-Schunck Jacobi update (HornSchunck.py:52-71) -------------------------------------------------------
+// inv = 1 / (alpha^2 + fx^2 + fy^2), iteration invariant
+OFRI_HD float hs_inv_den(float fx, float fy, float alpha2) {
+  return fdiv(1.0f, fmaf(fy, fy, fmaf(fx, fx, alpha2)));
+}
+// 3x3 weighted average: 1/6 on the 4 edge neighbours, 1/12 on the 4 corners (mirror applied by the caller)
+OFRI_HD float hs_avg(float n, float s, float w, float e, float nw, float ne, float sw, float se) {
+  float edges = fadd(fadd(n, s), fadd(w, e));
+  float corners = fadd(fadd(nw, ne), fadd(sw, se));
+  return fmaf(corners, 0.083333336f, fmul(edges, 0.16666667f));
+}
+// same average from column partial sums: vs_c = n_c + s_c of column c; m_c = centre-row sample of column c
+OFRI_HD float hs_avg_cols(float vsl, float vsc, float vsr, float ml, float mr) {
+  float edges = fadd(vsc, fadd(ml, mr));
+  float corners = fadd(vsl, vsr);
+  return fmaf(corners, 0.083333336f, fmul(edges, 0.16666667f));
+}
+OFRI_HD void hs_update(float ua, float va, float fx, float fy, float ft, float inv, float* u, float* v) {
+  float der = fmul(fmaf(fx, ua, fmaf(fy, va, ft)), inv);
+  *u = fmaf(-fx, der, ua);
+  *v = fmaf(-fy, der, va);
+}
+
+// ---- Liu-Shen (PhysicsBasedOpticalFlowLiuShen.py:47-158) ------------------------------------------------------
+// coefficient planes of one pixel from the 3x3 neighbourhoods (clamp-to-edge applied by the caller) of the
+// NORMALISED images i1, i2; cnt = number of in-bounds 8-neighbours (8 / 5 / 3).  Every product and sum is a
+// separately rounded f32 operation, as in numpy; stencil sums are f64-accumulated and rounded once, as in scipy.
+struct LsCoef { float IIx, IIy, II, Ixt, Iyt, B11, B12, B22; };
+OFRI_HD float ls_stencil_d(float lo, float hi) {   // (hi - lo)/2 : f64 accumulate of (-0.5 lo) + (0.5 hi)
+  return (float)dadd(dmul((double)lo, -0.5), dmul((double)hi, 0.5));
+}
+OFRI_HD LsCoef ls_coef_point(const float a[3][3], const float d[3][3], float hpar, float cnt) {
+  // a = i1 neighbourhood, d = (i2 - i1) neighbourhood (f32 difference), [row][col], centre [1][1]
+  LsCoef c;
+  float i1 = a[1][1];
+  c.IIx = fmul(i1, ls_stencil_d(a[0][1], a[2][1]));
+  c.IIy = fmul(i1, ls_stencil_d(a[1][0], a[1][2]));
+  c.II = fmul(i1, i1);
+  c.Ixt = fmul(i1, ls_stencil_d(d[0][1], d[2][1]));
+  c.Iyt = fmul(i1, ls_stencil_d(d[1][0], d[1][2]));
+  float d2r = (float)dadd(dadd((double)a[0][1], dmul((double)a[1][1], -2.0)), (double)a[2][1]);
+  float d2c = (float)dadd(dadd((double)a[1][0], dmul((double)a[1][1], -2.0)), (double)a[1][2]);
+  float mix = (float)dadd(dadd(dadd(dmul((double)a[0][0], 0.25), dmul((double)a[0][2], -0.25)),
+                               dmul((double)a[2][0], -0.25)), dmul((double)a[2][2], 0.25));
+  float two_i = fmul(2.0f, i1);
+  float hc = fmul(hpar, cnt);
+  float A11 = fsub(fmul(i1, fsub(d2r, two_i)), hc);
+  float A22 = fsub(fmul(i1, fsub(d2c, two_i)), hc);
+  float A12 = fmul(i1, mix);
+  float det = fsub(fmul(A11, A22), fmul(A12, A12));
+  c.B11 = fdiv(A22, det);
+  c.B12 = fdiv(-A12, det);
+  c.B22 = fdiv(A11, det);
+  return c;
+}
+// one Jacobi-type sweep at one pixel.  u = ROW component, v = COLUMN component (adapter swap, LS:38-39).
+// uc / vc: clamp-to-edge neighbourhoods ([row][col]); inb: bit (3*r + c) set iff that neighbour is inside the
+// image (zero padding of the 8-neighbour sum H).  Interior pixels pass inb = 0x1FF.
+OFRI_HD void ls_update(const float uc[3][3], const float vc[3][3], unsigned inb, const LsCoef& c, float hpar,
+                       float* un, float* vn) {
+  float dr_u = fmul(0.5f, fsub(uc[2][1], uc[0][1]));
+  float dc_u = fmul(0.5f, fsub(uc[1][2], uc[1][0]));
+  float dr_v = fmul(0.5f, fsub(vc[2][1], vc[0][1]));
+  float dc_v = fmul(0.5f, fsub(vc[1][2], vc[1][0]));
+  float fr_u = fadd(uc[0][1], uc[2][1]);
+  float fc_v = fadd(vc[1][0], vc[1][2]);
+  float mx_u = fmul(0.25f, fadd(fsub(fsub(uc[0][0], uc[0][2]), uc[2][0]), uc[2][2]));
+  float mx_v = fmul(0.25f, fadd(fsub(fsub(vc[0][0], vc[0][2]), vc[2][0]), vc[2][2]));
+  float h8u = 0.0f, h8v = 0.0f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 3; ++r)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 3; ++q) {
+      if (r == 1 && q == 1) continue;
+      bool in = (inb >> (3 * r + q)) & 1u;
+      h8u = fadd(h8u, in ? uc[r][q] : 0.0f);
+      h8v = fadd(h8v, in ? vc[r][q] : 0.0f);
+    }
+  // bu = 2 IIx Dr(u) + IIx Dc(v) + IIy Dr(v) + II Fr(u) + II Mx(v) + h H8(u) + Ixt     (LS:142-144)
+  float bu = fmul(fmul(2.0f, c.IIx), dr_u);
+  bu = fmaf(c.IIx, dc_v, bu);
+  bu = fmaf(c.IIy, dr_v, bu);
+  bu = fmaf(c.II, fr_u, bu);
+  bu = fmaf(c.II, mx_v, bu);
+  bu = fmaf(hpar, h8u, bu);
+  bu = fadd(bu, c.Ixt);
+  // bv = IIy Dr(u) + IIx Dc(u) + 2 IIy Dc(v) + II Mx(u) + II Fc(v) + h H8(v) + Iyt     (LS:146-148)
+  float bv = fmul(c.IIy, dr_u);
+  bv = fmaf(c.IIx, dc_u, bv);
+  bv = fmaf(fmul(2.0f, c.IIy), dc_v, bv);
+  bv = fmaf(c.II, mx_u, bv);
+  bv = fmaf(c.II, fc_v, bv);
+  bv = fmaf(hpar, h8v, bv);
+  bv = fadd(bv, c.Iyt);
+  *un = -fmaf(c.B11, bu, fmul(c.B12, bv));
+  *vn = -fmaf(c.B12, bu, fmul(c.B22, bv));
+}
+
+}  // namespace ofri

@@ -1,0 +1,297 @@
+// ofri_stages.cu -- per-level stage kernels (sm_100a): Gaussian pre-filter, Pillow-bicubic down-sample,
+// not-a-knot spline up-sample, symmetric bilinear warp, and small element-wise helpers.
+// Each of these runs once per pyramid level (a few % of the bytes of the iteration kernels); they are written
+// for coalesced access (threads along x) and exact reproduction of the reference arithmetic (ofri_pixel.cuh).
+#include "ofri_internal.h"
+#include "ofri_pixel.cuh"
+
+namespace ofri {
+
+static inline dim3 grid2d(int W, int H, int batch, dim3 b) {
+  return dim3((W + b.x - 1) / b.x, (H + b.y - 1) / b.y, batch);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gaussian pre-filter: rows then columns (gaussian_filter.py:54-85)
+// ---------------------------------------------------------------------------------------------------------------
+// Fused separable filter for small kernels: a CTA stages a (TY + 2h) x (TX + 2h) source tile -- already
+// remapped through the reference's padding rule -- in shared memory, row-filters TY+2h rows into a second
+// shared tile, then column-filters.  Rows that the column pass needs above/below the tile are row-filtered
+// redundantly (h rows each side), so the intermediate image never goes to HBM: 4 B read + 4 B written per pixel.
+template <int K, int TX, int TY>
+__global__ void __launch_bounds__(TX* TY) gauss_fused_kernel(Img in, Img out, GaussTaps taps) {
+  constexpr int h = K / 2;
+  constexpr int SW = TX + 2 * h, SH = TY + 2 * h;
+  __shared__ float src[SH][SW + 1];
+  __shared__ float rowf[SH][TX + 1];
+  const int b = blockIdx.z;
+  const float* ip = in.p + (long)b * in.stride;
+  float* op = out.p + (long)b * out.stride;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int tid = threadIdx.y * TX + threadIdx.x;
+  // stage: padded coordinates (py, px) of the tile origin are (y0, x0) .. ; padded index p maps to source
+  // index gauss_src_index(p, n, h).  Rows/cols beyond the image are clamped (never used by valid outputs).
+  for (int i = tid; i < SH * SW; i += TX * TY) {
+    int sy = i / SW, sx = i - sy * SW;
+    int py = y0 + sy, px = x0 + sx;                       // padded-line positions
+    int gy = gauss_src_index(py < in.H + 2 * h ? py : in.H + 2 * h - 1, in.H, h);
+    int gx = gauss_src_index(px < in.W + 2 * h ? px : in.W + 2 * h - 1, in.W, h);
+    src[sy][sx] = ip[(long)gy * in.pitch + gx];
+  }
+  __syncthreads();
+  // row pass: rowf[sy][x] = sum_j P[x + 2h - j] k[j] for the SH staged rows
+  for (int i = tid; i < SH * TX; i += TX * TY) {
+    int sy = i / TX, x = i - sy * TX;
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc = fadd(acc, fmul(src[sy][x + 2 * h - j], taps.k[j]));
+    rowf[sy][x] = acc;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x < in.W && y < in.H) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc = fadd(acc, fmul(rowf[threadIdx.y + 2 * h - j][threadIdx.x], taps.k[j]));
+    op[(long)y * out.pitch + x] = acc;
+  }
+}
+// NOTE on the fused kernel's column pass: the padded column of the ROW-FILTERED image is built from row-filtered
+// rows with the same padding rule; since staging applied the rule to source rows before row-filtering, and the
+// row filter acts independently on each row, rowf[sy] IS the row-filtered image row gauss_src_index(y0+sy).
+
+// generic two-pass fallback for any K (used by the truncate variant, K up to OFRI_MAX_GAUSS_TAPS)
+__global__ void gauss_rows_kernel(Img in, Img out, GaussTaps taps) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (x >= in.W || y >= in.H) return;
+  const float* row = in.p + (long)b * in.stride + (long)y * in.pitch;
+  out.p[(long)b * out.stride + (long)y * out.pitch + x] = gauss_point(row, 1, x, in.W, taps, taps.K);
+}
+__global__ void gauss_cols_kernel(Img in, Img out, GaussTaps taps) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (x >= in.W || y >= in.H) return;
+  const float* col = in.p + (long)b * in.stride + x;
+  out.p[(long)b * out.stride + (long)y * out.pitch + x] = gauss_point(col, in.pitch, y, in.H, taps, taps.K);
+}
+
+void launch_gauss(const Img& in, const Img& tmp, const Img& out, const GaussTaps& taps, cudaStream_t s,
+                  LaunchCounter& lc) {
+  if (taps.K == 3) {
+    dim3 b(32, 8);
+    gauss_fused_kernel<3, 32, 8><<<grid2d(in.W, in.H, in.batch, b), b, 0, s>>>(in, out, taps);
+    lc.n += 1;
+  } else if (taps.K == 5) {
+    dim3 b(32, 8);
+    gauss_fused_kernel<5, 32, 8><<<grid2d(in.W, in.H, in.batch, b), b, 0, s>>>(in, out, taps);
+    lc.n += 1;
+  } else {
+    dim3 b(32, 8);
+    gauss_rows_kernel<<<grid2d(in.W, in.H, in.batch, b), b, 0, s>>>(in, tmp, taps);
+    gauss_cols_kernel<<<grid2d(in.W, in.H, in.batch, b), b, 0, s>>>(tmp, out, taps);
+    lc.n += 2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pillow BICUBIC down-sample: horizontal pass (f32 intermediate) then vertical pass
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void resize_h_kernel(Img in, Img out, ResizeTaps t) {
+  int ox = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (ox >= out.W || y >= out.H) return;
+  const float* row = in.p + (long)b * in.stride + (long)y * in.pitch;
+  out.p[(long)b * out.stride + (long)y * out.pitch + ox] =
+      resample_point(row, 1, t.xmin[ox], t.cnt[ox], t.w + (long)ox * t.kmax);
+}
+__global__ void resize_v_kernel(Img in, Img out, ResizeTaps t) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (x >= out.W || oy >= out.H) return;
+  const float* col = in.p + (long)b * in.stride + x;
+  out.p[(long)b * out.stride + (long)oy * out.pitch + x] =
+      resample_point(col, in.pitch, t.xmin[oy], t.cnt[oy], t.w + (long)oy * t.kmax);
+}
+void launch_resize(const Img& in, const Img& tmp, const Img& out, const ResizeTaps& tx, const ResizeTaps& ty,
+                   cudaStream_t s, LaunchCounter& lc) {
+  dim3 b(32, 8);
+  // tmp: in.H x out.W
+  Img t = tmp;
+  t.H = in.H;
+  t.W = out.W;
+  if (out.W != in.W) {
+    resize_h_kernel<<<grid2d(t.W, t.H, in.batch, b), b, 0, s>>>(in, t, tx);
+    lc.n += 1;
+  } else {
+    t = in;
+  }
+  if (out.H != in.H) {
+    resize_v_kernel<<<grid2d(out.W, out.H, in.batch, b), b, 0, s>>>(t, out, ty);
+    lc.n += 1;
+  } else {
+    launch_copy(out, t, s, lc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Not-a-knot cubic spline up-sample (RectBivariateSpline kx=ky=3, s=0 restated).  f64 throughout.
+// ---------------------------------------------------------------------------------------------------------------
+// One thread per line.  Element e of line l at base[l*line_stride + e*elem_stride].  Writes the second derivatives
+// M (same indexing, f64).  Forward sweep keeps dp in M[e+1]; the backward sweep overwrites it in place.
+template <typename TIn>
+__global__ void spline_solve_kernel(const TIn* __restrict__ y, long y_elem, long y_line, long y_batch,
+                                    double* __restrict__ M, long m_elem, long m_line, long m_batch, int n, int lines,
+                                    SplineSys sys) {
+  int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= lines) return;
+  const TIn* yy = y + (long)blockIdx.z * y_batch + (long)l * y_line;
+  double* mm = M + (long)blockIdx.z * m_batch + (long)l * m_line;
+  const int m = n - 2;
+  double y0 = (double)yy[0], y1 = (double)yy[y_elem], y2;
+  double dp = 0.0;
+  for (int i = 0; i < m; ++i) {
+    y2 = (double)yy[(long)(i + 2) * y_elem];
+    double rhs = dmul(6.0, dadd(dsub(y0, dmul(2.0, y1)), y2));
+    if (i == 0) dp = ddiv(rhs, sys.den[0]);
+    else dp = ddiv(dsub(rhs, dmul(sys.lo[i], dp)), sys.den[i]);
+    mm[(long)(i + 1) * m_elem] = dp;
+    y0 = y1;
+    y1 = y2;
+  }
+  double next = mm[(long)m * m_elem];              // M[m] = dp[m-1]
+  for (int i = m - 2; i >= 0; --i) {
+    double v = dsub(mm[(long)(i + 1) * m_elem], dmul(sys.cp[i], next));
+    mm[(long)(i + 1) * m_elem] = v;
+    next = v;
+  }
+  mm[0] = dsub(dmul(2.0, mm[m_elem]), mm[2 * m_elem]);
+  mm[(long)(n - 1) * m_elem] = dsub(dmul(2.0, mm[(long)(n - 2) * m_elem]), mm[(long)(n - 3) * m_elem]);
+}
+// axis-0 evaluation: T1[k][x] for k < H from y[h][w] (f32) and M1[h][w]
+__global__ void spline_eval0_kernel(Img in, ImgD M1, ImgD T1, int H) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (x >= in.W || k >= H) return;
+  int i;
+  double sfr;
+  spline_locate(k, in.H, H, &i, &sfr);
+  const float* yp = in.p + (long)b * in.stride;
+  const double* mp = M1.p + (long)b * M1.stride;
+  double r = spline_eval((double)yp[(long)i * in.pitch + x], (double)yp[(long)(i + 1) * in.pitch + x],
+                         mp[(long)i * M1.pitch + x], mp[(long)(i + 1) * M1.pitch + x], sfr);
+  T1.p[(long)b * T1.stride + (long)k * T1.pitch + x] = r;
+}
+// axis-1 evaluation + f32 cast + optional scale (GPOF:160, 167-172)
+__global__ void spline_eval1_kernel(ImgD T1, ImgD M2, Img out, float mul, int apply_mul) {
+  int l = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (l >= out.W || k >= out.H) return;
+  int i;
+  double sfr;
+  spline_locate(l, T1.W, out.W, &i, &sfr);
+  const double* tp = T1.p + (long)b * T1.stride + (long)k * T1.pitch;
+  const double* mp = M2.p + (long)b * M2.stride + (long)k * M2.pitch;
+  float r = (float)spline_eval(tp[i], tp[i + 1], mp[i], mp[i + 1], sfr);
+  if (apply_mul) r = fmul(r, mul);
+  out.p[(long)b * out.stride + (long)k * out.pitch + l] = r;
+}
+void launch_spline(const Img& in, const Img& out, float mul, const SplineSys& sy, const SplineSys& sx, const ImgD& M1,
+                   const ImgD& T1, const ImgD& M2, cudaStream_t s, LaunchCounter& lc) {
+  const int h = in.H, w = in.W, H = out.H;
+  // axis 0: one thread per column
+  {
+    dim3 b(128), g((w + 127) / 128, 1, in.batch);
+    spline_solve_kernel<float><<<g, b, 0, s>>>(in.p, in.pitch, 1, in.stride, M1.p, M1.pitch, 1, M1.stride, h, w, sy);
+    dim3 b2(32, 8);
+    spline_eval0_kernel<<<grid2d(w, H, in.batch, b2), b2, 0, s>>>(in, M1, T1, H);
+  }
+  // axis 1: one thread per row of T1
+  {
+    dim3 b(64), g((H + 63) / 64, 1, in.batch);
+    spline_solve_kernel<double><<<g, b, 0, s>>>(T1.p, 1, T1.pitch, T1.stride, M2.p, 1, M2.pitch, M2.stride, w, H, sx);
+    dim3 b2(32, 8);
+    spline_eval1_kernel<<<grid2d(out.W, out.H, in.batch, b2), b2, 0, s>>>(T1, M2, out, mul, mul != 1.0f ? 1 : 0);
+  }
+  lc.n += 4;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bilinear warp (GPOF:70-116, 200-201)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void warp_pair_kernel(Img im1, Img im2, Img us, Img vs, Img o1, Img o2) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (x >= im1.W || y >= im1.H) return;
+  float u = us.p[(long)b * us.stride + (long)y * us.pitch + x];
+  float v = vs.p[(long)b * vs.stride + (long)y * vs.pitch + x];
+  float cy1 = warp_coord(y, v, -1.0f), cx1 = warp_coord(x, u, -1.0f);
+  float cy2 = warp_coord(y, v, +1.0f), cx2 = warp_coord(x, u, +1.0f);
+  o1.p[(long)b * o1.stride + (long)y * o1.pitch + x] =
+      warp_sample(im1.p + (long)b * im1.stride, im1.pitch, im1.H, im1.W, cy1, cx1);
+  o2.p[(long)b * o2.stride + (long)y * o2.pitch + x] =
+      warp_sample(im2.p + (long)b * im2.stride, im2.pitch, im2.H, im2.W, cy2, cx2);
+}
+__global__ void warp_coords_kernel(Img img, Img cy, Img cx, Img o) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (x >= img.W || y >= img.H) return;
+  float fy = cy.p[(long)b * cy.stride + (long)y * cy.pitch + x];
+  float fx = cx.p[(long)b * cx.stride + (long)y * cx.pitch + x];
+  o.p[(long)b * o.stride + (long)y * o.pitch + x] =
+      warp_sample(img.p + (long)b * img.stride, img.pitch, img.H, img.W, fy, fx);
+}
+void launch_warp_pair(const Img& im1, const Img& im2, const Img& us, const Img& vs, const Img& out1, const Img& out2,
+                      cudaStream_t s, LaunchCounter& lc) {
+  dim3 b(32, 8);
+  warp_pair_kernel<<<grid2d(im1.W, im1.H, im1.batch, b), b, 0, s>>>(im1, im2, us, vs, out1, out2);
+  lc.n += 1;
+}
+void launch_warp_coords(const Img& img, const Img& cy, const Img& cx, const Img& out, cudaStream_t s,
+                        LaunchCounter& lc) {
+  dim3 b(32, 8);
+  warp_coords_kernel<<<grid2d(img.W, img.H, img.batch, b), b, 0, s>>>(img, cy, cx, out);
+  lc.n += 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// element-wise helpers
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void axpy_kernel(Img acc, Img x) {
+  int xx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (xx >= acc.W || y >= acc.H) return;
+  long ia = (long)b * acc.stride + (long)y * acc.pitch + xx;
+  acc.p[ia] = fadd(acc.p[ia], x.p[(long)b * x.stride + (long)y * x.pitch + xx]);
+}
+__global__ void scale_kernel(Img x, float mul) {
+  int xx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (xx >= x.W || y >= x.H) return;
+  long i = (long)b * x.stride + (long)y * x.pitch + xx;
+  x.p[i] = fmul(x.p[i], mul);
+}
+__global__ void copy_kernel(Img d, Img sr) {
+  int xx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (xx >= d.W || y >= d.H) return;
+  d.p[(long)b * d.stride + (long)y * d.pitch + xx] = sr.p[(long)b * sr.stride + (long)y * sr.pitch + xx];
+}
+__global__ void fill_kernel(Img d, float v) {
+  int xx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (xx >= d.W || y >= d.H) return;
+  d.p[(long)b * d.stride + (long)y * d.pitch + xx] = v;
+}
+void launch_axpy(const Img& acc, const Img& x, cudaStream_t s, LaunchCounter& lc) {
+  dim3 b(32, 8);
+  axpy_kernel<<<grid2d(acc.W, acc.H, acc.batch, b), b, 0, s>>>(acc, x);
+  lc.n += 1;
+}
+void launch_scale(const Img& x, float mul, cudaStream_t s, LaunchCounter& lc) {
+  dim3 b(32, 8);
+  scale_kernel<<<grid2d(x.W, x.H, x.batch, b), b, 0, s>>>(x, mul);
+  lc.n += 1;
+}
+void launch_copy(const Img& dst, const Img& src, cudaStream_t s, LaunchCounter& lc) {
+  dim3 b(32, 8);
+  copy_kernel<<<grid2d(dst.W, dst.H, dst.batch, b), b, 0, s>>>(dst, src);
+  lc.n += 1;
+}
+void launch_fill(const Img& dst, float v, cudaStream_t s, LaunchCounter& lc) {
+  dim3 b(32, 8);
+  fill_kernel<<<grid2d(dst.W, dst.H, dst.batch, b), b, 0, s>>>(dst, v);
+  lc.n += 1;
+}
+
+const char* kernel_build_info() { return "libofri sm_100a " __DATE__ " " __TIME__; }
+
+}  // namespace ofri
