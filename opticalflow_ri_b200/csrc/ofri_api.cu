@@ -698,6 +698,7 @@ int ofri_synchronize(ofri_handle h) {
   OFRI_CUDA(h, cudaStreamSynchronize(h->stream));
   OFRI_CUDA(h, cudaStreamSynchronize(h->s_in));
   OFRI_CUDA(h, cudaStreamSynchronize(h->s_out));
+  collect_times(h);     // stage timings of device-pointer calls become readable after a synchronise
   return OFRI_OK;
 }
 

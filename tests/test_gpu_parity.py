@@ -1,0 +1,515 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`).  Every call goes through the C ABI of libofri.so
+(opticalflow_ri_b200.Handle is a thin ctypes binding) and is compared with
+
+  * the golden vectors produced by the unmodified reference (tests/golden/*.npz), and
+  * the CPU oracle (oracle/ofri_oracle.py, itself bit-exact against those vectors) on seeded inputs.
+
+Tolerances (north_star): one-off stages bit-exact; flows max|dU|, |dV| <= 1e-4 px; EPE-RMSE difference <= 1e-6 px.
+The fused (temporally blocked) kernels must be BIT-IDENTICAL to the one-sweep-per-launch kernels."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import ofri_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_FLOW = 1e-4
+TOL_EPE = 1e-6
+
+
+@pytest.fixture(scope="module")
+def ofri():
+    import opticalflow_ri_b200 as o
+    return o
+
+
+@pytest.fixture(scope="module")
+def h(ofri):
+    hd = ofri.Handle(0)          # raises (no CPU fallback) if the CUDA library / GPU is missing
+    yield hd
+    hd.close()
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if not np.array_equal(a, b):
+        d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+        raise AssertionError("not bit-exact: max|d| = %g at %s (%d of %d differ)" %
+                             (d.max(), np.unravel_index(np.argmax(d), d.shape), np.count_nonzero(a != b), a.size))
+
+
+def close(a, b, tol):
+    d = np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)))
+    assert d <= tol, "max|d| = %g > %g" % (d, tol)
+
+
+def rand_img(rng, H, W):
+    img = rng.uniform(0, 12, (H, W))
+    n = max(4, H * W // 40)
+    img[rng.integers(0, H, n), rng.integers(0, W, n)] += rng.uniform(40, 240, n)
+    return np.clip(np.rint(img), 0, 255).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stages vs reference goldens (bit-exact)
+# ---------------------------------------------------------------------------------------------------------------
+GK = {"g34_3": (3.4, 3), "g048_5": (0.48, 5), "g12_7": (1.2, 7), "g18_9": (1.8, 9)}
+
+
+@pytest.mark.parametrize("tag", sorted(GK))
+def test_gauss_golden(h, ofri, stages, tag):
+    same(h.gauss_px(stages["gauss_in"], ofri.gaussian_taps(*GK[tag])), stages["gauss_out_" + tag])
+
+
+def test_gauss_tiny_and_batched(h, ofri, stages):
+    same(h.gauss_px(stages["gauss_small_in"], ofri.gaussian_taps(0.48, 5)), stages["gauss_small_out"])
+    rng = np.random.default_rng(3)
+    imgs = np.stack([rand_img(rng, 67, 131) for _ in range(5)])
+    for sg, K in ((3.4, 3), (0.48, 5), (1.8, 9)):
+        out = h.gauss_px(imgs, ofri.gaussian_taps(sg, K))
+        for b in range(5):
+            same(out[b], O.gaussian_filter_px(imgs[b], sg, K))
+
+
+@pytest.mark.parametrize("tag", list("abcdq"))
+def test_resize_golden(h, stages, tag):
+    ref = stages["rs_out_" + tag]
+    same(h.resize_bicubic(stages["rs_in_" + tag], ref.shape[0], ref.shape[1]), ref)
+
+
+def test_resize_oracle_sizes(h):
+    rng = np.random.default_rng(4)
+    for H, W in ((512, 512), (301, 517), (96, 1024)):
+        img = rand_img(rng, H, W)
+        oh, ow = h.level_size(H, 0.5), h.level_size(W, 0.5)
+        assert (oh, ow) == (O.level_size(H, 0.5), O.level_size(W, 0.5))
+        same(h.resize_bicubic(img, oh, ow), O.imresize_bicubic(img, ow, oh))
+
+
+@pytest.mark.parametrize("tag", list("abcd"))
+@pytest.mark.parametrize("sc", [0, 1])
+def test_spline_warp_golden(h, stages, tag, sc):
+    s = "_s%d_" % sc
+    Ua, Va = stages["up_Ua_" + tag], stages["up_Va_" + tag]
+    n1, n2 = stages["up_n1_" + tag], stages["up_n2_" + tag]
+    H, W = n1.shape
+    hh, ww = Ua.shape
+    mx = np.float32(np.float32(W) / np.float32(ww)) if sc else 1.0
+    my = np.float32(np.float32(H) / np.float32(hh)) if sc else 1.0
+    us = h.spline_upsample(Ua, H, W, mx)
+    vs = h.spline_upsample(Va, H, W, my)
+    same(us, stages["up_Uacc" + s + tag])
+    same(vs, stages["up_Vacc" + s + tag])
+    w1, w2 = h.warp_pair(n1, n2, us, vs)
+    same(w1, stages["up_w1" + s + tag])
+    same(w2, stages["up_w2" + s + tag])
+
+
+def test_spline_oracle_big(h):
+    rng = np.random.default_rng(5)
+    a = rng.normal(0, 2, (3, 150, 259)).astype(np.float32)
+    out = h.spline_upsample(a, 301, 517, 2.0)
+    for b in range(3):
+        same(out[b], (O.spline_upsample(a[b], 301, 517) * np.float32(2.0)).astype(np.float32))
+
+
+def test_warp_coords_golden(h, stages):
+    same(h.warp_bilinear(stages["warp_img"], stages["warp_cy"], stages["warp_cx"]), stages["warp_out"])
+
+
+def test_spline_too_small_raises(h):
+    with pytest.raises(ValueError):
+        h.spline_upsample(np.zeros((3, 8), np.float32), 6, 16)
+
+
+def test_hs_derivatives_golden(h, stages):
+    fx, fy, ft = h.hs_derivatives(stages["hs_f1"], stages["hs_f2"])
+    same(fx, stages["hs_fx"])
+    same(fy, stages["hs_fy"])
+    same(ft, stages["hs_ft"])
+
+
+@pytest.mark.parametrize("tag,hp", [("h5", 5), ("h01", 0.1)])
+def test_ls_coefficients_golden(h, stages, tag, hp):
+    coef = h.ls_coefficients(stages["ls_g1"], stages["ls_g2"], hp)
+    ref = O.ls_coefficients(stages["ls_g1"], stages["ls_g2"], hp)
+    for i in range(8):
+        same(coef[i], ref[i])
+    same(coef[5], stages["ls_B11_" + tag])
+    same(coef[6], stages["ls_B12_" + tag])
+    same(coef[7], stages["ls_B22_" + tag])
+    if tag == "h5":
+        same(coef[3], stages["ls_Ixt"])
+        same(coef[4], stages["ls_Iyt"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Horn-Schunck iterations
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nit", [1, 2, 7, 50])
+@pytest.mark.parametrize("fuse", [0, 4])
+def test_hs_compute_golden(h, stages, nit, fuse):
+    h.set_option("hs_fuse", fuse)
+    try:
+        U, V, err = h.hs_compute(stages["hs_f1"], stages["hs_f2"], stages["hs_U0"], stages["hs_V0"], 3.0, nit)
+    finally:
+        h.set_option("hs_fuse", 4)
+    close(U, stages["hs_U_%d" % nit], 2e-6)
+    close(V, stages["hs_V_%d" % nit], 2e-6)
+    assert err == pytest.approx(float(stages["hs_err_%d" % nit]), rel=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(45, 58), (301, 517), (512, 512), (2, 2), (9, 1030)])
+def test_hs_fused_bit_identical_to_simple(h, shape):
+    """Temporal blocking must not change a single bit: every (T, tile variant) against one-sweep-per-launch."""
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    H, W = shape
+    B = 3
+    fx = rng.normal(0, 8, (B, H, W)).astype(np.float32)
+    fy = rng.normal(0, 8, (B, H, W)).astype(np.float32)
+    ft = rng.normal(0, 8, (B, H, W)).astype(np.float32)
+    U0 = rng.normal(0, 1, (B, H, W)).astype(np.float32)
+    V0 = rng.normal(0, 1, (B, H, W)).astype(np.float32)
+    nit = 13
+    try:
+        h.set_option("hs_fuse", 0)
+        Ur, Vr = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
+        for T in (1, 2, 3, 4, 5, 6, 8):
+            for variant in range(6):
+                h.set_option("hs_fuse", T)
+                h.set_option("hs_variant", variant)
+                U, V = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
+                try:
+                    same(U, Ur)
+                    same(V, Vr)
+                except AssertionError as e:
+                    raise AssertionError("T=%d variant=%d shape=%s: %s" % (T, variant, shape, e))
+    finally:
+        h.set_option("hs_fuse", 4)
+        h.set_option("hs_variant", 0)
+
+
+def test_hs_simple_vs_oracle(h):
+    rng = np.random.default_rng(11)
+    f1 = O.gaussian_filter_px(rand_img(rng, 120, 97), 3.4, 3)
+    f2 = O.gaussian_filter_px(rand_img(rng, 120, 97), 3.4, 3)
+    Uo, Vo, eo = O.hs_compute(f1, f2, 21.0, 40, np.zeros_like(f1), np.zeros_like(f1))
+    U, V, err = h.hs_compute(f1, f2, None, None, 21.0, 40)
+    close(U, Uo, 2e-6)
+    close(V, Vo, 2e-6)
+    assert err == pytest.approx(eo, rel=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Liu-Shen
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,hp", [("h5", 5), ("h01", 0.1)])
+@pytest.mark.parametrize("fuse", [0, 1, 2, 3, 4])
+def test_ls_compute_golden(h, stages, tag, hp, fuse):
+    h.set_option("ls_fuse", fuse)
+    try:
+        U, V, err, it = h.ls_compute(stages["ls_g1"], stages["ls_g2"], stages["ls_Uin"], stages["ls_Vin"], hp)
+    finally:
+        h.set_option("ls_fuse", 2)
+    assert it == 60
+    close(U, stages["ls_U_" + tag], 1e-6)
+    close(V, stages["ls_V_" + tag], 1e-6)
+    assert err == pytest.approx(float(stages["ls_err_" + tag]), rel=1e-4)
+
+
+def test_ls_first_sweep_golden(h, stages):
+    U, V, err, it = h.ls_compute(stages["ls_g1"], stages["ls_g2"], stages["ls_Uin"], stages["ls_Vin"], 5, maxiter=1)
+    assert it == 1
+    close(V, stages["ls_u1_h5"], 2e-7)     # inside the solver u is the ROW component = our V
+    close(U, stages["ls_v1_h5"], 2e-7)
+    assert err == pytest.approx(float(stages["ls_err0_h5"]), rel=1e-5)
+
+
+@pytest.mark.parametrize("fuse", [0, 1, 2, 3, 4])
+def test_ls_early_exit_identical_frames(h, stages, fuse):
+    """total_error == 0 after the first sweep -> the reference stops after ONE sweep (LS:141)."""
+    h.set_option("ls_fuse", fuse)
+    try:
+        U, V, err, it = h.ls_compute(stages["ls_g1"], stages["ls_g1"], None, None, 5)
+    finally:
+        h.set_option("ls_fuse", 2)
+    assert it == int(stages["ls_same_niter"]) == 1 and err == 0.0
+    same(U, stages["ls_same_U"])
+    same(V, stages["ls_same_V"])
+
+
+@pytest.mark.parametrize("shape", [(40, 52), (151, 259), (256, 256), (2, 3)])
+def test_ls_fused_bit_identical_and_midblock_stop(h, shape):
+    """Fused blocks vs single sweeps, including tolerances that trip in the MIDDLE of a fused block (replay path)."""
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    H, W = shape
+    B = 3
+    g1 = np.stack([O.gaussian_filter_px(rand_img(rng, H, W), 0.48, 5) if min(H, W) >= 2 else rand_img(rng, H, W)
+                   for _ in range(B)])
+    g2 = np.stack([O.gaussian_filter_px(rand_img(rng, H, W), 0.48, 5) if min(H, W) >= 2 else rand_img(rng, H, W)
+                   for _ in range(B)])
+    U0 = rng.normal(0, 0.3, (B, H, W)).astype(np.float32)
+    V0 = rng.normal(0, 0.3, (B, H, W)).astype(np.float32)
+    try:
+        for maxiter, tol in ((60, 1e-8), (17, 1e-8), (60, 2e-4), (60, 5e-5), (60, 1e-3)):
+            h.set_option("ls_fuse", 0)
+            Ur, Vr, er, itr = h.ls_compute(g1, g2, U0, V0, 5, maxiter=maxiter, tol=tol)
+            for T in (1, 2, 3, 4):
+                h.set_option("ls_fuse", T)
+                U, V, e, it = h.ls_compute(g1, g2, U0, V0, 5, maxiter=maxiter, tol=tol)
+                assert list(it) == list(itr), (T, maxiter, tol, list(it), list(itr))
+                try:
+                    same(U, Ur)
+                    same(V, Vr)
+                except AssertionError as ex:
+                    raise AssertionError("T=%d maxiter=%d tol=%g its=%s: %s" % (T, maxiter, tol, list(itr), ex))
+                np.testing.assert_allclose(e, er, rtol=1e-5)
+    finally:
+        h.set_option("ls_fuse", 2)
+
+
+def test_ls_stop_rule_vs_oracle(h):
+    rng = np.random.default_rng(21)
+    g1 = O.gaussian_filter_px(rand_img(rng, 64, 80), 0.48, 5)
+    g2 = O.gaussian_filter_px(rand_img(rng, 64, 80), 0.48, 5)
+    for tol in (1e-8, 1e-4, 3e-5):
+        Uo, Vo, eo, ko = O.ls_compute(g1, g2, 5, np.zeros_like(g1), np.zeros_like(g1), 60, tol)
+        U, V, err, it = h.ls_compute(g1, g2, None, None, 5, maxiter=60, tol=tol)
+        assert it == ko, (tol, it, ko)
+        close(U, Uo, 1e-6)
+        close(V, Vo, 1e-6)
+        assert err == pytest.approx(eo, rel=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole driver vs reference goldens
+# ---------------------------------------------------------------------------------------------------------------
+def flow(h, ofri, im1, im2, FILTER, main, L=1, K=1, FILTER_OPT=None, opt=None, **kw):
+    p = ofri.make_params(main, opt, filter_sigma=FILTER, filter_opt_sigma=FILTER_OPT, pyramid_levels=L, k_levels=K, **kw)
+    return h.pyramidal_flow(im1, im2, p)
+
+
+HS_DEF = dict(warping=True, bilinear=True, final_scaling=True)     # HS adapter defaults (HornSchunck.py:45-50)
+
+
+def test_driver_bom_rows(h, ofri, configs_small):
+    s = configs_small
+    for name, fs, L, use_ls in (("HS_Fs0_0", 0.0, 1, False), ("HS_Fs3_4", 3.4, 1, False),
+                                ("HS_Fs3_4_PyrLvls2", 3.4, 2, False), ("LiuSE_HS_Fs3_4_PyrLvls2", 3.4, 2, True)):
+        if use_ls:
+            U, V = flow(h, ofri, s["crop0"], s["crop1"], fs, ofri.ls_algo(0.1), L)
+        else:
+            U, V = flow(h, ofri, s["crop0"], s["crop1"], fs, ofri.hs_algo([1.0] * L, 100), L, **HS_DEF)
+        close(U, s["bom_%s_U" % name], TOL_FLOW)
+        close(V, s["bom_%s_V" % name], TOL_FLOW)
+
+
+def test_driver_variants(h, ofri, configs_small):
+    s = configs_small
+    c0, c1 = s["crop0"], s["crop1"]
+    cases = {
+        "odd_c3": lambda: flow(h, ofri, s["odd0"], s["odd1"], 3.4, ofri.hs_algo([45, 21], 200), 2, 1, 0.48,
+                               ofri.ls_algo(5), **HS_DEF),
+        "l3": lambda: flow(h, ofri, c0, c1, 3.4, ofri.hs_algo([45, 30, 21], 150), 3, 1, 0.48, ofri.ls_algo(5), **HS_DEF),
+        "k2": lambda: flow(h, ofri, c0, c1, 3.4, ofri.hs_algo([45, 45, 21, 21], 100), 2, 2, 0.48, ofri.ls_algo(5),
+                           **HS_DEF),
+        "k2f08": lambda: flow(h, ofri, c0, c1, 0.8, ofri.hs_algo([45, 45, 21, 21], 100), 2, 2, **HS_DEF),
+        "nowarp": lambda: flow(h, ofri, c0, c1, 3.4, ofri.hs_algo([45, 21], 100), 2, 1, warping=False,
+                               intermediate_scaling=True, final_scaling=True),
+        "nowarp_k2": lambda: flow(h, ofri, c0, c1, 3.4, ofri.hs_algo([45, 45, 21, 21], 60), 2, 2, warping=False,
+                                  final_scaling=True),
+        "lsmain_hsopt": lambda: flow(h, ofri, c0, c1, 3.4, ofri.ls_algo(5), 2, 1, 0.0, ofri.hs_algo([30, 30], 40)),
+    }
+    bad = []
+    for name, fn in cases.items():
+        U, V = fn()
+        du = np.max(np.abs(U - s[name + "_U"]))
+        dv = np.max(np.abs(V - s[name + "_V"]))
+        if not (du <= TOL_FLOW and dv <= TOL_FLOW):
+            bad.append((name, float(du), float(dv)))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3"])
+def test_driver_baseline_configs_bundled(h, ofri, configs_bundled, bundled_pair, cfg):
+    """BASELINE.json configs 1-3 on the bundled Poiseuille pair: flow within 1e-4 px of the reference and EPE-RMSE
+    (against the analytic Poiseuille profile) within 1e-6 px of the reference's."""
+    I0, I1 = bundled_pair
+    if cfg == "c1":
+        U, V = flow(h, ofri, I0, I1, 3.4, ofri.hs_algo([21], 600), 1, **HS_DEF)
+    elif cfg == "c2":
+        U, V = flow(h, ofri, I0, I1, 3.4, ofri.hs_algo([45, 21], 600), 2, **HS_DEF)
+    else:
+        U, V = flow(h, ofri, I0, I1, 3.4, ofri.hs_algo([45, 21], 600), 2, 1, 0.48, ofri.ls_algo(5), **HS_DEF)
+    Ur, Vr = configs_bundled[cfg + "_U"], configs_bundled[cfg + "_V"]
+    du, dv = np.max(np.abs(U - Ur)), np.max(np.abs(V - Vr))
+    Ut, Vt = O.poiseuille_truth(512, 512)
+    de = abs(O.epe_rmse(U, V, Ut, Vt) - O.epe_rmse(Ur, Vr, Ut, Vt))
+    print("\n%s: max|dU| %.3g max|dV| %.3g |dEPE-RMSE| %.3g" % (cfg, du, dv, de))
+    assert du <= TOL_FLOW and dv <= TOL_FLOW, (du, dv)
+    assert de <= TOL_EPE, de
+
+
+def test_errors_reported(h, ofri, configs_small):
+    s = configs_small
+    p = ofri.make_params(ofri.hs_algo([45, 21], 50), ofri.ls_algo(5), filter_sigma=3.4, filter_opt_sigma=0.48,
+                         pyramid_levels=2, **HS_DEF)
+    U, V, err = h.pyramidal_flow(s["crop0"], s["crop1"], p, want_errors=True)
+    assert err.shape == (2, 2) and np.all(np.isfinite(err)) and np.all(err > 0)
+    tr = []
+    O.pyramidal_flow(s["crop0"], s["crop1"], 3.4, O.HSParams([21, 45], 50), 2, 1, 0.48, O.LSParams(5), trace=tr)
+    for i in range(2):
+        assert err[i, 0] == pytest.approx(tr[i]["err_main"], rel=1e-3)
+        assert err[i, 1] == pytest.approx(tr[i]["err_opt"], rel=1e-3)
+
+
+def test_batch_equals_single_and_chunking(h, ofri, configs_small):
+    s = configs_small
+    a = np.stack([s["crop0"], s["crop1"], s["crop0"][::-1].copy(), s["crop1"][:, ::-1].copy(), s["crop0"]])
+    b = np.stack([s["crop1"], s["crop0"], s["crop1"][::-1].copy(), s["crop0"][:, ::-1].copy(), s["crop0"]])
+    mk = lambda: ofri.make_params(ofri.hs_algo([45, 21], 60), ofri.ls_algo(5), filter_sigma=3.4, filter_opt_sigma=0.48,
+                                  pyramid_levels=2, **HS_DEF)
+    U, V = h.pyramidal_flow(a, b, mk())
+    for i in range(5):
+        Ui, Vi = h.pyramidal_flow(a[i], b[i], mk())
+        same(U[i], Ui)
+        same(V[i], Vi)
+    try:
+        h.set_option("chunk_pairs", 2)          # 3 chunks through the double-buffered staging path
+        U2, V2 = h.pyramidal_flow(a, b, mk())
+    finally:
+        h.set_option("chunk_pairs", 0)
+    same(U2, U)
+    same(V2, V)
+    assert np.all(U[4] == 0) and np.all(V[4] == 0)      # identical frames -> zero flow
+
+
+def test_error_codes(h, ofri):
+    z = np.zeros((16, 16), np.float32)
+    with pytest.raises(IndexError):
+        h.pyramidal_flow(z, z, ofri.make_params(ofri.hs_algo([21], 5), pyramid_levels=2, **HS_DEF))
+    with pytest.raises(ValueError):       # 16 -> 2 px at level 1 of 4: too small for the cubic spline
+        h.pyramidal_flow(z, z, ofri.make_params(ofri.hs_algo([1, 1, 1, 1], 5), pyramid_levels=4, **HS_DEF))
+    with pytest.raises(NotImplementedError):
+        h.pyramidal_flow(z, z, ofri.make_params(ofri.ls_algo(5), pyramid_levels=2, bilinear=False))
+
+
+def test_synthetic_piv_vs_oracle_and_truth(h, ofri):
+    """Seeded synthetic PIV pair with known Poiseuille truth (the bench workload's generator), odd size."""
+    I0, I1 = O.synthetic_piv_pair(300, 420, seed=7)
+    Uo, Vo = O.pyramidal_flow(I0, I1, 3.4, O.HSParams([21, 45], 150), 2, 1, 0.48, O.LSParams(5))
+    U, V = flow(h, ofri, I0, I1, 3.4, ofri.hs_algo([45, 21], 150), 2, 1, 0.48, ofri.ls_algo(5), **HS_DEF)
+    close(U, Uo, TOL_FLOW)
+    close(V, Vo, TOL_FLOW)
+    Ut, Vt = O.poiseuille_truth(300, 420)
+    assert abs(O.epe_rmse(U, V, Ut, Vt) - O.epe_rmse(Uo, Vo, Ut, Vt)) <= TOL_EPE
+    assert O.epe_rmse(U, V, Ut, Vt) < 0.6
+
+
+def test_full_size_properties_1024(h, ofri):
+    """BASELINE config 4's frame size (1024 x 1024), too slow for the oracle at full iteration count: use
+    size-independent properties instead -- batch/chunk invariance, the x-mirror symmetry of the whole pipeline's
+    index logic is NOT exact (asymmetric Gaussian padding), so check: (a) identical pairs give identical flows,
+    (b) the flow of a pure Poiseuille pair recovers the profile, (c) fused == unfused bit-for-bit end to end."""
+    pairs = [O.synthetic_piv_pair(1024, 1024, seed=s) for s in (0, 1)]
+    a = np.stack([pairs[0][0], pairs[1][0], pairs[0][0]])
+    b = np.stack([pairs[0][1], pairs[1][1], pairs[0][1]])
+    mk = lambda: ofri.make_params(ofri.hs_algo([45, 21], 600), ofri.ls_algo(5), filter_sigma=3.4, filter_opt_sigma=0.48,
+                                  pyramid_levels=2, **HS_DEF)
+    U, V = h.pyramidal_flow(a, b, mk())
+    same(U[0], U[2])
+    same(V[0], V[2])
+    Ut, Vt = O.poiseuille_truth(1024, 1024)
+    for i in range(2):
+        assert O.epe_rmse(U[i], V[i], Ut, Vt) < 0.1
+    try:
+        h.set_option("hs_fuse", 0)
+        h.set_option("ls_fuse", 0)
+        U0, V0 = h.pyramidal_flow(a[:1], b[:1], mk())
+    finally:
+        h.set_option("hs_fuse", 4)
+        h.set_option("ls_fuse", 2)
+    same(U0[0], U[0])
+    same(V0[0], V[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# drop-in modules: the reference's example / benchmark call shapes, unchanged
+# ---------------------------------------------------------------------------------------------------------------
+def test_dropin_example3_and_wrapper(ofri, configs_bundled, bundled_pair, configs_small):
+    sys.path.insert(0, ofri.SRC_DIR)
+    try:
+        from GenericPyramidalOpticalFlow import genericPyramidalOpticalFlow
+        from GenericPyramidalOpticalFlowWrapper import GenericPyramidalOpticalFlowWrapper
+        from HornSchunck import HSOpticalFlowAlgoAdapter
+        from PhysicsBasedOpticalFlowLiuShen import LiuShenOpticalFlowAlgoAdapter
+        import gaussian_filter as GF
+    finally:
+        sys.path.remove(ofri.SRC_DIR)
+    Iold, Inew = bundled_pair
+    # examples/LiuSE_PyHSchunck_Fs3_4_PyrLvls2.py:133-139, verbatim call shape
+    alphas = [21, 45]
+    hsAdapter = HSOpticalFlowAlgoAdapter(alphas, 600)
+    lsAdapter = LiuShenOpticalFlowAlgoAdapter(5)
+    [U, V] = genericPyramidalOpticalFlow(Iold, Inew, 3.4, hsAdapter, 2, 1, 0.48, lsAdapter)
+    assert alphas == [] and U.dtype == np.float32 and U.shape == (512, 512)
+    close(U, configs_bundled["c3_U"], TOL_FLOW)
+    close(V, configs_bundled["c3_V"], TOL_FLOW)
+    with pytest.raises(IndexError):           # second call on the same adapter: alphas exhausted
+        genericPyramidalOpticalFlow(Iold, Inew, 3.4, hsAdapter, 2, 1, 0.48, lsAdapter)
+    # examples/PyHSchunck_Fs3_4.py:138 passes lsAdapter=None positionally into the FILTER_OPT slot
+    [U, V] = genericPyramidalOpticalFlow(Iold, Inew, 3.4, HSOpticalFlowAlgoAdapter([21], 600), 1, 1, None)
+    close(U, configs_bundled["c1_U"], TOL_FLOW)
+    # benchmark_of_methods.py:156-174
+    s = configs_small
+    w = GenericPyramidalOpticalFlowWrapper(LiuShenOpticalFlowAlgoAdapter(0.1), filter_sigma=3.4, pyr_levels=2)
+    U, V = w.calculateFlow(s["crop0"], s["crop1"])
+    close(U, s["bom_LiuSE_HS_Fs3_4_PyrLvls2_U"], TOL_FLOW)
+    close(V, s["bom_LiuSE_HS_Fs3_4_PyrLvls2_V"], TOL_FLOW)
+    w = GenericPyramidalOpticalFlowWrapper(HSOpticalFlowAlgoAdapter([1.0, 1.0], 100), filter_sigma=3.4, pyr_levels=2)
+    Ub, Vb = w.calculateFlowBatch(np.stack([s["crop0"]] * 2), np.stack([s["crop1"]] * 2))
+    close(Ub[1], s["bom_HS_Fs3_4_PyrLvls2_U"], TOL_FLOW)
+    # adapters stand-alone (the plugin protocol) and the in-place Gaussian
+    hs = HSOpticalFlowAlgoAdapter([3.0], 7)
+    st = np.load(os.path.join(os.path.dirname(__file__), "golden", "stages.npz"))
+    U, V, err = hs.compute(st["hs_f1"], st["hs_f2"], st["hs_U0"], st["hs_V0"])
+    close(U, st["hs_U_7"], 2e-6)
+    img = st["gauss_in"].copy()
+    out = GF.gaussian_filterPx(img, 3.4, 3)
+    assert out is img
+    same(img, st["gauss_out_g34_3"])
+
+
+def test_dropin_foreign_adapter_generic_path(ofri, configs_small):
+    """A third-party duck-typed adapter (here: the ORACLE's HS wrapped as a foreign plugin) drives the generic path:
+    GPU stages + adapter.compute on numpy arrays."""
+    sys.path.insert(0, ofri.SRC_DIR)
+    try:
+        from GenericPyramidalOpticalFlow import genericPyramidalOpticalFlow
+    finally:
+        sys.path.remove(ofri.SRC_DIR)
+
+    class Foreign(object):
+        def __init__(self):
+            self.alphas = [1.0, 1.0]
+
+        def compute(self, im1, im2, U, V):
+            return O.hs_compute(im1, im2, self.alphas.pop(), 100, U, V)
+
+        def getAlgoName(self):
+            return "foreign HS"
+
+        def hasGenericPyramidalDefaults(self):
+            return True
+
+        def getGenericPyramidalDefaults(self):
+            return {"warping": True, "biLinear": True, "scaling": True}
+
+    s = configs_small
+    U, V = genericPyramidalOpticalFlow(s["crop0"], s["crop1"], 3.4, Foreign(), 2, 1)
+    same(U, s["bom_HS_Fs3_4_PyrLvls2_U"])      # GPU stages are bit-exact and the oracle HS is bit-exact
+    same(V, s["bom_HS_Fs3_4_PyrLvls2_V"])
