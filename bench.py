@@ -207,7 +207,11 @@ def run_ours(args):
                               filter_sigma=FILTER, filter_opt_sigma=FILTER_OPT, pyramid_levels=LEVELS, warping=True,
                               bilinear=True, final_scaling=True)
     a_np, b_np = make_inputs(P)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the library launches on it and torch.cuda.Event times it.  (torch's default
+    # stream has handle 0, which ofri_set_stream treats as "use the handle's own stream".)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     h.set_stream(stream.cuda_stream)
     d_a = torch.from_numpy(a_np).cuda()
     d_b = torch.from_numpy(b_np).cuda()

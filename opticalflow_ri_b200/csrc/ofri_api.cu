@@ -45,6 +45,7 @@ struct ofri_ctx {
   LaunchCounter lc;
   // options
   int hs_fuse = 4, hs_variant = 0, ls_fuse = 2, chunk_pairs = 0, timing = 0;
+  int hs_precise = 1;   // 0 = fast f32/FMA everywhere, 1 = reference arithmetic on the coarse pyramid levels, 2 = everywhere
   // timings of the last call
   std::vector<StageTime> times;
   std::vector<std::pair<std::string, float>> times_ms;
@@ -333,7 +334,7 @@ GaussTaps make_taps(const float* k, int n) {
 // one adapter compute() on level planes.  U/V state lives in ws.U[cur] / ws.V[cur]; returns the new cur.
 // uv_zero: the initial guess is identically zero (lets HS skip the copy of U0 for its error norm).
 int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws, const Img& im1, const Img& im2,
-                int Hl, int Wl, int cur, bool uv_zero, float* d_err, int err_stride) {
+                int Hl, int Wl, int cur, bool uv_zero, bool coarse_level, float* d_err, int err_stride) {
   cudaStream_t s = h->stream;
   Img U[2] = {view(ws.U[0], Hl, Wl), view(ws.U[1], Hl, Wl)};
   Img V[2] = {view(ws.V[0], Hl, Wl), view(ws.V[1], Hl, Wl)};
@@ -353,8 +354,11 @@ int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws
     int res;
     {
       Timed t(h, "hs_iterate");
+      // rounding differences made on a coarse level are amplified by the warp + solve of the finer levels (up to
+      // x50 for weakly regularised problems), so the coarse levels default to the reference's exact arithmetic
+      const bool precise = h->hs_precise >= 2 || (h->hs_precise == 1 && coarse_level);
       res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], a.hs_niter,
-                              h->hs_fuse, h->hs_variant, s, h->lc);
+                              h->hs_fuse, h->hs_variant, precise, s, h->lc);
     }
     cur = res ? (cur ^ 1) : cur;
     if (d_err) {
@@ -512,10 +516,10 @@ int run_pyramid(ofri_handle h, const Img& im1, const Img& im2, const ofri_params
         }
       }
       float* e_main = d_err ? d_err + 2 * call_index : nullptr;
-      cur = run_adapter(h, p->main_algo, call_index, ws, work1, work2, Hl, Wl, cur, uv_zero, e_main, err_stride);
+      cur = run_adapter(h, p->main_algo, call_index, ws, work1, work2, Hl, Wl, cur, uv_zero, !last, e_main, err_stride);
       if (has_opt) {
         float* e_opt = d_err ? d_err + 2 * call_index + 1 : nullptr;
-        cur = run_adapter(h, p->opt_algo, call_index, ws, o1, o2, Hl, Wl, cur, false, e_opt, err_stride);
+        cur = run_adapter(h, p->opt_algo, call_index, ws, o1, o2, Hl, Wl, cur, false, !last, e_opt, err_stride);
       }
       Ucur = view(ws.U[cur], Hl, Wl);
       Vcur = view(ws.V[cur], Hl, Wl);
@@ -706,6 +710,7 @@ static int* option_slot(ofri_handle h, const char* key) {
   if (!key) return nullptr;
   if (!strcmp(key, "hs_fuse")) return &h->hs_fuse;
   if (!strcmp(key, "hs_variant")) return &h->hs_variant;
+  if (!strcmp(key, "hs_precise")) return &h->hs_precise;
   if (!strcmp(key, "ls_fuse")) return &h->ls_fuse;
   if (!strcmp(key, "chunk_pairs")) return &h->chunk_pairs;
   if (!strcmp(key, "timing")) return &h->timing;
@@ -851,8 +856,8 @@ int ofri_hs_compute(ofri_handle h, const float* im1, const float* im2, const flo
       return rc;
   }
   launch_hs_derivs(i1, i2, fx, fy, ft, h->stream, h->lc);
-  int res = launch_hs_iterate(U[0], V[0], U[1], V[1], fx, fy, ft, alpha, niter, h->hs_fuse, h->hs_variant, h->stream,
-                              h->lc);
+  int res = launch_hs_iterate(U[0], V[0], U[1], V[1], fx, fy, ft, alpha, niter, h->hs_fuse, h->hs_variant,
+                              h->hs_precise >= 2, h->stream, h->lc);
   Img nu, nv;
   launch_hs_error(U[res], V[res], zero0 ? nu : U0, zero0 ? nv : V0, acc, d_err, 1, h->stream, h->lc);
   if ((rc = download(h, u_out, U[res])) || (rc = download(h, v_out, V[res]))) return rc;
@@ -1033,8 +1038,8 @@ int ofri_hs_iterate(ofri_handle h, const float* u0, const float* v0, const float
   if ((rc = upload(h, dx, fx)) || (rc = upload(h, dy, fy)) || (rc = upload(h, dt, ft)) || (rc = upload(h, U[0], u0)) ||
       (rc = upload(h, V[0], v0)))
     return rc;
-  int res = launch_hs_iterate(U[0], V[0], U[1], V[1], dx, dy, dt, alpha, niter, h->hs_fuse, h->hs_variant, h->stream,
-                              h->lc);
+  int res = launch_hs_iterate(U[0], V[0], U[1], V[1], dx, dy, dt, alpha, niter, h->hs_fuse, h->hs_variant,
+                              h->hs_precise >= 2, h->stream, h->lc);
   if ((rc = download(h, u_out, U[res])) || (rc = download(h, v_out, V[res]))) return rc;
   return finish(h);
 }

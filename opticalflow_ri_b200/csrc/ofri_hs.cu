@@ -5,13 +5,9 @@
 //   uAvg = K (*) U, vAvg = K (*) V (3x3 weighted average, 'mirror' boundary), der = (fx uAvg + fy vAvg + ft) /
 //   (alpha^2 + fx^2 + fy^2), U = uAvg - fx der, V = vAvg - fy der, for exactly Niter sweeps.
 //
-// Fused kernel (hs_fused_kernel<T,...>): one launch advances T sweeps.  A CTA stages an SH x SW tile of U, V, fx,
-// fy, ft (halo T rows / HX >= T columns, HX a multiple of 4 so every row segment is 16-byte aligned) into shared
-// memory with 16-byte cp.async (zero-fill outside the image), computes 1/(alpha^2+fx^2+fy^2) once, then runs T
-// sweeps ping-ponging between two shared U/V buffers; after sweep s only cells at distance > s from the tile
-// border are valid, and the cells at distance >= T are written back with float4 stores.  The 'mirror' rule is
-// re-applied at every sweep for cells on the image border.  Algorithmic HBM traffic: 28 B per pixel per launch
-// (read U, V, fx, fy, ft; write U, V), i.e. 28/T B per pixel-sweep.
+// Fused kernel (hs_fused_kernel<T,...>, see the comment above it): one launch advances T sweeps on shared-memory
+// tiles of U, V with the per-pixel coefficients held in registers.  Algorithmic HBM traffic: 28 B per pixel per
+// launch (read U, V, fx, fy, ft; write U, V), i.e. 28/T B per pixel-sweep.
 #include "ofri_internal.h"
 #include "ofri_pixel.cuh"
 
@@ -44,9 +40,24 @@ void launch_hs_derivs(const Img& im1, const Img& im2, const Img& fx, const Img& 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// simple Jacobi sweep: one thread per pixel, one sweep per launch (cross-check for the fused kernel; also the
-// fallback for images narrower than 2 pixels)
+// coefficient preparation for the fast path: (fx, fy, ft) -> (a, b, c) in place, once per level
 // ---------------------------------------------------------------------------------------------------------------
+__global__ void hs_prepare_kernel(Img fx, Img fy, Img ft, float alpha2) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  if (x >= fx.W || y >= fx.H) return;
+  long o = (long)b * fx.stride + (long)y * fx.pitch + x;
+  float a, c, d;
+  hs_normalise(fx.p[o], fy.p[o], ft.p[o], alpha2, &a, &c, &d);
+  fx.p[o] = a;
+  fy.p[o] = c;
+  ft.p[o] = d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// simple Jacobi sweep: one thread per pixel, one sweep per launch (cross-check for the fused kernel; also the
+// fallback for images narrower than 2 pixels).  Fast path: planes hold the prepared (a, b, c); precise: raw.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool PRECISE>
 __global__ void hs_sweep_simple_kernel(Img ui, Img vi, Img uo, Img vo, Img fx, Img fy, Img ft, float alpha2) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
   const int W = ui.W, H = ui.H;
@@ -55,250 +66,362 @@ __global__ void hs_sweep_simple_kernel(Img ui, Img vi, Img uo, Img vo, Img fx, I
   const float* V = vi.p + (long)b * vi.stride;
   int xl = mirror1(x - 1, W), xr = mirror1(x + 1, W), yu = mirror1(y - 1, H), yd = mirror1(y + 1, H);
   long ru = (long)yu * ui.pitch, rm = (long)y * ui.pitch, rd = (long)yd * ui.pitch;
-  float ua = hs_avg_cols(fadd(U[ru + xl], U[rd + xl]), fadd(U[ru + x], U[rd + x]), fadd(U[ru + xr], U[rd + xr]),
-                         U[rm + xl], U[rm + xr]);
-  ru = (long)yu * vi.pitch, rm = (long)y * vi.pitch, rd = (long)yd * vi.pitch;
-  float va = hs_avg_cols(fadd(V[ru + xl], V[rd + xl]), fadd(V[ru + x], V[rd + x]), fadd(V[ru + xr], V[rd + xr]),
-                         V[rm + xl], V[rm + xr]);
+  long su = (long)yu * vi.pitch, sm = (long)y * vi.pitch, sd = (long)yd * vi.pitch;
   float dx = fx.p[(long)b * fx.stride + (long)y * fx.pitch + x];
   float dy = fy.p[(long)b * fy.stride + (long)y * fy.pitch + x];
   float dt = ft.p[(long)b * ft.stride + (long)y * ft.pitch + x];
-  float inv = hs_inv_den(dx, dy, alpha2);
   float un, vn;
-  hs_update(ua, va, dx, dy, dt, inv, &un, &vn);
+  if (!PRECISE) {
+    float ua = hs_avg_cols(fadd(U[ru + xl], U[rd + xl]), fadd(U[ru + x], U[rd + x]), fadd(U[ru + xr], U[rd + xr]),
+                           U[rm + xl], U[rm + xr]);
+    float va = hs_avg_cols(fadd(V[su + xl], V[sd + xl]), fadd(V[su + x], V[sd + x]), fadd(V[su + xr], V[sd + xr]),
+                           V[sm + xl], V[sm + xr]);
+    hs_update_n(ua, va, dx, dy, dt, &un, &vn);
+  } else {
+    float ua = hs_avg_cols_precise(dadd((double)U[ru + xl], (double)U[rd + xl]), dadd((double)U[ru + x], (double)U[rd + x]),
+                                   dadd((double)U[ru + xr], (double)U[rd + xr]), (double)U[rm + xl], (double)U[rm + xr]);
+    float va = hs_avg_cols_precise(dadd((double)V[su + xl], (double)V[sd + xl]), dadd((double)V[su + x], (double)V[sd + x]),
+                                   dadd((double)V[su + xr], (double)V[sd + xr]), (double)V[sm + xl], (double)V[sm + xr]);
+    float den = hs_den(dx, dy, alpha2);
+    hs_update_precise(ua, va, dx, dy, dt, den, rcp_rn(den), &un, &vn);
+  }
   uo.p[(long)b * uo.stride + (long)y * uo.pitch + x] = un;
   vo.p[(long)b * vo.stride + (long)y * vo.pitch + x] = vn;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// fused (temporally blocked) Jacobi kernel
+// fused (temporally blocked) Jacobi kernel, register-resident coefficients
 // ---------------------------------------------------------------------------------------------------------------
+// Geometry: a CTA owns a shared tile of SH x SW cells, SW = 4 NG, SH = R NRG + 2.  Thread (cg, rg) owns the 4 x R
+// cell strip at columns 4cg..4cg+3, rows 1 + rg R .. rg R + R -- the SAME cells in every sweep, so its coefficients
+// live in registers for the whole launch (loaded straight from HBM with LDG.128, never staged).  Only U and V go
+// through shared memory (two ping-pong buffers each, staged with 16-byte cp.async).  Per sweep a thread slides a
+// 3-row register window down its strip: one LDS.128 per plane per row; the two halo columns come from the
+// neighbouring lanes by warp shuffle.  With NG a multiple or divisor of 32 a warp never straddles a strip row, so
+// the lanes whose neighbour is in another warp are exactly the tile-border columns, whose cells are stale anyway:
+// no shared-memory fallback is needed.  After sweep s the cells at distance <= s from the tile border are stale;
+// the last sweep stores the TH x TW interior (distance >= T rows / HX columns) straight to HBM with float4 stores.
+// Tiles that touch the image border run the EDGE instantiation, which re-applies scipy's 'mirror' rule at every
+// sweep; interior tiles carry no boundary code at all.
+// PRECISE instantiation: stencil accumulated in float64 and rounded once, update with separately rounded f32
+// operations and a correctly rounded division -- the reference's arithmetic (scipy correlate + numba), bit for bit.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   int sz = valid ? 16 : 0;   // src-size 0 -> 16 bytes of zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-}
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-template <int T, int SW, int SH, int HX, int NRG>
-struct HsFusedCfg {
-  static constexpr int NG = SW / 4;           // float4 column groups per tile row
-  static constexpr int NT = NG * NRG;         // threads per CTA
-  static constexpr int TW = SW - 2 * HX;      // output tile
+template <int T, int R, int NRG, int NG>
+struct HsCfg {
+  static constexpr int HX = (T <= 4) ? 4 : 8;
+  static constexpr int SW = 4 * NG;
+  static constexpr int SH = R * NRG + 2;
+  static constexpr int NACT = NG * NRG;                 // threads that own a strip
+  static constexpr int NT = ((NACT + 31) / 32) * 32;    // whole warps (the halo exchange shuffles)
+  static constexpr bool ALIGNED = (NG % 32 == 0) || (32 % NG == 0);
+  static constexpr int TW = SW - 2 * HX;
   static constexpr int TH = SH - 2 * T;
-  static constexpr int PLANE = SH * SW;       // floats per shared plane
-  static constexpr int SMEM_BYTES = 8 * PLANE * 4;   // U[2], V[2], fx, fy, ft, inv
-  static_assert(SW % 4 == 0 && HX % 4 == 0 && HX >= T && TW > 0 && TH > 0, "bad tile");
+  static constexpr int PLANE = SH * SW;
+  static constexpr int SMEM_BYTES = 4 * PLANE * 4;      // U[2], V[2]
+  static_assert(TW > 0 && TH > 0 && HX >= T, "bad tile");
 };
 
-// load one shared row (6 columns sx-1 .. sx+4 of U and V) and apply the 'mirror' rule in x
-template <int SW>
-__device__ __forceinline__ void hs_load_row(const float* __restrict__ cu, const float* __restrict__ cv, int r, int sx,
-                                            int sxl, int sxr, bool left_edge, int right_j, float (&du)[6],
-                                            float (&dv)[6]) {
-  const float* pu = cu + r * SW;
-  const float* pv = cv + r * SW;
-  float4 q = *reinterpret_cast<const float4*>(pu + sx);
-  du[0] = pu[sxl]; du[1] = q.x; du[2] = q.y; du[3] = q.z; du[4] = q.w; du[5] = pu[sxr];
-  q = *reinterpret_cast<const float4*>(pv + sx);
-  dv[0] = pv[sxl]; dv[1] = q.x; dv[2] = q.y; dv[3] = q.z; dv[4] = q.w; dv[5] = pv[sxr];
-  // the left neighbour of global column 0 is column 1; the right neighbour of column W-1 is column W-2
-  if (left_edge) { du[0] = du[2]; dv[0] = dv[2]; }
-  if (right_j == 0) { du[2] = du[0]; dv[2] = dv[0]; }
-  if (right_j == 1) { du[3] = du[1]; dv[3] = dv[1]; }
-  if (right_j == 2) { du[4] = du[2]; dv[4] = dv[2]; }
-  if (right_j == 3) { du[5] = du[3]; dv[5] = dv[3]; }
-}
-// one row of 4 pixels: window rows (up, mid, down), coefficients from shared memory, result to the next buffer
-__device__ __forceinline__ void hs_row_compute(const float (&uu)[6], const float (&um)[6], const float (&ud)[6],
-                                               const float (&vu)[6], const float (&vm)[6], const float (&vd)[6],
-                                               const float* __restrict__ sFx, const float* __restrict__ sFy,
-                                               const float* __restrict__ sFt, const float* __restrict__ sIn, int so,
-                                               float* __restrict__ nu, float* __restrict__ nv) {
-  float vsu[6], vsv[6];
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    vsu[c] = fadd(uu[c], ud[c]);
-    vsv[c] = fadd(vu[c], vd[c]);
+struct HsEdge {      // per-thread boundary facts (EDGE tiles only)
+  bool left_edge;    // this strip starts at global column 0
+  int right_j;       // strip column j sitting on global column W-1 (else out of [0,4))
+  int top_j, bot_j;  // strip row j sitting on global row 0 / H-1 (else out of [0,R))
+};
+
+// one shared row of this thread's strip: columns sx-1 .. sx+4 of U and V
+template <int SW, bool EDGE, bool ALIGNED>
+__device__ __forceinline__ void hs_row6(const float* __restrict__ pu, const float* __restrict__ pv, int offl, int offr,
+                                        bool lane_lo, bool lane_hi, const HsEdge& eg, float (&du)[6], float (&dv)[6]) {
+  float4 qu = *reinterpret_cast<const float4*>(pu);
+  float4 qv = *reinterpret_cast<const float4*>(pv);
+  du[1] = qu.x; du[2] = qu.y; du[3] = qu.z; du[4] = qu.w;
+  dv[1] = qv.x; dv[2] = qv.y; dv[3] = qv.z; dv[4] = qv.w;
+  du[0] = __shfl_up_sync(0xffffffffu, qu.w, 1);
+  du[5] = __shfl_down_sync(0xffffffffu, qu.x, 1);
+  dv[0] = __shfl_up_sync(0xffffffffu, qv.w, 1);
+  dv[5] = __shfl_down_sync(0xffffffffu, qv.x, 1);
+  if (!ALIGNED) {   // lanes 0 / 31 may have their neighbour in another warp: fetch it from shared memory
+    float ul = pu[offl], ur = pu[offr], vl = pv[offl], vr = pv[offr];
+    du[0] = lane_lo ? ul : du[0];
+    du[5] = lane_hi ? ur : du[5];
+    dv[0] = lane_lo ? vl : dv[0];
+    dv[5] = lane_hi ? vr : dv[5];
   }
-  float4 qfx = *reinterpret_cast<const float4*>(sFx + so);
-  float4 qfy = *reinterpret_cast<const float4*>(sFy + so);
-  float4 qft = *reinterpret_cast<const float4*>(sFt + so);
-  float4 qin = *reinterpret_cast<const float4*>(sIn + so);
-  const float afx[4] = {qfx.x, qfx.y, qfx.z, qfx.w};
-  const float afy[4] = {qfy.x, qfy.y, qfy.z, qfy.w};
-  const float aft[4] = {qft.x, qft.y, qft.z, qft.w};
-  const float ain[4] = {qin.x, qin.y, qin.z, qin.w};
-  float ou[4], ov[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float ua = hs_avg_cols(vsu[j], vsu[j + 1], vsu[j + 2], um[j], um[j + 2]);
-    float va = hs_avg_cols(vsv[j], vsv[j + 1], vsv[j + 2], vm[j], vm[j + 2]);
-    hs_update(ua, va, afx[j], afy[j], aft[j], ain[j], &ou[j], &ov[j]);
+  if (EDGE) {   // 'mirror' in x: left neighbour of column 0 is column 1, right neighbour of column W-1 is column W-2
+    if (eg.left_edge) { du[0] = du[2]; dv[0] = dv[2]; }
+    if (eg.right_j == 0) { du[2] = du[0]; dv[2] = dv[0]; }
+    if (eg.right_j == 1) { du[3] = du[1]; dv[3] = dv[1]; }
+    if (eg.right_j == 2) { du[4] = du[2]; dv[4] = dv[2]; }
+    if (eg.right_j == 3) { du[5] = du[3]; dv[5] = dv[3]; }
   }
-  *reinterpret_cast<float4*>(nu + so) = make_float4(ou[0], ou[1], ou[2], ou[3]);
-  *reinterpret_cast<float4*>(nv + so) = make_float4(ov[0], ov[1], ov[2], ov[3]);
 }
 
-template <int T, int SW, int SH, int HX, int NRG>
-__global__ void __launch_bounds__(HsFusedCfg<T, SW, SH, HX, NRG>::NT)
-hs_fused_kernel(Img ui, Img vi, Img uo, Img vo, Img fx, Img fy, Img ft, float alpha2) {
-  using C = HsFusedCfg<T, SW, SH, HX, NRG>;
-  extern __shared__ __align__(16) float smem[];
-  // planes: U[0], U[1], V[0], V[1], fx, fy, ft, inv
-  float* sFx = smem + 4 * C::PLANE;
-  float* sFy = smem + 5 * C::PLANE;
-  float* sFt = smem + 6 * C::PLANE;
-  float* sIn = smem + 7 * C::PLANE;
+// coefficient registers of one strip row: fast path (a, b, c); precise (fx, fy, ft, den, 1/den)
+template <bool PRECISE>
+struct HsCoef {
+  float c0[4], c1[4], c2[4], c3[PRECISE ? 4 : 1], c4[PRECISE ? 4 : 1];
+};
 
+template <bool PRECISE>
+__device__ __forceinline__ void hs_row_update(const float (&uu)[6], const float (&um)[6], const float (&ud)[6],
+                                              const float (&vu)[6], const float (&vm)[6], const float (&vd)[6],
+                                              const HsCoef<PRECISE>& k, float (&ou)[4], float (&ov)[4]) {
+  if constexpr (!PRECISE) {
+    float vsu[6], vsv[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      vsu[c] = fadd(uu[c], ud[c]);
+      vsv[c] = fadd(vu[c], vd[c]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float ua = hs_avg_cols(vsu[j], vsu[j + 1], vsu[j + 2], um[j], um[j + 2]);
+      float va = hs_avg_cols(vsv[j], vsv[j + 1], vsv[j + 2], vm[j], vm[j + 2]);
+      hs_update_n(ua, va, k.c0[j], k.c1[j], k.c2[j], &ou[j], &ov[j]);
+    }
+  } else {
+    double vsu[6], vsv[6], mu[6], mv[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      vsu[c] = dadd((double)uu[c], (double)ud[c]);
+      vsv[c] = dadd((double)vu[c], (double)vd[c]);
+      mu[c] = (double)um[c];
+      mv[c] = (double)vm[c];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float ua = hs_avg_cols_precise(vsu[j], vsu[j + 1], vsu[j + 2], mu[j], mu[j + 2]);
+      float va = hs_avg_cols_precise(vsv[j], vsv[j + 1], vsv[j + 2], mv[j], mv[j + 2]);
+      hs_update_precise(ua, va, k.c0[j], k.c1[j], k.c2[j], k.c3[j], k.c4[j], &ou[j], &ov[j]);
+    }
+  }
+}
+
+// one sweep over this thread's strip.  LAST: results go to HBM (interior cells only) instead of the next buffer.
+template <int T, int R, int NRG, int NG, bool EDGE, bool PRECISE, bool LAST>
+__device__ __forceinline__ void hs_sweep(const float* __restrict__ cu, const float* __restrict__ cv,
+                                         float* __restrict__ nu, float* __restrict__ nv, int r0, int sx, int offl,
+                                         int offr, bool lane_lo, bool lane_hi, const HsEdge& eg, bool active,
+                                         const HsCoef<PRECISE> (&k)[R], float* __restrict__ gU, float* __restrict__ gV,
+                                         long gpitch, int gy0, int gx, int H, int W) {
+  using C = HsCfg<T, R, NRG, NG>;
+  constexpr int SW = C::SW;
+  float wu[3][6], wv[3][6];
+  const float* pu = cu + (r0 - 1) * SW + sx;
+  const float* pv = cv + (r0 - 1) * SW + sx;
+  hs_row6<SW, EDGE, C::ALIGNED>(pu, pv, offl, offr, lane_lo, lane_hi, eg, wu[0], wv[0]);
+  hs_row6<SW, EDGE, C::ALIGNED>(pu + SW, pv + SW, offl, offr, lane_lo, lane_hi, eg, wu[1], wv[1]);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int A = j % 3, B = (j + 1) % 3, Cc = (j + 2) % 3;     // window roles rotate statically
+    hs_row6<SW, EDGE, C::ALIGNED>(pu + (j + 2) * SW, pv + (j + 2) * SW, offl, offr, lane_lo, lane_hi, eg, wu[Cc],
+                                  wv[Cc]);
+    float ou[4], ov[4];
+    if (EDGE && j == eg.top_j)        // global row 0: the row above is row 1 (= down)
+      hs_row_update<PRECISE>(wu[Cc], wu[B], wu[Cc], wv[Cc], wv[B], wv[Cc], k[j], ou, ov);
+    else if (EDGE && j == eg.bot_j)   // global row H-1: the row below is row H-2 (= up)
+      hs_row_update<PRECISE>(wu[A], wu[B], wu[A], wv[A], wv[B], wv[A], k[j], ou, ov);
+    else
+      hs_row_update<PRECISE>(wu[A], wu[B], wu[Cc], wv[A], wv[B], wv[Cc], k[j], ou, ov);
+    if (!LAST) {
+      if (active) {
+        const int so = (r0 + j) * SW + sx;
+        *reinterpret_cast<float4*>(nu + so) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+        *reinterpret_cast<float4*>(nv + so) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      }
+    } else {
+      const int sy = r0 + j, gy = gy0 + j;
+      const bool in_rows = (sy >= T) && (sy < C::SH - T) && (gy < H);
+      const bool in_cols = (sx >= C::HX) && (sx < SW - C::HX) && (gx < W);
+      if (active && in_rows && in_cols) {   // the last group of a row may spill into the pitch padding
+        const long go = (long)gy * gpitch + gx;
+        *reinterpret_cast<float4*>(gU + go) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+        *reinterpret_cast<float4*>(gV + go) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      }
+    }
+  }
+}
+
+template <int T, int R, int NRG, int NG, bool EDGE, bool PRECISE>
+__device__ __forceinline__ void hs_fused_body(const Img& ui, const Img& vi, const Img& uo, const Img& vo,
+                                              const Img& fx, const Img& fy, const Img& ft, float alpha2, float* smem) {
+  using C = HsCfg<T, R, NRG, NG>;
+  constexpr int SW = C::SW, SH = C::SH, HX = C::HX;
   const int b = blockIdx.z;
   const int W = ui.W, H = ui.H;
   const int x0 = blockIdx.x * C::TW - HX;      // global x of shared column 0 (multiple of 4)
   const int y0 = blockIdx.y * C::TH - T;       // global y of shared row 0
   const int tid = threadIdx.x;
+  const int lane = tid & 31;
 
-  // ---- stage the tile (16-byte cp.async, zero fill outside the allocation) --------------------------------------
+  // ---- stage U, V (cp.async, zero fill outside the allocation) -------------------------------------------------
   {
     const float* gU = ui.p + (long)b * ui.stride;
     const float* gV = vi.p + (long)b * vi.stride;
-    const float* gFx = fx.p + (long)b * fx.stride;
-    const float* gFy = fy.p + (long)b * fy.stride;
-    const float* gFt = ft.p + (long)b * ft.stride;
-    for (int i = tid; i < SH * C::NG; i += C::NT) {
-      int sy = i / C::NG, sg = i - sy * C::NG;
+    for (int i = tid; i < SH * NG; i += C::NT) {
+      int sy = i / NG, sg = i - sy * NG;
       int gy = y0 + sy, gx = x0 + 4 * sg;
       bool ok = (gy >= 0) && (gy < H) && (gx >= 0) && (gx < (int)ui.pitch);
-      int cy = ok ? gy : 0, cx = ok ? gx : 0;
+      long go = ok ? (long)gy * ui.pitch + gx : 0;
       int so = sy * SW + 4 * sg;
-      cp_async16(smem + so, gU + (long)cy * ui.pitch + cx, ok);
-      cp_async16(smem + 2 * C::PLANE + so, gV + (long)cy * vi.pitch + cx, ok);
-      cp_async16(sFx + so, gFx + (long)cy * fx.pitch + cx, ok);
-      cp_async16(sFy + so, gFy + (long)cy * fy.pitch + cx, ok);
-      cp_async16(sFt + so, gFt + (long)cy * ft.pitch + cx, ok);
+      cp_async16(smem + so, gU + go, ok);
+      cp_async16(smem + 2 * C::PLANE + so, gV + go, ok);
     }
-    cp_async_commit_wait_all();
-    __syncthreads();
-    for (int i = tid; i < SH * C::NG; i += C::NT) {
-      float4 a = reinterpret_cast<const float4*>(sFx)[i];
-      float4 c = reinterpret_cast<const float4*>(sFy)[i];
-      float4 r;
-      r.x = hs_inv_den(a.x, c.x, alpha2);
-      r.y = hs_inv_den(a.y, c.y, alpha2);
-      r.z = hs_inv_den(a.z, c.z, alpha2);
-      r.w = hs_inv_den(a.w, c.w, alpha2);
-      reinterpret_cast<float4*>(sIn)[i] = r;
-    }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
+  // ---- this thread's strip and its coefficients (HBM -> registers) ---------------------------------------------
+  const bool active = (C::NT == C::NACT) || (tid < C::NACT);
+  const int t2 = active ? tid : C::NACT - 1;     // surplus threads shadow the last strip (they never store)
+  const int cg = t2 % NG, rg = t2 / NG;
+  const int sx = 4 * cg;
+  const int r0 = 1 + rg * R;
+  const int gx = x0 + sx;
+  HsCoef<PRECISE> k[R];
+  {
+    const float* g0 = fx.p + (long)b * fx.stride;
+    const float* g1 = fy.p + (long)b * fy.stride;
+    const float* g2 = ft.p + (long)b * ft.stride;
+    const bool okx = (gx >= 0) && (gx < (int)fx.pitch);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      int gy = y0 + r0 + j;
+      bool ok = okx && (gy >= 0) && (gy < H);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a, d = a;
+      if (!EDGE || ok) {      // interior tiles lie entirely inside the image
+        long go = (long)gy * fx.pitch + gx;
+        a = ldg_f4(g0 + go);
+        c = ldg_f4(g1 + go);
+        d = ldg_f4(g2 + go);
+      }
+      k[j].c0[0] = a.x; k[j].c0[1] = a.y; k[j].c0[2] = a.z; k[j].c0[3] = a.w;
+      k[j].c1[0] = c.x; k[j].c1[1] = c.y; k[j].c1[2] = c.z; k[j].c1[3] = c.w;
+      k[j].c2[0] = d.x; k[j].c2[1] = d.y; k[j].c2[2] = d.z; k[j].c2[3] = d.w;
+    }
+    if constexpr (PRECISE) {
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          k[j].c3[q] = hs_den(k[j].c0[q], k[j].c1[q], alpha2);
+          k[j].c4[q] = rcp_rn(k[j].c3[q]);
+        }
+    }
+  }
+  const int offl = sx > 0 ? -1 : 0;                 // clamped halo offsets (only used when !ALIGNED)
+  const int offr = sx + 4 < SW ? 4 : 3;
+  const bool lane_lo = (lane == 0), lane_hi = (lane == 31);
+  HsEdge eg;
+  eg.left_edge = EDGE && (gx == 0);
+  eg.right_j = EDGE ? (W - 1) - gx : -1;
+  eg.top_j = EDGE ? -(y0 + r0) : -1000;
+  eg.bot_j = EDGE ? (H - 1) - (y0 + r0) : -1000;
+  float* gU = uo.p + (long)b * uo.stride;
+  float* gV = vo.p + (long)b * vo.stride;
 
-  // ---- T sweeps --------------------------------------------------------------------------------------------------
-  const int cg = tid % C::NG, rg = tid / C::NG;
-  const int sx = 4 * cg;                          // first shared column of this thread's 4-pixel group
-  const int gx = x0 + sx;                         // its global x
-  const int sxl = sx > 0 ? sx - 1 : 0;            // clamped halo columns (garbage only reaches invalid cells)
-  const int sxr = sx + 4 < SW ? sx + 4 : SW - 1;
-  const bool left_edge = (gx == 0);
-  const int right_j = (W - 1) - gx;               // pixel j in [0,4) sitting on global column W-1 (else out of range)
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
 
+  // ---- T sweeps: T-1 through shared memory, the last one straight to HBM ----------------------------------------
 #pragma unroll 1
-  for (int s = 0; s < T; ++s) {
+  for (int s = 0; s < T - 1; ++s) {
     const float* cu = smem + (s & 1) * C::PLANE;
     const float* cv = smem + (2 + (s & 1)) * C::PLANE;
     float* nu = smem + ((s + 1) & 1) * C::PLANE;
     float* nv = smem + (2 + ((s + 1) & 1)) * C::PLANE;
-    // rows that can still become valid after this sweep: [s+1, SH-s-1), clipped to the image
-    int lo = s + 1, hi = SH - s - 1;
-    if (y0 + lo < 0) lo = -y0;
-    if (y0 + hi > H) hi = H - y0;
-    const int R = (hi - lo + NRG - 1) / NRG;
-    const int r0 = lo + rg * R;
-    const int r1 = (r0 + R < hi) ? r0 + R : hi;
-    if (r0 < r1) {
-      float wu[3][6], wv[3][6];   // sliding window of three shared rows x columns (sx-1 .. sx+4)
-      // prime: row r0-1 (or its mirror, row -1 -> row 1) and row r0
-      hs_load_row<SW>(cu, cv, (y0 + r0 == 0) ? r0 + 1 : r0 - 1, sx, sxl, sxr, left_edge, right_j, wu[0], wv[0]);
-      hs_load_row<SW>(cu, cv, r0, sx, sxl, sxr, left_edge, right_j, wu[1], wv[1]);
-      int r = r0;
-      // rotate the window roles instead of moving registers (mirror: row H -> row H-2)
-#define OFRI_HS_STEP(A, B, Cc)                                                                                       \
-  hs_load_row<SW>(cu, cv, (y0 + r == H - 1) ? r - 1 : r + 1, sx, sxl, sxr, left_edge, right_j, wu[Cc], wv[Cc]);      \
-  hs_row_compute(wu[A], wu[B], wu[Cc], wv[A], wv[B], wv[Cc], sFx, sFy, sFt, sIn, r * SW + sx, nu, nv);               \
-  if (++r >= r1) break;
-      while (true) {
-        OFRI_HS_STEP(0, 1, 2)
-        OFRI_HS_STEP(1, 2, 0)
-        OFRI_HS_STEP(2, 0, 1)
-      }
-#undef OFRI_HS_STEP
-    }
+    hs_sweep<T, R, NRG, NG, EDGE, PRECISE, false>(cu, cv, nu, nv, r0, sx, offl, offr, lane_lo, lane_hi, eg, active, k,
+                                                  gU, gV, uo.pitch, y0 + r0, gx, H, W);
     __syncthreads();
   }
-
-  // ---- write back the valid interior (distance >= T from the tile border) ----------------------------------------
   {
-    const float* fu = smem + (T & 1) * C::PLANE;
-    const float* fv = smem + (2 + (T & 1)) * C::PLANE;
-    float* gU = uo.p + (long)b * uo.stride;
-    float* gV = vo.p + (long)b * vo.stride;
-    constexpr int OG = C::TW / 4;
-    for (int i = tid; i < C::TH * OG; i += C::NT) {
-      int ty = i / OG, tg = i - ty * OG;
-      int sy = ty + T, sxx = HX + 4 * tg;
-      int gy = y0 + sy, gxx = x0 + sxx;
-      if (gy < H && gxx < W) {      // the last group of a row may spill into the pitch padding (garbage there is fine)
-        float4 a = *reinterpret_cast<const float4*>(fu + sy * SW + sxx);
-        float4 c = *reinterpret_cast<const float4*>(fv + sy * SW + sxx);
-        *reinterpret_cast<float4*>(gU + (long)gy * uo.pitch + gxx) = a;
-        *reinterpret_cast<float4*>(gV + (long)gy * vo.pitch + gxx) = c;
-      }
-    }
+    constexpr int s = T - 1;
+    const float* cu = smem + (s & 1) * C::PLANE;
+    const float* cv = smem + (2 + (s & 1)) * C::PLANE;
+    hs_sweep<T, R, NRG, NG, EDGE, PRECISE, true>(cu, cv, nullptr, nullptr, r0, sx, offl, offr, lane_lo, lane_hi, eg,
+                                                 active, k, gU, gV, uo.pitch, y0 + r0, gx, H, W);
   }
 }
 
-template <int T, int SW, int SH, int HX, int NRG>
+template <int T, int R, int NRG, int NG, bool PRECISE, int MINB>
+__global__ void __launch_bounds__(HsCfg<T, R, NRG, NG>::NT, MINB)
+hs_fused_kernel(Img ui, Img vi, Img uo, Img vo, Img fx, Img fy, Img ft, float alpha2) {
+  using C = HsCfg<T, R, NRG, NG>;
+  extern __shared__ __align__(16) float smem[];
+  const int x0 = blockIdx.x * C::TW - C::HX, y0 = blockIdx.y * C::TH - T;
+  const bool edge = (x0 < 0) || (x0 + C::SW > ui.W) || (y0 < 0) || (y0 + C::SH > ui.H);   // CTA-uniform
+  if (edge)
+    hs_fused_body<T, R, NRG, NG, true, PRECISE>(ui, vi, uo, vo, fx, fy, ft, alpha2, smem);
+  else
+    hs_fused_body<T, R, NRG, NG, false, PRECISE>(ui, vi, uo, vo, fx, fy, ft, alpha2, smem);
+}
+
+template <int T, int R, int NRG, int NG, bool PRECISE, int MINB>
 static void launch_hs_fused_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
                                 const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
-  using C = HsFusedCfg<T, SW, SH, HX, NRG>;
-  auto kern = hs_fused_kernel<T, SW, SH, HX, NRG>;
+  using C = HsCfg<T, R, NRG, NG>;
+  auto kern = hs_fused_kernel<T, R, NRG, NG, PRECISE, MINB>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   dim3 g((ui.W + C::TW - 1) / C::TW, (ui.H + C::TH - 1) / C::TH, ui.batch);
   kern<<<g, C::NT, C::SMEM_BYTES, s>>>(ui, vi, uo, vo, fx, fy, ft, alpha2);
 }
 
-// variant table: (SW, SH, NRG) choices per T.  variant 0 = default.
-template <int T>
+// tile variants (R rows per thread, NRG row groups, NG float4 column groups, min CTAs/SM for the register cap)
+template <int T, bool PRECISE>
 static void launch_hs_fused_T(int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
                               const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
   constexpr int HX = (T <= 4) ? 4 : 8;
-  switch (variant) {
-    default:
-    case 0: launch_hs_fused_cfg<T, 64 + 2 * HX, 32 + 2 * T, HX, 8>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    case 1: launch_hs_fused_cfg<T, 128 + 2 * HX, 16 + 2 * T, HX, 6>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    case 2: launch_hs_fused_cfg<T, 128 + 2 * HX, 32 + 2 * T, HX, 8>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    case 3: launch_hs_fused_cfg<T, 64 + 2 * HX, 16 + 2 * T, HX, 6>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    case 4: launch_hs_fused_cfg<T, 32 + 2 * HX, 32 + 2 * T, HX, 8>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    case 5: launch_hs_fused_cfg<T, 64 + 2 * HX, 32 + 2 * T, HX, 16>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+  constexpr int NG64 = (64 + 2 * HX) / 4;      // 64-wide output tile: 18 or 20 column groups (not warp aligned)
+  if constexpr (PRECISE) {
+    switch (variant) {
+      default:
+      case 0: launch_hs_fused_cfg<T, 4, 8, 32, true, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+      case 1: launch_hs_fused_cfg<T, 2, 16, 32, true, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+      case 2: launch_hs_fused_cfg<T, 4, 8, 16, true, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+    }
+    return;
+  } else {
+    switch (variant) {
+      default:
+      case 0: launch_hs_fused_cfg<T, 4, 8, 32, false, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+      case 1: launch_hs_fused_cfg<T, 4, 10, 32, false, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+      case 2: launch_hs_fused_cfg<T, 6, 6, 32, false, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+      case 3: launch_hs_fused_cfg<T, 3, 10, 32, false, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+      case 4: launch_hs_fused_cfg<T, 4, 8, 16, false, 4>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+      case 5: launch_hs_fused_cfg<T, 4, 10, NG64, false, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+      case 6: launch_hs_fused_cfg<T, 2, 16, 32, false, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+      case 7: launch_hs_fused_cfg<T, 8, 4, 32, false, 3>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+    }
   }
 }
 
-static void launch_hs_fused(int T, int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo,
-                            const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
+static void launch_hs_fused(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo,
+                            const Img& vo, const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
+#define OFRI_HS_T(TT)                                                                             \
+  case TT:                                                                                        \
+    if (precise) launch_hs_fused_T<TT, true>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s);     \
+    else launch_hs_fused_T<TT, false>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s);            \
+    break;
   switch (T) {
-    case 1: launch_hs_fused_T<1>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    case 2: launch_hs_fused_T<2>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    case 3: launch_hs_fused_T<3>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    case 4: launch_hs_fused_T<4>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    case 5: launch_hs_fused_T<5>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    case 6: launch_hs_fused_T<6>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    default: launch_hs_fused_T<8>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+    OFRI_HS_T(1)
+    OFRI_HS_T(2)
+    OFRI_HS_T(3)
+    OFRI_HS_T(4)
+    OFRI_HS_T(5)
+    OFRI_HS_T(6)
+    default:
+      if (precise) launch_hs_fused_T<8, true>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s);
+      else launch_hs_fused_T<8, false>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s);
+      break;
   }
+#undef OFRI_HS_T
 }
 
 int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb, const Img& fx, const Img& fy,
-                      const Img& ft, float alpha, int niter, int fuse, int variant, cudaStream_t s,
+                      const Img& ft, float alpha, int niter, int fuse, int variant, bool precise, cudaStream_t s,
                       LaunchCounter& lc) {
   const float alpha2 = alpha * alpha;   // f32 alpha**2 as in the numba signature (HornSchunck.py:52-55)
   int cur = 0;
@@ -309,18 +432,28 @@ int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb
   const bool can_fuse = fuse >= 1 && ua.W >= 2 && ua.H >= 2 && (ua.pitch % 4 == 0) && ua.pitch == va.pitch &&
                         ua.pitch == ub.pitch && ua.pitch == vb.pitch && ua.pitch == fx.pitch &&
                         ua.pitch == fy.pitch && ua.pitch == ft.pitch && ((uintptr_t)ua.p % 16 == 0) &&
-                        ((uintptr_t)ub.p % 16 == 0) && ((uintptr_t)fx.p % 16 == 0) && (ua.stride % 4 == 0);
+                        ((uintptr_t)va.p % 16 == 0) && ((uintptr_t)ub.p % 16 == 0) && ((uintptr_t)vb.p % 16 == 0) &&
+                        ((uintptr_t)fx.p % 16 == 0) && ((uintptr_t)fy.p % 16 == 0) && ((uintptr_t)ft.p % 16 == 0) &&
+                        (ua.stride % 4 == 0) && (fx.stride % 4 == 0);
+  if (niter > 0 && !precise) {   // fast path: (fx, fy, ft) -> normalised (a, b, c), in place
+    dim3 b(32, 8), g((fx.W + 31) / 32, (fx.H + 7) / 8, fx.batch);
+    hs_prepare_kernel<<<g, b, 0, s>>>(fx, fy, ft, alpha2);
+    lc.n += 1;
+  }
   int done = 0;
   while (done < niter) {
     int left = niter - done;
     if (fuse <= 0 || !can_fuse) {
       dim3 b(32, 8), g((ua.W + 31) / 32, (ua.H + 7) / 8, ua.batch);
-      hs_sweep_simple_kernel<<<g, b, 0, s>>>(*U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2);
+      if (precise)
+        hs_sweep_simple_kernel<true><<<g, b, 0, s>>>(*U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2);
+      else
+        hs_sweep_simple_kernel<false><<<g, b, 0, s>>>(*U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2);
       done += 1;
     } else {
       int T = left < fuse ? left : fuse;
       if (T == 7) T = 6;
-      launch_hs_fused(T, variant, *U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2, s);
+      launch_hs_fused(T, variant, precise, *U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2, s);
       done += T;
     }
     cur ^= 1;

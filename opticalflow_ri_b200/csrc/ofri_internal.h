@@ -67,9 +67,11 @@ void launch_fill(const Img& dst, float v, cudaStream_t s, LaunchCounter& lc);
 void launch_hs_derivs(const Img& im1, const Img& im2, const Img& fx, const Img& fy, const Img& ft, cudaStream_t s,
                       LaunchCounter& lc);
 // `niter` Jacobi sweeps.  u0/v0 -> result in ua/va or ub/vb (ping-pong); returns which (0 = a, 1 = b).
-// fuse = sweeps per launch (1 = simple per-pixel kernel; >= 2 = temporally blocked shared-memory kernel).
+// fuse = sweeps per launch (0 = simple per-pixel kernel; >= 1 = temporally blocked shared-memory kernel).
+// precise = reference arithmetic bit for bit (f64-accumulated stencil, IEEE division) instead of the f32/FMA fast path.
 int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb, const Img& fx, const Img& fy,
-                      const Img& ft, float alpha, int niter, int fuse, int variant, cudaStream_t s, LaunchCounter& lc);
+                      const Img& ft, float alpha, int niter, int fuse, int variant, bool precise, cudaStream_t s,
+                      LaunchCounter& lc);
 // err[b] = (sqrt(sum (u-u0)^2) + sqrt(sum (v-v0)^2)) / (H*W); u0.p == nullptr means u0 = v0 = 0.  acc: [batch][2] f64 scratch
 void launch_hs_error(const Img& u, const Img& v, const Img& u0, const Img& v0, double* acc, float* err, int err_stride,
                      cudaStream_t s, LaunchCounter& lc);

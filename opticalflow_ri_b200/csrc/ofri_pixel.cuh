@@ -176,6 +176,61 @@ OFRI_HD void hs_update(float ua, float va, float fx, float fy, float ft, float i
   *u = fmaf(-fx, der, ua);
   *v = fmaf(-fy, der, va);
 }
+// Fast path used by the kernels: NORMALISED coefficients a = fx n, b = fy n, c = ft n, n = 1/sqrt(alpha^2+fx^2+fy^2),
+// prepared once per level.  Then fx (fx ua + fy va + ft)/(alpha^2+fx^2+fy^2) = a (a ua + b va + c): three
+// coefficients per pixel instead of four, four FMAs per update, no division in the sweep.
+OFRI_HD float rsqrt_rn(float x) {
+#if defined(__CUDA_ARCH__)
+  return __frsqrt_rn(x);
+#else
+  return (float)(1.0 / sqrt((double)x));
+#endif
+}
+OFRI_HD void hs_normalise(float fx, float fy, float ft, float alpha2, float* a, float* b, float* c) {
+  float n = rsqrt_rn(fmaf(fy, fy, fmaf(fx, fx, alpha2)));
+  *a = fmul(fx, n);
+  *b = fmul(fy, n);
+  *c = fmul(ft, n);
+}
+OFRI_HD void hs_update_n(float ua, float va, float a, float b, float c, float* u, float* v) {
+  float g = fmaf(a, ua, fmaf(b, va, c));
+  *u = fmaf(-a, g, ua);
+  *v = fmaf(-b, g, va);
+}
+// "precise" formulation = the reference's arithmetic, operation by operation:
+//   stencil: scipy correlate accumulates the 8 products in float64 and rounds ONCE to float32.  The weights are
+//   w6 = f32(1/6) and w12 = f32(1/12) = w6/2, so the exact value is w6*E + w12*C with E, C the (exact in f64) sums of
+//   the edge / corner neighbours; evaluated here in f64 it differs from scipy's sequential f64 sum by ~1e-16
+//   relative, i.e. the float32 results agree except in ~1e-9 of the evaluations (double-rounding ties).
+//   update: numba evaluates every f32 operation separately rounded, with a true division (HornSchunck.py:55-58).
+OFRI_HD float hs_den(float fx, float fy, float alpha2) { return fadd(fadd(alpha2, fmul(fx, fx)), fmul(fy, fy)); }
+OFRI_HD float hs_avg_cols_precise(double vsl, double vsc, double vsr, double ml, double mr) {
+  double E = dadd(vsc, dadd(ml, mr));
+  double C = dadd(vsl, vsr);
+  return (float)dadd(dmul(E, (double)0.16666667f), dmul(C, (double)0.083333336f));
+}
+// RN(s / den) from rcp = RN(1/den): product, then two residual corrections (the sequence the hardware division
+// expands to, without its range checks: den >= alpha^2 is always a normal number here)
+OFRI_HD float div_rn_rcp(float s, float den, float rcp) {
+  float q = fmul(s, rcp);
+  float e = fmaf(-den, q, s);
+  q = fmaf(e, rcp, q);
+  e = fmaf(-den, q, s);
+  return fmaf(e, rcp, q);
+}
+OFRI_HD float rcp_rn(float x) {
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(x);
+#else
+  return fdiv(1.0f, x);
+#endif
+}
+OFRI_HD void hs_update_precise(float ua, float va, float fx, float fy, float ft, float den, float rcp, float* u,
+                               float* v) {
+  float der = div_rn_rcp(fadd(fadd(fmul(fx, ua), fmul(fy, va)), ft), den, rcp);
+  *u = fsub(ua, fmul(fx, der));
+  *v = fsub(va, fmul(fy, der));
+}
 
 // ---- Liu-Shen (PhysicsBasedOpticalFlowLiuShen.py:47-158) ------------------------------------------------------
 // coefficient planes of one pixel from the 3x3 neighbourhoods (clamp-to-edge applied by the caller) of the

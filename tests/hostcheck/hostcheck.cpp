@@ -105,6 +105,29 @@ void hc_hs_derivs(const float* A, const float* B, int H, int W, float* fx, float
                      fx + (size_t)y * W + x, fy + (size_t)y * W + x, ft + (size_t)y * W + x);
     }
 }
+void hc_hs_iterate_precise(const float* u0, const float* v0, const float* fx, const float* fy, const float* ft, int H,
+                           int W, float alpha, int niter, float* uo, float* vo) {
+  std::vector<float> U(u0, u0 + (size_t)H * W), V(v0, v0 + (size_t)H * W), Un((size_t)H * W), Vn((size_t)H * W);
+  const float a2 = alpha * alpha;
+  for (int it = 0; it < niter; ++it) {
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        int xl = mirror1(x - 1, W), xr = mirror1(x + 1, W), yu = mirror1(y - 1, H), yd = mirror1(y + 1, H);
+        size_t ru = (size_t)yu * W, rm = (size_t)y * W, rd = (size_t)yd * W;
+        float ua = hs_avg_cols_precise(dadd((double)U[ru + xl], (double)U[rd + xl]), dadd((double)U[ru + x], (double)U[rd + x]),
+                                       dadd((double)U[ru + xr], (double)U[rd + xr]), (double)U[rm + xl], (double)U[rm + xr]);
+        float va = hs_avg_cols_precise(dadd((double)V[ru + xl], (double)V[rd + xl]), dadd((double)V[ru + x], (double)V[rd + x]),
+                                       dadd((double)V[ru + xr], (double)V[rd + xr]), (double)V[rm + xl], (double)V[rm + xr]);
+        float dx = fx[rm + x], dy = fy[rm + x], dt = ft[rm + x];
+        float den = hs_den(dx, dy, a2);
+        hs_update_precise(ua, va, dx, dy, dt, den, rcp_rn(den), &Un[rm + x], &Vn[rm + x]);
+      }
+    U.swap(Un);
+    V.swap(Vn);
+  }
+  memcpy(uo, U.data(), sizeof(float) * H * W);
+  memcpy(vo, V.data(), sizeof(float) * H * W);
+}
 void hc_hs_iterate(const float* u0, const float* v0, const float* fx, const float* fy, const float* ft, int H, int W,
                    float alpha, int niter, float* uo, float* vo) {
   std::vector<float> U(u0, u0 + (size_t)H * W), V(v0, v0 + (size_t)H * W), Un((size_t)H * W), Vn((size_t)H * W);
@@ -119,7 +142,9 @@ void hc_hs_iterate(const float* u0, const float* v0, const float* fx, const floa
         float va = hs_avg_cols(fadd(V[ru + xl], V[rd + xl]), fadd(V[ru + x], V[rd + x]), fadd(V[ru + xr], V[rd + xr]),
                                V[rm + xl], V[rm + xr]);
         float dx = fx[rm + x], dy = fy[rm + x], dt = ft[rm + x];
-        hs_update(ua, va, dx, dy, dt, hs_inv_den(dx, dy, a2), &Un[rm + x], &Vn[rm + x]);
+        float ca, cb, cc;
+        hs_normalise(dx, dy, dt, a2, &ca, &cb, &cc);
+        hs_update_n(ua, va, ca, cb, cc, &Un[rm + x], &Vn[rm + x]);
       }
     U.swap(Un);
     V.swap(Vn);

@@ -155,12 +155,18 @@ def test_ls_coefficients_golden(h, stages, tag, hp):
 def test_hs_compute_golden(h, stages, nit, fuse):
     h.set_option("hs_fuse", fuse)
     try:
+        h.set_option("hs_precise", 0)      # fast f32/FMA formulation: within 2e-6 px
         U, V, err = h.hs_compute(stages["hs_f1"], stages["hs_f2"], stages["hs_U0"], stages["hs_V0"], 3.0, nit)
+        close(U, stages["hs_U_%d" % nit], 2e-6)
+        close(V, stages["hs_V_%d" % nit], 2e-6)
+        assert err == pytest.approx(float(stages["hs_err_%d" % nit]), rel=1e-4)
+        h.set_option("hs_precise", 2)      # reference arithmetic: bit-exact
+        U, V, err = h.hs_compute(stages["hs_f1"], stages["hs_f2"], stages["hs_U0"], stages["hs_V0"], 3.0, nit)
+        same(U, stages["hs_U_%d" % nit])
+        same(V, stages["hs_V_%d" % nit])
     finally:
         h.set_option("hs_fuse", 4)
-    close(U, stages["hs_U_%d" % nit], 2e-6)
-    close(V, stages["hs_V_%d" % nit], 2e-6)
-    assert err == pytest.approx(float(stages["hs_err_%d" % nit]), rel=1e-4)
+        h.set_option("hs_precise", 1)
 
 
 @pytest.mark.parametrize("shape", [(45, 58), (301, 517), (512, 512), (2, 2), (9, 1030)])
@@ -176,21 +182,24 @@ def test_hs_fused_bit_identical_to_simple(h, shape):
     V0 = rng.normal(0, 1, (B, H, W)).astype(np.float32)
     nit = 13
     try:
-        h.set_option("hs_fuse", 0)
-        Ur, Vr = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
-        for T in (1, 2, 3, 4, 5, 6, 8):
-            for variant in range(6):
-                h.set_option("hs_fuse", T)
-                h.set_option("hs_variant", variant)
-                U, V = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
-                try:
-                    same(U, Ur)
-                    same(V, Vr)
-                except AssertionError as e:
-                    raise AssertionError("T=%d variant=%d shape=%s: %s" % (T, variant, shape, e))
+        for precise in (0, 2):
+            h.set_option("hs_precise", precise)
+            h.set_option("hs_fuse", 0)
+            Ur, Vr = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
+            for T in (1, 2, 3, 4, 5, 6, 8):
+                for variant in (range(8) if precise == 0 else [0]):
+                    h.set_option("hs_fuse", T)
+                    h.set_option("hs_variant", variant)
+                    U, V = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
+                    try:
+                        same(U, Ur)
+                        same(V, Vr)
+                    except AssertionError as e:
+                        raise AssertionError("precise=%d T=%d variant=%d shape=%s: %s" % (precise, T, variant, shape, e))
     finally:
         h.set_option("hs_fuse", 4)
         h.set_option("hs_variant", 0)
+        h.set_option("hs_precise", 1)
 
 
 def test_hs_simple_vs_oracle(h):
@@ -198,10 +207,18 @@ def test_hs_simple_vs_oracle(h):
     f1 = O.gaussian_filter_px(rand_img(rng, 120, 97), 3.4, 3)
     f2 = O.gaussian_filter_px(rand_img(rng, 120, 97), 3.4, 3)
     Uo, Vo, eo = O.hs_compute(f1, f2, 21.0, 40, np.zeros_like(f1), np.zeros_like(f1))
-    U, V, err = h.hs_compute(f1, f2, None, None, 21.0, 40)
-    close(U, Uo, 2e-6)
-    close(V, Vo, 2e-6)
-    assert err == pytest.approx(eo, rel=1e-4)
+    try:
+        h.set_option("hs_precise", 0)
+        U, V, err = h.hs_compute(f1, f2, None, None, 21.0, 40)
+        close(U, Uo, 2e-6)
+        close(V, Vo, 2e-6)
+        assert err == pytest.approx(eo, rel=1e-4)
+        h.set_option("hs_precise", 2)
+        U, V, err = h.hs_compute(f1, f2, None, None, 21.0, 40)
+        same(U, Uo)
+        same(V, Vo)
+    finally:
+        h.set_option("hs_precise", 1)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -435,6 +452,13 @@ def test_full_size_properties_1024(h, ofri):
         h.set_option("ls_fuse", 2)
     same(U0[0], U[0])
     same(V0[0], V[0])
+    try:          # all-levels reference arithmetic vs the default (coarse levels only): final level differs by rounding only
+        h.set_option("hs_precise", 2)
+        U2, V2 = h.pyramidal_flow(a[:1], b[:1], mk())
+    finally:
+        h.set_option("hs_precise", 1)
+    close(U2[0], U[0], 2e-5)
+    close(V2[0], V[0], 2e-5)
 
 
 # ---------------------------------------------------------------------------------------------------------------

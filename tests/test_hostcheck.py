@@ -96,6 +96,23 @@ def test_hs(hc, stages):
                          nit, p(uo), p(vo))
         assert np.max(np.abs(uo - stages["hs_U_%d" % nit])) < 2e-6
         assert np.max(np.abs(vo - stages["hs_V_%d" % nit])) < 2e-6
+        # "precise" formulation (reference arithmetic): bit-exact
+        hc.hc_hs_iterate_precise(p(f32(stages["hs_U0"])), p(f32(stages["hs_V0"])), p(fx), p(fy), p(ft), H, W,
+                                 C.c_float(3.0), nit, p(uo), p(vo))
+        assert np.array_equal(uo, stages["hs_U_%d" % nit]) and np.array_equal(vo, stages["hs_V_%d" % nit])
+
+
+def test_hs_precise_bom_row_bit_exact(hc, configs_small):
+    """alpha = 1, 100 sweeps, no pre-filter (benchmark_of_methods.py row HS_Fs0_0): flows of +-26 px, bit for bit."""
+    s = configs_small
+    c0, c1 = f32(s["crop0"]), f32(s["crop1"])
+    H, W = c0.shape
+    fx, fy, ft = np.empty_like(c0), np.empty_like(c0), np.empty_like(c0)
+    hc.hc_hs_derivs(p(c0), p(c1), H, W, p(fx), p(fy), p(ft))
+    z = np.zeros_like(c0)
+    uo, vo = np.empty_like(c0), np.empty_like(c0)
+    hc.hc_hs_iterate_precise(p(z), p(z), p(fx), p(fy), p(ft), H, W, C.c_float(1.0), 100, p(uo), p(vo))
+    assert np.array_equal(uo, s["bom_HS_Fs0_0_U"]) and np.array_equal(vo, s["bom_HS_Fs0_0_V"])
 
 
 @pytest.mark.parametrize("tag,h", [("h5", 5), ("h01", 0.1)])

@@ -16,7 +16,9 @@ from opticalflow_ri_b200.synthetic import synthetic_piv_pair  # noqa: E402
 P = int(os.environ.get("SWEEP_PAIRS", "64"))
 H = W = int(os.environ.get("SWEEP_SIZE", "1024"))
 h = ofri.Handle(0)
-h.set_stream(torch.cuda.current_stream().cuda_stream)
+_stream = torch.cuda.Stream()
+torch.cuda.set_stream(_stream)
+h.set_stream(_stream.cuda_stream)
 base = [synthetic_piv_pair(H, W, s) for s in range(4)]
 a = torch.from_numpy(np.stack([base[i % 4][0] for i in range(P)])).cuda()
 b = torch.from_numpy(np.stack([base[i % 4][1] for i in range(P)])).cuda()
@@ -51,11 +53,17 @@ def run(tag):
     print(json.dumps(out), flush=True)
 
 
+h.set_option("hs_precise", int(os.environ.get("HS_PRECISE", "1")))
 which = os.environ.get("SWEEP", "hs,ls")
+if "one" in which:
+    h.set_option("hs_fuse", int(os.environ.get("HS_FUSE", "4")))
+    h.set_option("hs_variant", int(os.environ.get("HS_VARIANT", "0")))
+    h.set_option("ls_fuse", int(os.environ.get("LS_FUSE", "2")))
+    run({"hs_fuse": h.get_option("hs_fuse"), "hs_variant": h.get_option("hs_variant"), "ls_fuse": h.get_option("ls_fuse")})
 if "hs" in which:
     h.set_option("ls_fuse", 2)
-    for T in (0, 1, 2, 3, 4, 5, 6, 8):
-        for variant in (range(6) if T > 0 else [0]):
+    for T in [int(x) for x in os.environ.get("HS_TS", "0,1,2,3,4,6").split(",")]:
+        for variant in ([int(x) for x in os.environ.get("HS_VARIANTS", "0,1,2,3,4,5,6,7").split(",")] if T > 0 else [0]):
             h.set_option("hs_fuse", T)
             h.set_option("hs_variant", variant)
             run({"hs_fuse": T, "hs_variant": variant, "ls_fuse": 2})
