@@ -44,7 +44,7 @@ struct ofri_ctx {
   std::map<int, DevSplineSys> splines;
   LaunchCounter lc;
   // options
-  int hs_fuse = 4, hs_variant = 0, ls_fuse = 2, chunk_pairs = 0, timing = 0;
+  int hs_fuse = 4, hs_variant = 0, ls_fuse = 2, ls_variant = 0, chunk_pairs = 0, timing = 0;
   int hs_precise = 1;   // 0 = fast f32/FMA everywhere, 1 = reference arithmetic on the coarse pyramid levels, 2 = everywhere
   // timings of the last call
   std::vector<StageTime> times;
@@ -376,7 +376,8 @@ int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws
   }
   {
     Timed t(h, "ls_iterate");
-    launch_ls_solve(V[cur], U[cur], V[cur ^ 1], U[cur ^ 1], co, a.ls_h, a.ls_maxiter, a.ls_tol, h->ls_fuse, ws.ls_errs,
+    launch_ls_solve(V[cur], U[cur], V[cur ^ 1], U[cur ^ 1], co, a.ls_h, a.ls_maxiter, a.ls_tol, h->ls_fuse,
+                    h->ls_variant, ws.ls_errs,
                     ws.ls_state, V[cur], U[cur], d_err, err_stride, nullptr, s, h->lc);
   }
   return cur;
@@ -712,6 +713,7 @@ static int* option_slot(ofri_handle h, const char* key) {
   if (!strcmp(key, "hs_variant")) return &h->hs_variant;
   if (!strcmp(key, "hs_precise")) return &h->hs_precise;
   if (!strcmp(key, "ls_fuse")) return &h->ls_fuse;
+  if (!strcmp(key, "ls_variant")) return &h->ls_variant;
   if (!strcmp(key, "chunk_pairs")) return &h->chunk_pairs;
   if (!strcmp(key, "timing")) return &h->timing;
   return nullptr;
@@ -894,7 +896,8 @@ int ofri_ls_compute(ofri_handle h, const float* im1, const float* im2, const flo
     return rc;
   }
   launch_ls_coefficients(i1, i2, hpar, co, mx, h->stream, h->lc);
-  launch_ls_solve(V[0], U[0], V[1], U[1], co, hpar, maxiter, tol, h->ls_fuse, errs, state, V[0], U[0], d_err, 1, d_it,
+  launch_ls_solve(V[0], U[0], V[1], U[1], co, hpar, maxiter, tol, h->ls_fuse, h->ls_variant, errs, state, V[0], U[0],
+                  d_err, 1, d_it,
                   h->stream, h->lc);
   if ((rc = download(h, u_out, U[0])) || (rc = download(h, v_out, V[0]))) return rc;
   if (err) OFRI_CUDA(h, cudaMemcpyAsync(err, d_err, sizeof(float) * batch, cudaMemcpyDeviceToHost, h->stream));

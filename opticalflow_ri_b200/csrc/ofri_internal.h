@@ -85,8 +85,8 @@ void launch_ls_coefficients(const Img& im1, const Img& im2, float hpar, const Ls
 // (ROW component in ua!), (ub,vb) is the ping-pong partner; the final state is copied into (uo, vo).
 // errs: [batch][maxiter][2] f64 scratch; err_out[b*err_stride] = last total_error; iters_out[b] = sweeps run.
 void launch_ls_solve(const Img& ua, const Img& va, const Img& ub, const Img& vb, const LsPlanes& coef, float hpar,
-                     int maxiter, double tol, int fuse, double* errs, int* state, const Img& uo, const Img& vo,
-                     float* err_out, int err_stride, int* iters_out, cudaStream_t s, LaunchCounter& lc);
+                     int maxiter, double tol, int fuse, int variant, double* errs, int* state, const Img& uo,
+                     const Img& vo, float* err_out, int err_stride, int* iters_out, cudaStream_t s, LaunchCounter& lc);
 
 const char* kernel_build_info();
 

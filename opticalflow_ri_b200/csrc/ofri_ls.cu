@@ -198,200 +198,256 @@ ls_sweep_simple_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// fused (temporally blocked) sweep kernel: T sweeps per launch, tile staged in shared memory by cp.async
+// fused (temporally blocked) sweep kernel: T sweeps per launch
 // ---------------------------------------------------------------------------------------------------------------
+// Same geometry as the Horn-Schunck kernel (ofri_hs.cu): shared tile SH x SW, SW = 4 NG, SH = R NRG + 2; thread
+// (cg, rg) owns the 4 x R strip at columns 4cg.., rows 1 + rg R .., the same cells in every sweep; NG is 16 or 32 so
+// the halo columns come from the neighbouring lanes by shuffle.  Liu-Shen has 8 coefficient planes per pixel -- too
+// many for registers -- so they are staged in shared memory next to the two ping-pong buffers of u and v (12 planes,
+// 16-byte cp.async).  The residual of every sweep is accumulated in f32 per thread over the CTA's own output cells,
+// reduced in f64 (warp shuffle) and added to errs[pair][k] with one atomicAdd per CTA.  The last sweep stores its
+// interior results straight to HBM.  EDGE instantiation (tiles touching the image border): 'nearest' clamp for the
+// D / F / M stencils and zero padding for the 8-neighbour sum, re-applied every sweep.
 __device__ __forceinline__ void cp_async16_ls(void* smem_dst, const void* gsrc, bool valid) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   int sz = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
 
-template <int T, int SW, int SH, int HX, int NRG>
-struct LsFusedCfg {
-  static constexpr int NG = SW / 4;
-  // threads per CTA, rounded up to whole warps (the residual reduction shuffles); surplus threads own no rows
-  static constexpr int NT = ((NG * NRG + 31) / 32) * 32;
+template <int T, int R, int NRG, int NG>
+struct LsCfg {
+  static constexpr int HX = 4;
+  static constexpr int SW = 4 * NG;
+  static constexpr int SH = R * NRG + 2;
+  static constexpr int NT = NG * NRG;
   static constexpr int TW = SW - 2 * HX;
   static constexpr int TH = SH - 2 * T;
   static constexpr int PLANE = SH * SW;
   static constexpr int SMEM_BYTES = 12 * PLANE * 4;    // u[2], v[2], 8 coefficient planes
-  static_assert(SW % 4 == 0 && HX % 4 == 0 && HX >= T && TW > 0 && TH > 0 && NT <= 1024, "bad tile");
+  static_assert((NG == 16 || NG == 32) && NT % 32 == 0 && T <= HX && TW > 0 && TH > 0 && NT <= 1024, "bad tile");
 };
 
-// load one shared row: 6 columns (sx-1 .. sx+4), clamp-to-edge in x ('nearest')
-template <int SW>
-__device__ __forceinline__ void ls_load_row(const float* __restrict__ cu, const float* __restrict__ cv, int r, int sx,
-                                            int sxl, int sxr, bool left_edge, int right_j, float (&du)[6],
-                                            float (&dv)[6]) {
-  const float* pu = cu + r * SW;
-  const float* pv = cv + r * SW;
-  float4 q = *reinterpret_cast<const float4*>(pu + sx);
-  du[0] = pu[sxl]; du[1] = q.x; du[2] = q.y; du[3] = q.z; du[4] = q.w; du[5] = pu[sxr];
-  q = *reinterpret_cast<const float4*>(pv + sx);
-  dv[0] = pv[sxl]; dv[1] = q.x; dv[2] = q.y; dv[3] = q.z; dv[4] = q.w; dv[5] = pv[sxr];
-  // 'nearest': the left neighbour of column 0 is column 0; the right neighbour of column W-1 is column W-1
-  if (left_edge) { du[0] = du[1]; dv[0] = dv[1]; }
-  if (right_j == 0) { du[2] = du[1]; dv[2] = dv[1]; }
-  if (right_j == 1) { du[3] = du[2]; dv[3] = dv[2]; }
-  if (right_j == 2) { du[4] = du[3]; dv[4] = dv[3]; }
-  if (right_j == 3) { du[5] = du[4]; dv[5] = dv[4]; }
+struct LsEdge {
+  bool left_edge;
+  int right_j, top_j, bot_j;
+};
+
+// one shared row of this thread's strip: columns sx-1 .. sx+4 of u and v; EDGE: 'nearest' clamp in x
+template <bool EDGE>
+__device__ __forceinline__ void ls_row6(const float* __restrict__ pu, const float* __restrict__ pv, const LsEdge& eg,
+                                        float (&du)[6], float (&dv)[6]) {
+  float4 qu = *reinterpret_cast<const float4*>(pu);
+  float4 qv = *reinterpret_cast<const float4*>(pv);
+  du[1] = qu.x; du[2] = qu.y; du[3] = qu.z; du[4] = qu.w;
+  dv[1] = qv.x; dv[2] = qv.y; dv[3] = qv.z; dv[4] = qv.w;
+  du[0] = __shfl_up_sync(0xffffffffu, qu.w, 1);
+  du[5] = __shfl_down_sync(0xffffffffu, qu.x, 1);
+  dv[0] = __shfl_up_sync(0xffffffffu, qv.w, 1);
+  dv[5] = __shfl_down_sync(0xffffffffu, qv.x, 1);
+  if (EDGE) {   // the left neighbour of column 0 is column 0; the right neighbour of column W-1 is column W-1
+    if (eg.left_edge) { du[0] = du[1]; dv[0] = dv[1]; }
+    if (eg.right_j == 0) { du[2] = du[1]; dv[2] = dv[1]; }
+    if (eg.right_j == 1) { du[3] = du[2]; dv[3] = dv[2]; }
+    if (eg.right_j == 2) { du[4] = du[3]; dv[4] = dv[3]; }
+    if (eg.right_j == 3) { du[5] = du[4]; dv[5] = dv[4]; }
+  }
 }
 
-template <int T, int SW, int SH, int HX, int NRG>
-__global__ void __launch_bounds__(LsFusedCfg<T, SW, SH, HX, NRG>::NT)
-ls_fused_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, int k0, int maxiter, double tol,
-                double* errs) {
-  using C = LsFusedCfg<T, SW, SH, HX, NRG>;
-  extern __shared__ __align__(16) float smem[];
-  __shared__ double sh[64];
-  const int b = blockIdx.z;
-  const int W = u0.W, H = u0.H;
-  const double npix = (double)H * (double)W;
-  double* errs_pair = errs + (long)b * maxiter * 2;
-  if (k0 > 0 && ls_stopped_before(errs_pair, k0, tol, npix, T)) return;   // uniform per CTA
-  // launch index parity selects the ping-pong direction: launches alternate u0->u1, u1->u0
-  const bool odd = ((k0 / T) & 1) != 0;   // only used when every earlier launch fused exactly T sweeps
-  Img ui = odd ? u1 : u0, vi = odd ? v1 : v0, uo = odd ? u0 : u1, vo = odd ? v0 : v1;
+// 4 pixels of one strip row.  (uu, um, ud) = window rows above / at / below, already clamped in x (and in y by the
+// caller's choice of rows).  ztop / zbot: the row above / below lies outside the image (zero padding of H8).
+template <bool EDGE>
+__device__ __forceinline__ void ls_row_update(const float (&uu)[6], const float (&um)[6], const float (&ud)[6],
+                                              const float (&vu)[6], const float (&vm)[6], const float (&vd)[6],
+                                              const float* __restrict__ sC, int plane, int so, float hpar, bool ztop,
+                                              bool zbot, const LsEdge& eg, float (&ou)[4], float (&ov)[4]) {
+  float4 q0 = *reinterpret_cast<const float4*>(sC + 0 * plane + so);
+  float4 q1 = *reinterpret_cast<const float4*>(sC + 1 * plane + so);
+  float4 q2 = *reinterpret_cast<const float4*>(sC + 2 * plane + so);
+  float4 q3 = *reinterpret_cast<const float4*>(sC + 3 * plane + so);
+  float4 q4 = *reinterpret_cast<const float4*>(sC + 4 * plane + so);
+  float4 q5 = *reinterpret_cast<const float4*>(sC + 5 * plane + so);
+  float4 q6 = *reinterpret_cast<const float4*>(sC + 6 * plane + so);
+  float4 q7 = *reinterpret_cast<const float4*>(sC + 7 * plane + so);
+  const float c0[4] = {q0.x, q0.y, q0.z, q0.w}, c1[4] = {q1.x, q1.y, q1.z, q1.w};
+  const float c2[4] = {q2.x, q2.y, q2.z, q2.w}, c3[4] = {q3.x, q3.y, q3.z, q3.w};
+  const float c4[4] = {q4.x, q4.y, q4.z, q4.w}, c5[4] = {q5.x, q5.y, q5.z, q5.w};
+  const float c6[4] = {q6.x, q6.y, q6.z, q6.w}, c7[4] = {q7.x, q7.y, q7.z, q7.w};
+  // zero-padded column sums for H8 (interior: identical to the clamped values)
+  float zsu[6], zsv[6], zmu[6], zmv[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    float a = uu[c], d = ud[c], e = vu[c], f = vd[c];
+    if (EDGE) {
+      if (ztop) { a = 0.0f; e = 0.0f; }
+      if (zbot) { d = 0.0f; f = 0.0f; }
+    }
+    zsu[c] = fadd(a, d);
+    zsv[c] = fadd(e, f);
+    zmu[c] = um[c];
+    zmv[c] = vm[c];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float vlu = zsu[j], vru = zsu[j + 2], wu_ = zmu[j], eu_ = zmu[j + 2];
+    float vlv = zsv[j], vrv = zsv[j + 2], wv_ = zmv[j], ev_ = zmv[j + 2];
+    if (EDGE) {
+      if (eg.left_edge && j == 0) { vlu = 0.0f; vlv = 0.0f; wu_ = 0.0f; wv_ = 0.0f; }
+      if (eg.right_j == j) { vru = 0.0f; vrv = 0.0f; eu_ = 0.0f; ev_ = 0.0f; }
+    }
+    float h8u = ls_h8_cols(vlu, zsu[j + 1], vru, wu_, eu_);
+    float h8v = ls_h8_cols(vlv, zsv[j + 1], vrv, wv_, ev_);
+    LsNb nu{uu[j + 1], ud[j + 1], um[j], um[j + 2], uu[j], uu[j + 2], ud[j], ud[j + 2]};
+    LsNb nv{vu[j + 1], vd[j + 1], vm[j], vm[j + 2], vu[j], vu[j + 2], vd[j], vd[j + 2]};
+    LsCoef c;
+    c.IIx = c0[j]; c.IIy = c1[j]; c.II = c2[j]; c.Ixt = c3[j]; c.Iyt = c4[j]; c.B11 = c5[j]; c.B12 = c6[j]; c.B22 = c7[j];
+    ls_update2(nu, nv, h8u, h8v, c, hpar, &ou[j], &ov[j]);
+  }
+}
 
+template <int T, int R, int NRG, int NG, bool EDGE, bool LAST>
+__device__ __forceinline__ void ls_sweep(const float* __restrict__ cu, const float* __restrict__ cv,
+                                         float* __restrict__ nu, float* __restrict__ nv, const float* __restrict__ sC,
+                                         int r0, int sx, const LsEdge& eg, float hpar, float* __restrict__ gU,
+                                         float* __restrict__ gV, long gpitch, int gy0, int gx, int H, int W,
+                                         float& du2, float& dv2) {
+  using C = LsCfg<T, R, NRG, NG>;
+  constexpr int SW = C::SW;
+  float wu[3][6], wv[3][6];
+  const float* pu = cu + (r0 - 1) * SW + sx;
+  const float* pv = cv + (r0 - 1) * SW + sx;
+  ls_row6<EDGE>(pu, pv, eg, wu[0], wv[0]);
+  ls_row6<EDGE>(pu + SW, pv + SW, eg, wu[1], wv[1]);
+  const bool in_cols = (sx >= C::HX) && (sx < SW - C::HX);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int A = j % 3, B = (j + 1) % 3, Cc = (j + 2) % 3;
+    ls_row6<EDGE>(pu + (j + 2) * SW, pv + (j + 2) * SW, eg, wu[Cc], wv[Cc]);
+    float ou[4], ov[4];
+    const int so = (r0 + j) * SW + sx;
+    if (EDGE && j == eg.top_j)        // global row 0: 'nearest' -> the row above is the row itself; H8: zero
+      ls_row_update<EDGE>(wu[B], wu[B], wu[Cc], wv[B], wv[B], wv[Cc], sC, C::PLANE, so, hpar, true, false, eg, ou, ov);
+    else if (EDGE && j == eg.bot_j)
+      ls_row_update<EDGE>(wu[A], wu[B], wu[B], wv[A], wv[B], wv[B], sC, C::PLANE, so, hpar, false, true, eg, ou, ov);
+    else
+      ls_row_update<EDGE>(wu[A], wu[B], wu[Cc], wv[A], wv[B], wv[Cc], sC, C::PLANE, so, hpar, false, false, eg, ou, ov);
+    // residual over the CTA's own output cells only (each pixel counted by exactly one CTA)
+    const int sy = r0 + j, gy = gy0 + j;
+    const bool own = in_cols && (sy >= T) && (sy < C::SH - T) && (gy < H);
+    if (own) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!EDGE || gx + q < W) {
+          float eu = fsub(ou[q], wu[B][q + 1]), ev = fsub(ov[q], wv[B][q + 1]);
+          du2 = fmaf(eu, eu, du2);
+          dv2 = fmaf(ev, ev, dv2);
+        }
+      }
+    }
+    if (!LAST) {
+      *reinterpret_cast<float4*>(nu + so) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+      *reinterpret_cast<float4*>(nv + so) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    } else if (own && gx < W) {
+      const long go = (long)gy * gpitch + gx;
+      *reinterpret_cast<float4*>(gU + go) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+      *reinterpret_cast<float4*>(gV + go) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    }
+  }
+}
+
+template <int T, int R, int NRG, int NG, bool EDGE>
+__device__ __forceinline__ void ls_fused_body(const Img& ui, const Img& vi, const Img& uo, const Img& vo,
+                                              const LsPlanes& co, float hpar, int k0, double* errs_pair, float* smem,
+                                              double* sh) {
+  using C = LsCfg<T, R, NRG, NG>;
+  constexpr int SW = C::SW, SH = C::SH, HX = C::HX;
+  const int b = blockIdx.z;
+  const int W = ui.W, H = ui.H;
   const int x0 = blockIdx.x * C::TW - HX;
   const int y0 = blockIdx.y * C::TH - T;
   const int tid = threadIdx.x;
-  float* sC = smem + 4 * C::PLANE;    // 8 coefficient planes
-
+  float* sC = smem + 4 * C::PLANE;
   {
     const float* gU = ui.p + (long)b * ui.stride;
     const float* gV = vi.p + (long)b * vi.stride;
     const long cb = (long)b * co.c[0].stride;
-    for (int i = tid; i < SH * C::NG; i += C::NT) {
-      int sy = i / C::NG, sg = i - sy * C::NG;
+    for (int i = tid; i < SH * NG; i += C::NT) {
+      int sy = i / NG, sg = i - sy * NG;
       int gy = y0 + sy, gx = x0 + 4 * sg;
       bool ok = (gy >= 0) && (gy < H) && (gx >= 0) && (gx < (int)ui.pitch);
-      int cy = ok ? gy : 0, cx = ok ? gx : 0;
+      long go = ok ? (long)gy * ui.pitch + gx : 0;
       int so = sy * SW + 4 * sg;
-      long go = (long)cy * ui.pitch + cx;
       cp_async16_ls(smem + so, gU + go, ok);
       cp_async16_ls(smem + 2 * C::PLANE + so, gV + go, ok);
 #pragma unroll
       for (int c = 0; c < 8; ++c) cp_async16_ls(sC + c * C::PLANE + so, co.c[c].p + cb + go, ok);
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();
   }
-
-  const int cg = tid % C::NG, rg = tid / C::NG;
+  const int cg = tid % NG, rg = tid / NG;
   const int sx = 4 * cg;
+  const int r0 = 1 + rg * R;
   const int gx = x0 + sx;
-  const int sxl = sx > 0 ? sx - 1 : 0;
-  const int sxr = sx + 4 < SW ? sx + 4 : SW - 1;
-  const bool left_edge = (gx == 0);
-  const int right_j = (W - 1) - gx;
-  // this thread's pixels count towards the residual only inside the CTA's OWN output tile
-  const int own_x_lo = HX, own_x_hi = HX + C::TW;      // shared columns
-  const int own_y_lo = T, own_y_hi = T + C::TH;        // shared rows
+  LsEdge eg;
+  eg.left_edge = EDGE && (gx == 0);
+  eg.right_j = EDGE ? (W - 1) - gx : -1;
+  eg.top_j = EDGE ? -(y0 + r0) : -1000;
+  eg.bot_j = EDGE ? (H - 1) - (y0 + r0) : -1000;
+  float* gU = uo.p + (long)b * uo.stride;
+  float* gV = vo.p + (long)b * vo.stride;
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
 
 #pragma unroll 1
-  for (int s = 0; s < T; ++s) {
+  for (int s = 0; s < T - 1; ++s) {
     const float* cu = smem + (s & 1) * C::PLANE;
     const float* cv = smem + (2 + (s & 1)) * C::PLANE;
     float* nu = smem + ((s + 1) & 1) * C::PLANE;
     float* nv = smem + (2 + ((s + 1) & 1)) * C::PLANE;
-    int lo = s + 1, hi = SH - s - 1;
-    if (y0 + lo < 0) lo = -y0;
-    if (y0 + hi > H) hi = H - y0;
-    const int R = (hi - lo + NRG - 1) / NRG;
-    const int r0 = lo + rg * R;
-    const int r1 = (r0 + R < hi) ? r0 + R : hi;
-    double du2 = 0.0, dv2 = 0.0;
-    if (r0 < r1) {
-      float wu[3][6], wv[3][6];
-      // 'nearest' in y: row -1 -> row 0, row H -> row H-1
-      ls_load_row<SW>(cu, cv, (y0 + r0 == 0) ? r0 : r0 - 1, sx, sxl, sxr, left_edge, right_j, wu[0], wv[0]);
-      ls_load_row<SW>(cu, cv, r0, sx, sxl, sxr, left_edge, right_j, wu[1], wv[1]);
-      int r = r0;
-#define OFRI_LS_STEP(A, B, Cc)                                                                                       \
-  {                                                                                                                  \
-    const int gy = y0 + r;                                                                                           \
-    ls_load_row<SW>(cu, cv, (gy == H - 1) ? r : r + 1, sx, sxl, sxr, left_edge, right_j, wu[Cc], wv[Cc]);            \
-    const int so = r * SW + sx;                                                                                      \
-    float4 q0 = *reinterpret_cast<const float4*>(sC + 0 * C::PLANE + so);                                            \
-    float4 q1 = *reinterpret_cast<const float4*>(sC + 1 * C::PLANE + so);                                            \
-    float4 q2 = *reinterpret_cast<const float4*>(sC + 2 * C::PLANE + so);                                            \
-    float4 q3 = *reinterpret_cast<const float4*>(sC + 3 * C::PLANE + so);                                            \
-    float4 q4 = *reinterpret_cast<const float4*>(sC + 4 * C::PLANE + so);                                            \
-    float4 q5 = *reinterpret_cast<const float4*>(sC + 5 * C::PLANE + so);                                            \
-    float4 q6 = *reinterpret_cast<const float4*>(sC + 6 * C::PLANE + so);                                            \
-    float4 q7 = *reinterpret_cast<const float4*>(sC + 7 * C::PLANE + so);                                            \
-    const float c0[4] = {q0.x, q0.y, q0.z, q0.w}, c1[4] = {q1.x, q1.y, q1.z, q1.w};                                  \
-    const float c2[4] = {q2.x, q2.y, q2.z, q2.w}, c3[4] = {q3.x, q3.y, q3.z, q3.w};                                  \
-    const float c4[4] = {q4.x, q4.y, q4.z, q4.w}, c5[4] = {q5.x, q5.y, q5.z, q5.w};                                  \
-    const float c6[4] = {q6.x, q6.y, q6.z, q6.w}, c7[4] = {q7.x, q7.y, q7.z, q7.w};                                  \
-    const bool top = (gy == 0), bot = (gy == H - 1);                                                                 \
-    const bool own_row = (r >= own_y_lo) && (r < own_y_hi);                                                          \
-    float ou[4], ov[4];                                                                                              \
-    _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                  \
-      float uc[3][3], vc[3][3];                                                                                      \
-      _Pragma("unroll") for (int q = 0; q < 3; ++q) {                                                                \
-        uc[0][q] = wu[A][j + q]; uc[1][q] = wu[B][j + q]; uc[2][q] = wu[Cc][j + q];                                  \
-        vc[0][q] = wv[A][j + q]; vc[1][q] = wv[B][j + q]; vc[2][q] = wv[Cc][j + q];                                  \
-      }                                                                                                              \
-      const bool lft = left_edge && (j == 0), rgt = (right_j == j);                                                  \
-      unsigned inb = 0x1FFu;                                                                                         \
-      if (top) inb &= ~0x007u;                                                                                       \
-      if (bot) inb &= ~0x1C0u;                                                                                       \
-      if (lft) inb &= ~0x049u;                                                                                       \
-      if (rgt) inb &= ~0x124u;                                                                                       \
-      LsCoef c;                                                                                                      \
-      c.IIx = c0[j]; c.IIy = c1[j]; c.II = c2[j]; c.Ixt = c3[j]; c.Iyt = c4[j]; c.B11 = c5[j]; c.B12 = c6[j];        \
-      c.B22 = c7[j];                                                                                                 \
-      ls_update(uc, vc, inb, c, hpar, &ou[j], &ov[j]);                                                               \
-      const int scol = sx + j;                                                                                       \
-      if (own_row && scol >= own_x_lo && scol < own_x_hi && (x0 + scol) < W) {                                       \
-        float eu = fsub(ou[j], uc[1][1]), ev = fsub(ov[j], vc[1][1]);                                                \
-        du2 += (double)eu * (double)eu;                                                                              \
-        dv2 += (double)ev * (double)ev;                                                                              \
-      }                                                                                                              \
-    }                                                                                                                \
-    *reinterpret_cast<float4*>(nu + so) = make_float4(ou[0], ou[1], ou[2], ou[3]);                                   \
-    *reinterpret_cast<float4*>(nv + so) = make_float4(ov[0], ov[1], ov[2], ov[3]);                                   \
-  }                                                                                                                  \
-  if (++r >= r1) break;
-      while (true) {
-        OFRI_LS_STEP(0, 1, 2)
-        OFRI_LS_STEP(1, 2, 0)
-        OFRI_LS_STEP(2, 0, 1)
-      }
-#undef OFRI_LS_STEP
-    }
-    // residual of sweep k0+s over this CTA's own pixels (block_atomic_add2 also synchronises the sweep)
-    block_atomic_add2(du2, dv2, errs_pair + 2 * (k0 + s), sh);
+    float du2 = 0.0f, dv2 = 0.0f;
+    ls_sweep<T, R, NRG, NG, EDGE, false>(cu, cv, nu, nv, sC, r0, sx, eg, hpar, gU, gV, uo.pitch, y0 + r0, gx, H, W, du2,
+                                         dv2);
+    block_atomic_add2((double)du2, (double)dv2, errs_pair + 2 * (k0 + s), sh);   // also the sweep barrier
   }
-
   {
-    const float* fu = smem + (T & 1) * C::PLANE;
-    const float* fv = smem + (2 + (T & 1)) * C::PLANE;
-    float* gU = uo.p + (long)b * uo.stride;
-    float* gV = vo.p + (long)b * vo.stride;
-    constexpr int OG = C::TW / 4;
-    for (int i = tid; i < C::TH * OG; i += C::NT) {
-      int ty = i / OG, tg = i - ty * OG;
-      int sy = ty + T, sxx = HX + 4 * tg;
-      int gy = y0 + sy, gxx = x0 + sxx;
-      if (gy < H && gxx < W) {
-        float4 a = *reinterpret_cast<const float4*>(fu + sy * SW + sxx);
-        float4 c = *reinterpret_cast<const float4*>(fv + sy * SW + sxx);
-        *reinterpret_cast<float4*>(gU + (long)gy * uo.pitch + gxx) = a;
-        *reinterpret_cast<float4*>(gV + (long)gy * vo.pitch + gxx) = c;
-      }
-    }
+    constexpr int s = T - 1;
+    const float* cu = smem + (s & 1) * C::PLANE;
+    const float* cv = smem + (2 + (s & 1)) * C::PLANE;
+    float du2 = 0.0f, dv2 = 0.0f;
+    ls_sweep<T, R, NRG, NG, EDGE, true>(cu, cv, nullptr, nullptr, sC, r0, sx, eg, hpar, gU, gV, uo.pitch, y0 + r0, gx, H,
+                                        W, du2, dv2);
+    block_atomic_add2((double)du2, (double)dv2, errs_pair + 2 * (k0 + s), sh);
   }
 }
 
-template <int T, int SW, int SH, int HX, int NRG>
+template <int T, int R, int NRG, int NG, int MINB>
+__global__ void __launch_bounds__(LsCfg<T, R, NRG, NG>::NT, MINB)
+ls_fused_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, int k0, int maxiter, double tol, double* errs) {
+  using C = LsCfg<T, R, NRG, NG>;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double sh[64];
+  const int b = blockIdx.z;
+  const double npix = (double)u0.H * (double)u0.W;
+  double* errs_pair = errs + (long)b * maxiter * 2;
+  if (k0 > 0 && ls_stopped_before(errs_pair, k0, tol, npix, T)) return;   // uniform per CTA
+  // launch index parity selects the ping-pong direction: launches alternate u0->u1, u1->u0
+  const bool odd = ((k0 / T) & 1) != 0;   // every earlier launch fused exactly T sweeps
+  const Img& ui = odd ? u1 : u0;
+  const Img& vi = odd ? v1 : v0;
+  const Img& uo = odd ? u0 : u1;
+  const Img& vo = odd ? v0 : v1;
+  const int x0 = blockIdx.x * C::TW - C::HX, y0 = blockIdx.y * C::TH - T;
+  const bool edge = (x0 < 0) || (x0 + C::SW > u0.W) || (y0 < 0) || (y0 + C::SH > u0.H);
+  if (edge)
+    ls_fused_body<T, R, NRG, NG, true>(ui, vi, uo, vo, co, hpar, k0, errs_pair, smem, sh);
+  else
+    ls_fused_body<T, R, NRG, NG, false>(ui, vi, uo, vo, co, hpar, k0, errs_pair, smem, sh);
+}
+
+template <int T, int R, int NRG, int NG, int MINB>
 static void launch_ls_fused_cfg(const Img& u0, const Img& v0, const Img& u1, const Img& v1, const LsPlanes& co,
                                 float hpar, int k0, int maxiter, double tol, double* errs, cudaStream_t s) {
-  using C = LsFusedCfg<T, SW, SH, HX, NRG>;
-  auto kern = ls_fused_kernel<T, SW, SH, HX, NRG>;
+  using C = LsCfg<T, R, NRG, NG>;
+  auto kern = ls_fused_kernel<T, R, NRG, NG, MINB>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   dim3 g((u0.W + C::TW - 1) / C::TW, (u0.H + C::TH - 1) / C::TH, u0.batch);
   kern<<<g, C::NT, C::SMEM_BYTES, s>>>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs);
@@ -447,18 +503,34 @@ __global__ void ls_select_kernel(Img u0, Img v0, Img u1, Img v1, Img uo, Img vo,
   vo.p[(long)b * vo.stride + (long)y * vo.pitch + x] = sv.p[(long)b * sv.stride + (long)y * sv.pitch + x];
 }
 
-static void launch_ls_fused(int T, const Img& u0, const Img& v0, const Img& u1, const Img& v1, const LsPlanes& co,
-                            float hpar, int k0, int maxiter, double tol, double* errs, cudaStream_t s) {
+template <int T>
+static void launch_ls_fused_T(int variant, const Img& u0, const Img& v0, const Img& u1, const Img& v1,
+                              const LsPlanes& co, float hpar, int k0, int maxiter, double tol, double* errs,
+                              cudaStream_t s) {
+  switch (variant) {
+    default:
+    case 0: launch_ls_fused_cfg<T, 4, 4, 16, 4>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 18 x 64
+    case 1: launch_ls_fused_cfg<T, 4, 8, 16, 2>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 34 x 64
+    case 2: launch_ls_fused_cfg<T, 4, 4, 32, 2>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 18 x 128
+    case 3: launch_ls_fused_cfg<T, 3, 6, 16, 3>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 20 x 64
+    case 4: launch_ls_fused_cfg<T, 2, 8, 16, 4>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 18 x 64
+    case 5: launch_ls_fused_cfg<T, 6, 4, 16, 3>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 26 x 64
+  }
+}
+static void launch_ls_fused(int T, int variant, const Img& u0, const Img& v0, const Img& u1, const Img& v1,
+                            const LsPlanes& co, float hpar, int k0, int maxiter, double tol, double* errs,
+                            cudaStream_t s) {
   switch (T) {
-    case 1: launch_ls_fused_cfg<1, 72, 18, 4, 6>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
-    case 2: launch_ls_fused_cfg<2, 72, 20, 4, 6>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
-    case 3: launch_ls_fused_cfg<3, 72, 22, 4, 6>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
-    default: launch_ls_fused_cfg<4, 72, 24, 4, 6>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
+    case 1: launch_ls_fused_T<1>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
+    case 2: launch_ls_fused_T<2>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
+    case 3: launch_ls_fused_T<3>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
+    default: launch_ls_fused_T<4>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
   }
 }
 
 void launch_ls_solve(const Img& ua, const Img& va, const Img& ub, const Img& vb, const LsPlanes& coef, float hpar,
-                     int maxiter, double tol, int fuse, double* errs, int* state, const Img& uo, const Img& vo,
+                     int maxiter, double tol, int fuse, int variant, double* errs, int* state, const Img& uo,
+                     const Img& vo,
                      float* err_out, int err_stride, int* iters_out, cudaStream_t s, LaunchCounter& lc) {
   const int batch = ua.batch;
   const double npix = (double)ua.H * (double)ua.W;
@@ -476,7 +548,7 @@ void launch_ls_solve(const Img& ua, const Img& va, const Img& ub, const Img& vb,
   if (can_fuse && T >= 1) {
     nfull = maxiter / T;
     for (int i = 0; i < nfull; ++i) {
-      launch_ls_fused(T, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, s);
+      launch_ls_fused(T, variant, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, s);
       lc.n += 1;
     }
   } else {

@@ -265,50 +265,54 @@ OFRI_HD LsCoef ls_coef_point(const float a[3][3], const float d[3][3], float hpa
   return c;
 }
 // one Jacobi-type sweep at one pixel.  u = ROW component, v = COLUMN component (adapter swap, LS:38-39).
-// uc / vc: clamp-to-edge neighbourhoods ([row][col]); inb: bit (3*r + c) set iff that neighbour is inside the
-// image (zero padding of the 8-neighbour sum H).  Interior pixels pass inb = 0x1FF.
-OFRI_HD void ls_update(const float uc[3][3], const float vc[3][3], unsigned inb, const LsCoef& c, float hpar,
-                       float* un, float* vn) {
-  float dr_u = fmul(0.5f, fsub(uc[2][1], uc[0][1]));
-  float dc_u = fmul(0.5f, fsub(uc[1][2], uc[1][0]));
-  float dr_v = fmul(0.5f, fsub(vc[2][1], vc[0][1]));
-  float dc_v = fmul(0.5f, fsub(vc[1][2], vc[1][0]));
-  float fr_u = fadd(uc[0][1], uc[2][1]);
-  float fc_v = fadd(vc[1][0], vc[1][2]);
-  float mx_u = fmul(0.25f, fadd(fsub(fsub(uc[0][0], uc[0][2]), uc[2][0]), uc[2][2]));
-  float mx_v = fmul(0.25f, fadd(fsub(fsub(vc[0][0], vc[0][2]), vc[2][0]), vc[2][2]));
-  float h8u = 0.0f, h8v = 0.0f;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int r = 0; r < 3; ++r)
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int q = 0; q < 3; ++q) {
-      if (r == 1 && q == 1) continue;
-      bool in = (inb >> (3 * r + q)) & 1u;
-      h8u = fadd(h8u, in ? uc[r][q] : 0.0f);
-      h8v = fadd(h8v, in ? vc[r][q] : 0.0f);
-    }
-  // bu = 2 IIx Dr(u) + IIx Dc(v) + IIy Dr(v) + II Fr(u) + II Mx(v) + h H8(u) + Ixt     (LS:142-144)
-  float bu = fmul(fmul(2.0f, c.IIx), dr_u);
-  bu = fmaf(c.IIx, dc_v, bu);
-  bu = fmaf(c.IIy, dr_v, bu);
-  bu = fmaf(c.II, fr_u, bu);
-  bu = fmaf(c.II, mx_v, bu);
+// LsNb: the 8 neighbours with clamp-to-edge ('nearest') applied by the caller; h8u / h8v: the 8-neighbour sums with
+// ZERO padding (the reference's H kernel uses mode='constant'), summed as ((nw+sw) + (n+s) + (ne+se)) + (w+e).
+// Fast f32/FMA formulation; the power-of-two factors of the D / M stencils are folded into the coefficients, which is
+// exact:   bu = 2 IIx Dr(u) + IIx Dc(v) + IIy Dr(v) + II Fr(u) + II Mx(v) + h H8(u) + Ixt          (LS:142-144)
+//          bv = IIy Dr(u) + IIx Dc(u) + 2 IIy Dc(v) + II Mx(u) + II Fc(v) + h H8(v) + Iyt          (LS:146-148)
+struct LsNb { float n, s, w, e, nw, ne, sw, se; };
+OFRI_HD float ls_h8_cols(float vl, float vc, float vr, float w, float e) {   // vl = nw+sw, vc = n+s, vr = ne+se
+  return fadd(fadd(fadd(vl, vc), vr), fadd(w, e));
+}
+OFRI_HD void ls_update2(const LsNb& u, const LsNb& v, float h8u, float h8v, const LsCoef& c, float hpar, float* un,
+                        float* vn) {
+  float dru = fsub(u.s, u.n), dcu = fsub(u.e, u.w), drv = fsub(v.s, v.n), dcv = fsub(v.e, v.w);   // 2 Dr, 2 Dc
+  float fru = fadd(u.n, u.s), fcv = fadd(v.w, v.e);
+  float mxu = fadd(fsub(fsub(u.nw, u.ne), u.sw), u.se);                                          // 4 Mx
+  float mxv = fadd(fsub(fsub(v.nw, v.ne), v.sw), v.se);
+  float hx = fmul(0.5f, c.IIx), hy = fmul(0.5f, c.IIy), q = fmul(0.25f, c.II);
+  float bu = fmul(c.IIx, dru);
+  bu = fmaf(hx, dcv, bu);
+  bu = fmaf(hy, drv, bu);
+  bu = fmaf(c.II, fru, bu);
+  bu = fmaf(q, mxv, bu);
   bu = fmaf(hpar, h8u, bu);
   bu = fadd(bu, c.Ixt);
-  // bv = IIy Dr(u) + IIx Dc(u) + 2 IIy Dc(v) + II Mx(u) + II Fc(v) + h H8(v) + Iyt     (LS:146-148)
-  float bv = fmul(c.IIy, dr_u);
-  bv = fmaf(c.IIx, dc_u, bv);
-  bv = fmaf(fmul(2.0f, c.IIy), dc_v, bv);
-  bv = fmaf(c.II, mx_u, bv);
-  bv = fmaf(c.II, fc_v, bv);
+  float bv = fmul(hy, dru);
+  bv = fmaf(hx, dcu, bv);
+  bv = fmaf(c.IIy, dcv, bv);
+  bv = fmaf(q, mxu, bv);
+  bv = fmaf(c.II, fcv, bv);
   bv = fmaf(hpar, h8v, bv);
   bv = fadd(bv, c.Iyt);
   *un = -fmaf(c.B11, bu, fmul(c.B12, bv));
   *vn = -fmaf(c.B12, bu, fmul(c.B22, bv));
+}
+// convenience for per-pixel callers: 3x3 clamped neighbourhoods + in-bounds mask (bit 3r+c)
+OFRI_HD void ls_update(const float uc[3][3], const float vc[3][3], unsigned inb, const LsCoef& c, float hpar,
+                       float* un, float* vn) {
+  LsNb u{uc[0][1], uc[2][1], uc[1][0], uc[1][2], uc[0][0], uc[0][2], uc[2][0], uc[2][2]};
+  LsNb v{vc[0][1], vc[2][1], vc[1][0], vc[1][2], vc[0][0], vc[0][2], vc[2][0], vc[2][2]};
+  float zu[3][3], zv[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int q = 0; q < 3; ++q) {
+      bool in = (inb >> (3 * r + q)) & 1u;
+      zu[r][q] = in ? uc[r][q] : 0.0f;
+      zv[r][q] = in ? vc[r][q] : 0.0f;
+    }
+  float h8u = ls_h8_cols(fadd(zu[0][0], zu[2][0]), fadd(zu[0][1], zu[2][1]), fadd(zu[0][2], zu[2][2]), zu[1][0], zu[1][2]);
+  float h8v = ls_h8_cols(fadd(zv[0][0], zv[2][0]), fadd(zv[0][1], zv[2][1]), fadd(zv[0][2], zv[2][2]), zv[1][0], zv[1][2]);
+  ls_update2(u, v, h8u, h8v, c, hpar, un, vn);
 }
 
 }  // namespace ofri

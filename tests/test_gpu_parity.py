@@ -276,17 +276,21 @@ def test_ls_fused_bit_identical_and_midblock_stop(h, shape):
             h.set_option("ls_fuse", 0)
             Ur, Vr, er, itr = h.ls_compute(g1, g2, U0, V0, 5, maxiter=maxiter, tol=tol)
             for T in (1, 2, 3, 4):
-                h.set_option("ls_fuse", T)
-                U, V, e, it = h.ls_compute(g1, g2, U0, V0, 5, maxiter=maxiter, tol=tol)
-                assert list(it) == list(itr), (T, maxiter, tol, list(it), list(itr))
-                try:
-                    same(U, Ur)
-                    same(V, Vr)
-                except AssertionError as ex:
-                    raise AssertionError("T=%d maxiter=%d tol=%g its=%s: %s" % (T, maxiter, tol, list(itr), ex))
-                np.testing.assert_allclose(e, er, rtol=1e-5)
+                for lv in range(6):
+                    h.set_option("ls_fuse", T)
+                    h.set_option("ls_variant", lv)
+                    U, V, e, it = h.ls_compute(g1, g2, U0, V0, 5, maxiter=maxiter, tol=tol)
+                    assert list(it) == list(itr), (T, lv, maxiter, tol, list(it), list(itr))
+                    try:
+                        same(U, Ur)
+                        same(V, Vr)
+                    except AssertionError as ex:
+                        raise AssertionError("T=%d variant=%d maxiter=%d tol=%g its=%s: %s" % (T, lv, maxiter, tol,
+                                                                                                   list(itr), ex))
+                    np.testing.assert_allclose(e, er, rtol=1e-5)
     finally:
         h.set_option("ls_fuse", 2)
+        h.set_option("ls_variant", 0)
 
 
 def test_ls_stop_rule_vs_oracle(h):

@@ -59,6 +59,7 @@ if "one" in which:
     h.set_option("hs_fuse", int(os.environ.get("HS_FUSE", "4")))
     h.set_option("hs_variant", int(os.environ.get("HS_VARIANT", "0")))
     h.set_option("ls_fuse", int(os.environ.get("LS_FUSE", "2")))
+    h.set_option("ls_variant", int(os.environ.get("LS_VARIANT", "0")))
     run({"hs_fuse": h.get_option("hs_fuse"), "hs_variant": h.get_option("hs_variant"), "ls_fuse": h.get_option("ls_fuse")})
 if "hs" in which:
     h.set_option("ls_fuse", 2)
@@ -69,7 +70,9 @@ if "hs" in which:
             run({"hs_fuse": T, "hs_variant": variant, "ls_fuse": 2})
 if "ls" in which:
     h.set_option("hs_fuse", 4)
-    h.set_option("hs_variant", 0)
+    h.set_option("hs_variant", int(os.environ.get("HS_VARIANT", "0")))
     for T in (0, 1, 2, 3, 4):
-        h.set_option("ls_fuse", T)
-        run({"hs_fuse": 4, "hs_variant": 0, "ls_fuse": T})
+        for lv in (range(6) if T > 0 else [0]):
+            h.set_option("ls_fuse", T)
+            h.set_option("ls_variant", lv)
+            run({"hs_fuse": 4, "ls_fuse": T, "ls_variant": lv})
