@@ -178,8 +178,7 @@ def workload_config(args, handle):
            "l2": "inputs larger than L2 (%.1f GiB of frames per step per GPU); no flush needed"
                  % (args.pairs_per_gpu * 2 * H * W * 4 / 2 ** 30)}
     if handle is not None:
-        cfg.update({"hs_fuse": handle.get_option("hs_fuse"), "hs_variant": handle.get_option("hs_variant"),
-                    "ls_fuse": handle.get_option("ls_fuse")})
+        cfg.update({k: handle.get_option(k) for k in ("hs_fuse", "hs_variant", "hs_precise", "ls_fuse", "ls_variant")})
     return cfg
 
 
@@ -199,7 +198,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     h = ofri.Handle(local)
     for k, v in (("hs_fuse", args.hs_fuse), ("hs_variant", args.hs_variant), ("ls_fuse", args.ls_fuse),
-                 ("chunk_pairs", args.chunk_pairs)):
+                 ("ls_variant", args.ls_variant), ("hs_precise", args.hs_precise), ("chunk_pairs", args.chunk_pairs)):
         if v is not None:
             h.set_option(k, v)
     P = args.pairs_per_gpu
@@ -334,6 +333,8 @@ def main():
     ap.add_argument("--hs-fuse", type=int, default=None)
     ap.add_argument("--hs-variant", type=int, default=None)
     ap.add_argument("--ls-fuse", type=int, default=None)
+    ap.add_argument("--ls-variant", type=int, default=None)
+    ap.add_argument("--hs-precise", type=int, default=None)
     ap.add_argument("--chunk-pairs", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":

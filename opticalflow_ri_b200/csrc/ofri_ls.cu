@@ -151,12 +151,18 @@ __global__ void __launch_bounds__(256)
 ls_sweep_simple_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, int k, int maxiter, double tol,
                        double* errs, const int* state, int mode, int lookback) {
   __shared__ double sh[64];
+  __shared__ int s_stop;
   const int b = blockIdx.z;
   const int W = u0.W, H = u0.H;
   const double npix = (double)H * (double)W;
   Img ui, vi, uo, vo;
   if (mode == 0) {
-    if (k > 0 && ls_stopped_before(errs + (long)b * maxiter * 2, k, tol, npix, lookback)) return;
+    if (k > 0) {
+      if (threadIdx.x == 0 && threadIdx.y == 0)
+        s_stop = ls_stopped_before(errs + (long)b * maxiter * 2, k, tol, npix, lookback) ? 1 : 0;
+      __syncthreads();
+      if (s_stop) return;
+    }
     if (k & 1) { ui = u1; vi = v1; uo = u0; vo = v0; } else { ui = u0; vi = v0; uo = u1; vo = v1; }
   } else {
     const int* st = state + 4 * b;
@@ -425,10 +431,15 @@ ls_fused_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, int k0,
   using C = LsCfg<T, R, NRG, NG>;
   extern __shared__ __align__(16) float smem[];
   __shared__ double sh[64];
+  __shared__ int s_stop;
   const int b = blockIdx.z;
   const double npix = (double)u0.H * (double)u0.W;
   double* errs_pair = errs + (long)b * maxiter * 2;
-  if (k0 > 0 && ls_stopped_before(errs_pair, k0, tol, npix, T)) return;   // uniform per CTA
+  if (k0 > 0) {   // stopping rule evaluated by one thread (f64 square roots), CTA-uniform result
+    if (threadIdx.x == 0) s_stop = ls_stopped_before(errs_pair, k0, tol, npix, T) ? 1 : 0;
+    __syncthreads();
+    if (s_stop) return;
+  }
   // launch index parity selects the ping-pong direction: launches alternate u0->u1, u1->u0
   const bool odd = ((k0 / T) & 1) != 0;   // every earlier launch fused exactly T sweeps
   const Img& ui = odd ? u1 : u0;

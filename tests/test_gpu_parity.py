@@ -198,7 +198,7 @@ def test_hs_fused_bit_identical_to_simple(h, shape):
                         raise AssertionError("precise=%d T=%d variant=%d shape=%s: %s" % (precise, T, variant, shape, e))
     finally:
         h.set_option("hs_fuse", 4)
-        h.set_option("hs_variant", 0)
+        h.set_option("hs_variant", 4)
         h.set_option("hs_precise", 1)
 
 
@@ -290,7 +290,7 @@ def test_ls_fused_bit_identical_and_midblock_stop(h, shape):
                     np.testing.assert_allclose(e, er, rtol=1e-5)
     finally:
         h.set_option("ls_fuse", 2)
-        h.set_option("ls_variant", 0)
+        h.set_option("ls_variant", 4)
 
 
 def test_ls_stop_rule_vs_oracle(h):
