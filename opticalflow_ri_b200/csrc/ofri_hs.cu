@@ -10,6 +10,7 @@
 // launch (read U, V, fx, fy, ft; write U, V), i.e. 28/T B per pixel-sweep.
 #include "ofri_internal.h"
 #include "ofri_pixel.cuh"
+#include "ofri_hs_common.cuh"
 
 namespace ofri {
 
@@ -110,7 +111,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
   int sz = valid ? 16 : 0;   // src-size 0 -> 16 bytes of zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
-__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 template <int T, int R, int NRG, int NG>
 struct HsCfg {
@@ -127,11 +127,6 @@ struct HsCfg {
   static_assert(TW > 0 && TH > 0 && HX >= T, "bad tile");
 };
 
-struct HsEdge {      // per-thread boundary facts (EDGE tiles only)
-  bool left_edge;    // this strip starts at global column 0
-  int right_j;       // strip column j sitting on global column W-1 (else out of [0,4))
-  int top_j, bot_j;  // strip row j sitting on global row 0 / H-1 (else out of [0,R))
-};
 
 // one shared row of this thread's strip: columns sx-1 .. sx+4 of U and V
 template <int SW, bool EDGE, bool ALIGNED>
@@ -158,47 +153,6 @@ __device__ __forceinline__ void hs_row6(const float* __restrict__ pu, const floa
     if (eg.right_j == 1) { du[3] = du[1]; dv[3] = dv[1]; }
     if (eg.right_j == 2) { du[4] = du[2]; dv[4] = dv[2]; }
     if (eg.right_j == 3) { du[5] = du[3]; dv[5] = dv[3]; }
-  }
-}
-
-// coefficient registers of one strip row: fast path (a, b, c); precise (fx, fy, ft, den, 1/den)
-template <bool PRECISE>
-struct HsCoef {
-  float c0[4], c1[4], c2[4], c3[PRECISE ? 4 : 1], c4[PRECISE ? 4 : 1];
-};
-
-template <bool PRECISE>
-__device__ __forceinline__ void hs_row_update(const float (&uu)[6], const float (&um)[6], const float (&ud)[6],
-                                              const float (&vu)[6], const float (&vm)[6], const float (&vd)[6],
-                                              const HsCoef<PRECISE>& k, float (&ou)[4], float (&ov)[4]) {
-  if constexpr (!PRECISE) {
-    float vsu[6], vsv[6];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      vsu[c] = fadd(uu[c], ud[c]);
-      vsv[c] = fadd(vu[c], vd[c]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float ua = hs_avg_cols(vsu[j], vsu[j + 1], vsu[j + 2], um[j], um[j + 2]);
-      float va = hs_avg_cols(vsv[j], vsv[j + 1], vsv[j + 2], vm[j], vm[j + 2]);
-      hs_update_n(ua, va, k.c0[j], k.c1[j], k.c2[j], &ou[j], &ov[j]);
-    }
-  } else {
-    double vsu[6], vsv[6], mu[6], mv[6];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      vsu[c] = dadd((double)uu[c], (double)ud[c]);
-      vsv[c] = dadd((double)vu[c], (double)vd[c]);
-      mu[c] = (double)um[c];
-      mv[c] = (double)vm[c];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float ua = hs_avg_cols_precise(vsu[j], vsu[j + 1], vsu[j + 2], mu[j], mu[j + 2]);
-      float va = hs_avg_cols_precise(vsv[j], vsv[j + 1], vsv[j + 2], mv[j], mv[j + 2]);
-      hs_update_precise(ua, va, k.c0[j], k.c1[j], k.c2[j], k.c3[j], k.c4[j], &ou[j], &ov[j]);
-    }
   }
 }
 
@@ -398,8 +352,237 @@ static void launch_hs_fused_T(int variant, const Img& ui, const Img& vi, const I
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// register-resident fused Jacobi kernel (hs_regs_kernel): variants >= 8
+// ---------------------------------------------------------------------------------------------------------------
+// Same tile geometry and ownership as hs_fused_kernel (tile SH x 128, thread (lane, rg) owns the 4 x R strip at columns
+// 4 lane.., rows 1 + rg R..), but a thread keeps its strip of U and V in REGISTERS for all T sweeps next to the
+// coefficients: the strip is read from HBM once (LDG.128), swept T times in place (3-row sliding window, halo columns
+// by warp shuffle) and written back once (STG.128).  A warp is exactly one row group (NG = 32), so the only data that
+// crosses warps is the row above / below each strip: every sweep a thread publishes its first and last row in a small
+// double-buffered shared array and reads its neighbours' rows from it -- 4 STS.128 + 4 LDS.128 per thread per sweep
+// instead of 2(R+2) LDS.128 + 2R STS.128, one __syncthreads per sweep.  Shared memory holds only those edge rows
+// (2 buffers x 2 planes x 2(NRG+2) rows).  Arithmetic is the same expression tree (hs_row_update), so results are
+// bit-identical to the other kernels.
+template <int T, int R, int NRG>
+struct HrCfg {
+  static constexpr int HX = (T <= 4) ? 4 : 8;
+  static constexpr int SW = 128;
+  static constexpr int SH = R * NRG + 2;
+  static constexpr int NT = 32 * NRG;
+  static constexpr int TW = SW - 2 * HX;
+  static constexpr int TH = SH - 2 * T;
+  static constexpr int XG = NRG + 2;                     // edge-row slots: g = rg + 1; g = 0 / NRG+1 are the tile halos
+  static constexpr int XPLANE = XG * 2 * SW;             // [g][top / bottom][SW]
+  static constexpr int SMEM_BYTES = 2 * 2 * XPLANE * 4;  // [buffer][U / V]
+  static_assert(TW > 0 && TH > 0 && HX >= T && NT <= 1024, "bad tile");
+};
+
+template <int T, int R, int NRG, bool EDGE, bool PRECISE>
+__device__ __forceinline__ void hs_regs_body(const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
+                                             const Img& fy, const Img& ft, float alpha2, float* smem) {
+  using C = HrCfg<T, R, NRG>;
+  constexpr int SW = C::SW, SH = C::SH, HX = C::HX;
+  const int b = blockIdx.z;
+  const int W = ui.W, H = ui.H;
+  const int x0 = blockIdx.x * C::TW - HX;
+  const int y0 = blockIdx.y * C::TH - T;
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int sx = 4 * lane, gx = x0 + sx;
+  const int r0 = 1 + rg * R, gy0 = y0 + r0;
+  const long pitch = ui.pitch;
+  const bool okx = (gx >= 0) && (gx < (int)pitch);
+  const float* gUi = ui.p + (long)b * ui.stride;
+  const float* gVi = vi.p + (long)b * vi.stride;
+  auto X = [&](int buf, int plane, int g, int which) -> float* {
+    return smem + ((buf * 2 + plane) * C::XG + g) * 2 * SW + which * SW + sx;
+  };
+  // ---- tile halo rows (shared row 0 and SH-1): one warp each, into both buffers -----------------------------------
+  if (rg == 0 || rg == NRG - 1) {
+    const int gy = (rg == 0) ? y0 : y0 + SH - 1;
+    const int g = (rg == 0) ? 0 : NRG + 1, which = (rg == 0) ? 1 : 0;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+    if (!EDGE || (okx && gy >= 0 && gy < H)) {
+      a = ldg_f4(gUi + (long)gy * pitch + gx);
+      c = ldg_f4(gVi + (long)gy * pitch + gx);
+    }
+    *reinterpret_cast<float4*>(X(0, 0, g, which)) = a;
+    *reinterpret_cast<float4*>(X(0, 1, g, which)) = c;
+    *reinterpret_cast<float4*>(X(1, 0, g, which)) = a;
+    *reinterpret_cast<float4*>(X(1, 1, g, which)) = c;
+    if (NRG == 1) {   // a single row group owns both halos
+      const int gy2 = y0 + SH - 1;
+      a = c = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!EDGE || (okx && gy2 >= 0 && gy2 < H)) {
+        a = ldg_f4(gUi + (long)gy2 * pitch + gx);
+        c = ldg_f4(gVi + (long)gy2 * pitch + gx);
+      }
+      *reinterpret_cast<float4*>(X(0, 0, NRG + 1, 0)) = a;
+      *reinterpret_cast<float4*>(X(0, 1, NRG + 1, 0)) = c;
+      *reinterpret_cast<float4*>(X(1, 0, NRG + 1, 0)) = a;
+      *reinterpret_cast<float4*>(X(1, 1, NRG + 1, 0)) = c;
+    }
+  }
+  // ---- this thread's strip: U, V and coefficients, HBM -> registers -------------------------------------------------
+  float u[R][4], v[R][4];
+  HsCoef<PRECISE> k[R];
+  {
+    const float* g0 = fx.p + (long)b * fx.stride;
+    const float* g1 = fy.p + (long)b * fy.stride;
+    const float* g2 = ft.p + (long)b * ft.stride;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int gy = gy0 + j;
+      float4 qu = make_float4(0.f, 0.f, 0.f, 0.f), qv = qu, a = qu, c = qu, d = qu;
+      if (!EDGE || (okx && gy >= 0 && gy < H)) {
+        const long go = (long)gy * pitch + gx;
+        qu = ldg_f4(gUi + go);
+        qv = ldg_f4(gVi + go);
+        a = ldg_f4(g0 + go);
+        c = ldg_f4(g1 + go);
+        d = ldg_f4(g2 + go);
+      }
+      u[j][0] = qu.x; u[j][1] = qu.y; u[j][2] = qu.z; u[j][3] = qu.w;
+      v[j][0] = qv.x; v[j][1] = qv.y; v[j][2] = qv.z; v[j][3] = qv.w;
+      k[j].c0[0] = a.x; k[j].c0[1] = a.y; k[j].c0[2] = a.z; k[j].c0[3] = a.w;
+      k[j].c1[0] = c.x; k[j].c1[1] = c.y; k[j].c1[2] = c.z; k[j].c1[3] = c.w;
+      k[j].c2[0] = d.x; k[j].c2[1] = d.y; k[j].c2[2] = d.z; k[j].c2[3] = d.w;
+    }
+    if constexpr (PRECISE) {
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          k[j].c3[q] = hs_den(k[j].c0[q], k[j].c1[q], alpha2);
+          k[j].c4[q] = rcp_rn(k[j].c3[q]);
+        }
+    }
+  }
+  HsEdge eg;
+  eg.left_edge = EDGE && (gx == 0);
+  eg.right_j = EDGE ? (W - 1) - gx : -1;
+  eg.top_j = EDGE ? -gy0 : -1000;
+  eg.bot_j = EDGE ? (H - 1) - gy0 : -1000;
+  // publish the strip's first / last row for sweep 0
+  *reinterpret_cast<float4*>(X(0, 0, rg + 1, 0)) = make_float4(u[0][0], u[0][1], u[0][2], u[0][3]);
+  *reinterpret_cast<float4*>(X(0, 1, rg + 1, 0)) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
+  *reinterpret_cast<float4*>(X(0, 0, rg + 1, 1)) = make_float4(u[R - 1][0], u[R - 1][1], u[R - 1][2], u[R - 1][3]);
+  *reinterpret_cast<float4*>(X(0, 1, rg + 1, 1)) = make_float4(v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3]);
+  __syncthreads();
+
+  // ---- T sweeps in registers ------------------------------------------------------------------------------------------
+#pragma unroll 1
+  for (int s = 0; s < T; ++s) {
+    const int cur = s & 1;
+    float wu[3][6], wv[3][6];
+    hs_row6_smem<EDGE>(X(cur, 0, rg, 1), X(cur, 1, rg, 1), eg, wu[0], wv[0]);        // last row of the group above
+    hs_row6_vals<EDGE>(u[0], v[0], eg, wu[1], wv[1]);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int A = j % 3, B = (j + 1) % 3, Cc = (j + 2) % 3;
+      if (j + 1 < R)
+        hs_row6_vals<EDGE>(u[j + 1], v[j + 1], eg, wu[Cc], wv[Cc]);                  // still the old values
+      else
+        hs_row6_smem<EDGE>(X(cur, 0, rg + 2, 0), X(cur, 1, rg + 2, 0), eg, wu[Cc], wv[Cc]);   // first row of the group below
+      float ou[4], ov[4];
+      if (EDGE && j == eg.top_j)
+        hs_row_update<PRECISE>(wu[Cc], wu[B], wu[Cc], wv[Cc], wv[B], wv[Cc], k[j], ou, ov);
+      else if (EDGE && j == eg.bot_j)
+        hs_row_update<PRECISE>(wu[A], wu[B], wu[A], wv[A], wv[B], wv[A], k[j], ou, ov);
+      else
+        hs_row_update<PRECISE>(wu[A], wu[B], wu[Cc], wv[A], wv[B], wv[Cc], k[j], ou, ov);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { u[j][q] = ou[q]; v[j][q] = ov[q]; }
+    }
+    if (s + 1 < T) {
+      const int nxt = cur ^ 1;
+      *reinterpret_cast<float4*>(X(nxt, 0, rg + 1, 0)) = make_float4(u[0][0], u[0][1], u[0][2], u[0][3]);
+      *reinterpret_cast<float4*>(X(nxt, 1, rg + 1, 0)) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
+      *reinterpret_cast<float4*>(X(nxt, 0, rg + 1, 1)) = make_float4(u[R - 1][0], u[R - 1][1], u[R - 1][2], u[R - 1][3]);
+      *reinterpret_cast<float4*>(X(nxt, 1, rg + 1, 1)) = make_float4(v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3]);
+      __syncthreads();
+    }
+  }
+  // ---- interior cells -> HBM ---------------------------------------------------------------------------------------------
+  float* gU = uo.p + (long)b * uo.stride;
+  float* gV = vo.p + (long)b * vo.stride;
+  const bool in_cols = (sx >= HX) && (sx < SW - HX) && (gx < W);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int sy = r0 + j, gy = gy0 + j;
+    if (in_cols && (sy >= T) && (sy < SH - T) && (gy < H)) {
+      const long go = (long)gy * uo.pitch + gx;
+      *reinterpret_cast<float4*>(gU + go) = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
+      *reinterpret_cast<float4*>(gV + go) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+    }
+  }
+}
+
+template <int T, int R, int NRG, bool PRECISE, int MINB>
+__global__ void __launch_bounds__(HrCfg<T, R, NRG>::NT, MINB)
+hs_regs_kernel(Img ui, Img vi, Img uo, Img vo, Img fx, Img fy, Img ft, float alpha2) {
+  using C = HrCfg<T, R, NRG>;
+  extern __shared__ __align__(16) float smem[];
+  const int x0 = blockIdx.x * C::TW - C::HX, y0 = blockIdx.y * C::TH - T;
+  const bool edge = (x0 < 0) || (x0 + C::SW > ui.W) || (y0 < 0) || (y0 + C::SH > ui.H);
+  if (edge)
+    hs_regs_body<T, R, NRG, true, PRECISE>(ui, vi, uo, vo, fx, fy, ft, alpha2, smem);
+  else
+    hs_regs_body<T, R, NRG, false, PRECISE>(ui, vi, uo, vo, fx, fy, ft, alpha2, smem);
+}
+
+template <int T, int R, int NRG, bool PRECISE, int MINB>
+static void launch_hs_regs_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
+                               const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
+  using C = HrCfg<T, R, NRG>;
+  auto kern = hs_regs_kernel<T, R, NRG, PRECISE, MINB>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  dim3 g((ui.W + C::TW - 1) / C::TW, (ui.H + C::TH - 1) / C::TH, ui.batch);
+  kern<<<g, C::NT, C::SMEM_BYTES, s>>>(ui, vi, uo, vo, fx, fy, ft, alpha2);
+}
+
+template <int T, bool PRECISE>
+static void launch_hs_regs_T(int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
+                             const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
+  switch (variant) {
+    default:
+    case 8: launch_hs_regs_cfg<T, 4, 8, PRECISE, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;     // 34 x 128, 256 thr
+    case 9: launch_hs_regs_cfg<T, 4, 16, PRECISE, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 66 x 128, 512 thr
+    case 10: launch_hs_regs_cfg<T, 8, 8, PRECISE, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 66 x 128, 256 thr
+    case 11: launch_hs_regs_cfg<T, 6, 8, PRECISE, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 50 x 128, 256 thr
+    case 12: launch_hs_regs_cfg<T, 8, 4, PRECISE, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 34 x 128, 128 thr
+    case 13: launch_hs_regs_cfg<T, 6, 4, PRECISE, 3>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 26 x 128, 128 thr
+    case 14: launch_hs_regs_cfg<T, 4, 4, PRECISE, 4>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 18 x 128, 128 thr
+    case 15: launch_hs_regs_cfg<T, 6, 10, PRECISE, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;   // 62 x 128, 320 thr
+  }
+}
+
 static void launch_hs_fused(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo,
                             const Img& vo, const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
+  if (variant >= 8 && precise) variant = 2;   // the register-resident kernels are built for the fast arithmetic only
+  if (variant >= 24) {                        // persistent TMA-fed register-resident kernel (ofri_hs_tma.cu)
+    if (launch_hs_tma(T, variant, ui, vi, uo, vo, fx, fy, ft, s)) return;
+    variant = 8;                              // other T / no tensor-map support: non-persistent register kernel
+  }
+  if (variant >= 16) {                        // packed-f32x2 register-resident kernel (ofri_hs_pk.cu)
+    launch_hs_packed(T, variant, ui, vi, uo, vo, fx, fy, ft, s);
+    return;
+  }
+  if (variant >= 8) {
+#define OFRI_HR_T(TT) \
+  case TT: launch_hs_regs_T<TT, false>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+    switch (T) {
+      OFRI_HR_T(1)
+      OFRI_HR_T(2)
+      OFRI_HR_T(3)
+      OFRI_HR_T(4)
+      OFRI_HR_T(5)
+      OFRI_HR_T(6)
+      default: launch_hs_regs_T<8, false>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
+    }
+#undef OFRI_HR_T
+    return;
+  }
 #define OFRI_HS_T(TT)                                                                             \
   case TT:                                                                                        \
     if (precise) launch_hs_fused_T<TT, true>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s);     \

@@ -1,0 +1,362 @@
+// ofri_hs_tma.cu -- persistent, TMA-fed, register-resident Horn-Schunck Jacobi kernel (sm_100a).
+//
+// Reference: HornSchunck.py:52-71 (HS_helper / HS_helper2), fast arithmetic; same expression tree as every other
+// Horn-Schunck kernel here (ofri_hs_common.cuh: hs_row_update), hence bit-identical results.
+//
+// One CTA per SM walks over the tiles of the launch (tile = SH x 128 cells of one pair, SH = R NRG + 2; static
+// round-robin).  Per tile:
+//   1. the five planes of the tile (U, V and the prepared coefficients a, b, c) arrive in a shared staging buffer by
+//      TMA (cp.async.bulk.tensor, 3-D tensor maps [batch][H][W]; out-of-image elements are zero-filled by the copy
+//      engine, so border tiles need no address logic) and complete on an mbarrier;
+//      tiles that touch the image border then turn the out-of-image frame into GHOST cells: columns -1..-HX become
+//      copies of columns 1..HX (W..W+HX-1 of W-2..W-1-HX), rows likewise, for all five planes.  scipy's 'mirror'
+//      rule is a reflection about the border pixel and every operation of the update is symmetric under it (the
+//      stencil sums commute), so a ghost cell evolves bit-identically to the cell it mirrors: the boundary condition
+//      holds at every fused sweep with NO boundary code in the sweep itself;
+//   2. every thread moves its 4 x R strip from the staging buffer into REGISTERS (LDS.128) -- after a CTA barrier the
+//      staging buffer is free again and one thread immediately issues the TMA loads of the CTA's NEXT tile, which
+//      then overlap with
+//   3. T Jacobi sweeps done entirely in registers (3-row sliding window, halo columns by warp shuffle, the rows
+//      above / below a strip exchanged through a small double-buffered shared array, one __syncthreads per sweep), and
+//   4. float4 stores of the (SH - 2T) x (128 - 2 HX) interior straight from registers to HBM.
+// HBM reads of tile i+1 therefore run under the arithmetic of tile i, with a single CTA (8-12 warps, up to 255
+// registers per thread) per SM and no redundant staging of state through shared memory during the sweeps.
+// Algorithmic HBM traffic: 28 B per pixel per launch (read U, V, a, b, c; write U, V) for T sweeps.
+#include <cuda.h>
+
+#include "ofri_hs_common.cuh"
+
+namespace ofri {
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// 3-D map over a plane stack: dims (W, H, batch), strides (pitch, stride) floats, box (128, box_rows, 1), zero OOB fill
+bool make_map(CUtensorMap* m, const Img& img, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)img.W, (cuuint64_t)img.H, (cuuint64_t)img.batch};
+  cuuint64_t strides[2] = {(cuuint64_t)img.pitch * 4, (cuuint64_t)img.stride * 4};
+  cuuint32_t box[3] = {128, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, img.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(z), "r"(bar)
+      : "memory");
+}
+
+}  // namespace
+
+template <int T, int R, int NRG>
+struct TmCfg {
+  static constexpr int HX = (T <= 4) ? 4 : 8;
+  static constexpr int SW = 128;
+  static constexpr int SH = R * NRG + 2;
+  static constexpr int NT = 32 * NRG;
+  static constexpr int TW = SW - 2 * HX;
+  static constexpr int TH = SH - 2 * T;
+  static constexpr int PLANE = SH * SW;                      // floats per staged plane
+  static constexpr int XG = NRG + 2;
+  static constexpr int XPLANE = XG * 2 * SW;                 // [g][top / bottom][SW]
+  static constexpr int STAGE_BYTES = 5 * PLANE * 4;
+  static constexpr int X_BYTES = 2 * 2 * XPLANE * 4;         // [buffer][U / V]
+  static constexpr int SMEM_BYTES = STAGE_BYTES + X_BYTES + 64;
+  static_assert(TW > 0 && TH > 0 && HX >= T && NT <= 1024 && SH <= 256, "bad tile");
+  static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit in shared memory");
+  static_assert((PLANE * 4) % 128 == 0, "TMA destination alignment");
+};
+
+struct TmTile { int x0, y0, b; };
+
+template <int T, int R, int NRG>
+__device__ __forceinline__ TmTile tm_decode(int tile, int tiles_x, int tiles_y) {
+  using C = TmCfg<T, R, NRG>;
+  const int per = tiles_x * tiles_y;
+  TmTile t;
+  t.b = tile / per;
+  const int r = tile - t.b * per;
+  const int by = r / tiles_x, bx = r - by * tiles_x;
+  t.x0 = bx * C::TW - C::HX;
+  t.y0 = by * C::TH - T;
+  return t;
+}
+
+// Border tiles: fill the ghost frame of the staged planes (see the file comment).  x first, then y over the full tile
+// width, so the corners come out right.  Needs W > HX and H > T (checked on the host).
+template <int T, int R, int NRG>
+__device__ __forceinline__ void hs_tma_ghosts(const TmTile& tl, int W, int H, float* stage) {
+  using C = TmCfg<T, R, NRG>;
+  constexpr int SW = C::SW, SH = C::SH, HX = C::HX;
+  const int tid = threadIdx.x;
+  const bool left = tl.x0 < 0;                       // then x0 == -HX: global column 0 is tile column HX
+  const int cw = (W - 1) - tl.x0;                    // tile column of global column W-1
+  const bool right = cw + 1 < SW;
+  if (left || right) {
+    for (int i = tid; i < 5 * SH * HX; i += C::NT) {
+      const int k = 1 + i % HX, row = (i / HX) % SH, pl = i / (HX * SH);
+      float* r = stage + pl * C::PLANE + row * SW;
+      if (left) r[HX - k] = r[HX + k];
+      if (right && cw + k < SW) r[cw + k] = r[cw - k];
+    }
+    __syncthreads();
+  }
+  const bool top = tl.y0 < 0;                        // then y0 == -T: global row 0 is tile row T
+  const int rh = (H - 1) - tl.y0;                    // tile row of global row H-1
+  const bool bottom = rh + 1 < SH;
+  if (top || bottom) {
+    for (int i = tid; i < 5 * T * (SW / 4); i += C::NT) {
+      const int c4 = i % (SW / 4), k = 1 + (i / (SW / 4)) % T, pl = i / ((SW / 4) * T);
+      float* p = stage + pl * C::PLANE + 4 * c4;
+      if (top) *reinterpret_cast<float4*>(p + (T - k) * SW) = *reinterpret_cast<const float4*>(p + (T + k) * SW);
+      if (bottom && rh + k < SH)
+        *reinterpret_cast<float4*>(p + (rh + k) * SW) = *reinterpret_cast<const float4*>(p + (rh - k) * SW);
+    }
+    __syncthreads();
+  }
+}
+
+template <int T, int R, int NRG>
+__device__ __forceinline__ void hs_tma_tile(const TmTile& tl, int W, int H, const Img& uo, const Img& vo,
+                                            const float* stage, float* xbuf, bool issue_next, const TmTile& nx,
+                                            const CUtensorMap* mU, const CUtensorMap* mV, const CUtensorMap* mA,
+                                            const CUtensorMap* mB, const CUtensorMap* mC, unsigned bar) {
+  using C = TmCfg<T, R, NRG>;
+  constexpr int SW = C::SW, SH = C::SH, HX = C::HX;
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int sx = 4 * lane, gx = tl.x0 + sx;
+  const int r0 = 1 + rg * R, gy0 = tl.y0 + r0;
+  auto X = [&](int buf, int plane, int g, int which) -> float* {
+    return xbuf + ((buf * 2 + plane) * C::XG + g) * 2 * SW + which * SW + sx;
+  };
+  // ---- staging buffer -> registers -----------------------------------------------------------------------------------
+  float u[R][4], v[R][4];
+  HsCoef<false> k[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int so = (r0 + j) * SW + sx;
+    const float4 qu = *reinterpret_cast<const float4*>(stage + 0 * C::PLANE + so);
+    const float4 qv = *reinterpret_cast<const float4*>(stage + 1 * C::PLANE + so);
+    const float4 a = *reinterpret_cast<const float4*>(stage + 2 * C::PLANE + so);
+    const float4 c = *reinterpret_cast<const float4*>(stage + 3 * C::PLANE + so);
+    const float4 d = *reinterpret_cast<const float4*>(stage + 4 * C::PLANE + so);
+    u[j][0] = qu.x; u[j][1] = qu.y; u[j][2] = qu.z; u[j][3] = qu.w;
+    v[j][0] = qv.x; v[j][1] = qv.y; v[j][2] = qv.z; v[j][3] = qv.w;
+    k[j].c0[0] = a.x; k[j].c0[1] = a.y; k[j].c0[2] = a.z; k[j].c0[3] = a.w;
+    k[j].c1[0] = c.x; k[j].c1[1] = c.y; k[j].c1[2] = c.z; k[j].c1[3] = c.w;
+    k[j].c2[0] = d.x; k[j].c2[1] = d.y; k[j].c2[2] = d.z; k[j].c2[3] = d.w;
+  }
+  // tile halo rows (tile rows 0 and SH-1) -> both exchange buffers; first / last strip row -> buffer 0
+  if (rg == 0) {
+    const float4 a = *reinterpret_cast<const float4*>(stage + 0 * C::PLANE + sx);
+    const float4 c = *reinterpret_cast<const float4*>(stage + 1 * C::PLANE + sx);
+    *reinterpret_cast<float4*>(X(0, 0, 0, 1)) = a;
+    *reinterpret_cast<float4*>(X(0, 1, 0, 1)) = c;
+    *reinterpret_cast<float4*>(X(1, 0, 0, 1)) = a;
+    *reinterpret_cast<float4*>(X(1, 1, 0, 1)) = c;
+  }
+  if (rg == NRG - 1) {
+    const float4 a = *reinterpret_cast<const float4*>(stage + 0 * C::PLANE + (SH - 1) * SW + sx);
+    const float4 c = *reinterpret_cast<const float4*>(stage + 1 * C::PLANE + (SH - 1) * SW + sx);
+    *reinterpret_cast<float4*>(X(0, 0, NRG + 1, 0)) = a;
+    *reinterpret_cast<float4*>(X(0, 1, NRG + 1, 0)) = c;
+    *reinterpret_cast<float4*>(X(1, 0, NRG + 1, 0)) = a;
+    *reinterpret_cast<float4*>(X(1, 1, NRG + 1, 0)) = c;
+  }
+  *reinterpret_cast<float4*>(X(0, 0, rg + 1, 0)) = make_float4(u[0][0], u[0][1], u[0][2], u[0][3]);
+  *reinterpret_cast<float4*>(X(0, 1, rg + 1, 0)) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
+  *reinterpret_cast<float4*>(X(0, 0, rg + 1, 1)) = make_float4(u[R - 1][0], u[R - 1][1], u[R - 1][2], u[R - 1][3]);
+  *reinterpret_cast<float4*>(X(0, 1, rg + 1, 1)) = make_float4(v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3]);
+  __syncthreads();   // every thread has drained the staging buffer; exchange buffer 0 is complete
+  // ---- prefetch the CTA's next tile under this tile's arithmetic ---------------------------------------------------------
+  if (issue_next && threadIdx.x == 0) {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads above -> async-proxy writes below
+    mbar_expect_tx(bar, (unsigned)C::STAGE_BYTES);
+    const unsigned dst = smem_u32(stage);
+    tma_load_3d(dst + 0 * C::PLANE * 4, mU, nx.x0, nx.y0, nx.b, bar);
+    tma_load_3d(dst + 1 * C::PLANE * 4, mV, nx.x0, nx.y0, nx.b, bar);
+    tma_load_3d(dst + 2 * C::PLANE * 4, mA, nx.x0, nx.y0, nx.b, bar);
+    tma_load_3d(dst + 3 * C::PLANE * 4, mB, nx.x0, nx.y0, nx.b, bar);
+    tma_load_3d(dst + 4 * C::PLANE * 4, mC, nx.x0, nx.y0, nx.b, bar);
+  }
+  const HsEdge eg = {false, -1, -1000, -1000};   // unused: the ghost frame carries the boundary condition
+
+  // ---- T sweeps in registers (no boundary code: see hs_tma_ghosts) ----------------------------------------------------------------------------------------------
+#pragma unroll 1
+  for (int s = 0; s < T; ++s) {
+    const int cur = s & 1;
+    float wu[3][6], wv[3][6];
+    hs_row6_smem<false>(X(cur, 0, rg, 1), X(cur, 1, rg, 1), eg, wu[0], wv[0]);         // last row of the group above
+    hs_row6_vals<false>(u[0], v[0], eg, wu[1], wv[1]);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int A = j % 3, B = (j + 1) % 3, Cc = (j + 2) % 3;
+      if (j + 1 < R)
+        hs_row6_vals<false>(u[j + 1], v[j + 1], eg, wu[Cc], wv[Cc]);                   // still the previous sweep's values
+      else
+        hs_row6_smem<false>(X(cur, 0, rg + 2, 0), X(cur, 1, rg + 2, 0), eg, wu[Cc], wv[Cc]);  // first row of the group below
+      float ou[4], ov[4];
+      hs_row_update<false>(wu[A], wu[B], wu[Cc], wv[A], wv[B], wv[Cc], k[j], ou, ov);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { u[j][q] = ou[q]; v[j][q] = ov[q]; }
+    }
+    if (s + 1 < T) {
+      const int nxt = cur ^ 1;
+      *reinterpret_cast<float4*>(X(nxt, 0, rg + 1, 0)) = make_float4(u[0][0], u[0][1], u[0][2], u[0][3]);
+      *reinterpret_cast<float4*>(X(nxt, 1, rg + 1, 0)) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
+      *reinterpret_cast<float4*>(X(nxt, 0, rg + 1, 1)) = make_float4(u[R - 1][0], u[R - 1][1], u[R - 1][2], u[R - 1][3]);
+      *reinterpret_cast<float4*>(X(nxt, 1, rg + 1, 1)) = make_float4(v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3]);
+      __syncthreads();
+    }
+  }
+  // ---- interior cells -> HBM ------------------------------------------------------------------------------------------------
+  float* gU = uo.p + (long)tl.b * uo.stride;
+  float* gV = vo.p + (long)tl.b * vo.stride;
+  const bool in_cols = (sx >= HX) && (sx < SW - HX) && (gx < W);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int sy = r0 + j, gy = gy0 + j;
+    if (in_cols && (sy >= T) && (sy < SH - T) && (gy < H)) {
+      const long go = (long)gy * uo.pitch + gx;
+      *reinterpret_cast<float4*>(gU + go) = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
+      *reinterpret_cast<float4*>(gV + go) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+    }
+  }
+  __syncthreads();   // the exchange buffers are free for the next tile
+}
+
+template <int T, int R, int NRG>
+__global__ void __launch_bounds__(TmCfg<T, R, NRG>::NT, 1)
+hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CUtensorMap mV,
+              const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
+              const __grid_constant__ CUtensorMap mC, Img uo, Img vo, int W, int H, int tiles_x, int tiles_y,
+              int ntiles) {
+  using C = TmCfg<T, R, NRG>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* stage = reinterpret_cast<float*>(smem_raw);
+  float* xbuf = stage + 5 * C::PLANE;
+  const unsigned bar = smem_u32(smem_raw + C::STAGE_BYTES + C::X_BYTES);
+  int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    const TmTile t0 = tm_decode<T, R, NRG>(tile, tiles_x, tiles_y);
+    mbar_expect_tx(bar, (unsigned)C::STAGE_BYTES);
+    const unsigned dst = smem_u32(stage);
+    tma_load_3d(dst + 0 * C::PLANE * 4, &mU, t0.x0, t0.y0, t0.b, bar);
+    tma_load_3d(dst + 1 * C::PLANE * 4, &mV, t0.x0, t0.y0, t0.b, bar);
+    tma_load_3d(dst + 2 * C::PLANE * 4, &mA, t0.x0, t0.y0, t0.b, bar);
+    tma_load_3d(dst + 3 * C::PLANE * 4, &mB, t0.x0, t0.y0, t0.b, bar);
+    tma_load_3d(dst + 4 * C::PLANE * 4, &mC, t0.x0, t0.y0, t0.b, bar);
+  }
+  __syncthreads();
+  unsigned phase = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    const TmTile tl = tm_decode<T, R, NRG>(tile, tiles_x, tiles_y);
+    const int nt = tile + gridDim.x;
+    const bool has_next = nt < ntiles;
+    const TmTile nx = tm_decode<T, R, NRG>(has_next ? nt : tile, tiles_x, tiles_y);
+    const bool edge = (tl.x0 < 0) || (tl.x0 + C::SW > W) || (tl.y0 < 0) || (tl.y0 + C::SH > H);   // CTA-uniform
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    if (edge) hs_tma_ghosts<T, R, NRG>(tl, W, H, stage);
+    hs_tma_tile<T, R, NRG>(tl, W, H, uo, vo, stage, xbuf, has_next, nx, &mU, &mV, &mA, &mB, &mC, bar);
+  }
+}
+
+template <int T, int R, int NRG>
+static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx, const Img& fy,
+                       const Img& ft, int num_sms, cudaStream_t s) {
+  using C = TmCfg<T, R, NRG>;
+  if (ui.W <= C::HX + 1 || ui.H <= T + 1) return false;   // the ghost frame mirrors HX columns / T rows of real cells
+  CUtensorMap mU, mV, mA, mB, mC;
+  if (!make_map(&mU, ui, C::SH) || !make_map(&mV, vi, C::SH) || !make_map(&mA, fx, C::SH) ||
+      !make_map(&mB, fy, C::SH) || !make_map(&mC, ft, C::SH))
+    return false;
+  auto kern = hs_tma_kernel<T, R, NRG>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const int tiles_x = (ui.W + C::TW - 1) / C::TW, tiles_y = (ui.H + C::TH - 1) / C::TH;
+  const long ntiles = (long)tiles_x * tiles_y * ui.batch;
+  if (ntiles > 0x7fffffffL) return false;
+  const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+  kern<<<grid, C::NT, C::SMEM_BYTES, s>>>(mU, mV, mA, mB, mC, uo, vo, ui.W, ui.H, tiles_x, tiles_y, (int)ntiles);
+  return true;
+}
+
+template <int T>
+static bool launch_T(int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
+                     const Img& fy, const Img& ft, int num_sms, cudaStream_t s) {
+  switch (variant) {
+    default:
+    case 24: return launch_cfg<T, 8, 8>(ui, vi, uo, vo, fx, fy, ft, num_sms, s);     // 66 x 128, 256 threads
+    case 25: return launch_cfg<T, 6, 8>(ui, vi, uo, vo, fx, fy, ft, num_sms, s);     // 50 x 128, 256 threads
+    case 26: return launch_cfg<T, 4, 12>(ui, vi, uo, vo, fx, fy, ft, num_sms, s);    // 50 x 128, 384 threads
+    case 27: return launch_cfg<T, 6, 10>(ui, vi, uo, vo, fx, fy, ft, num_sms, s);    // 62 x 128, 320 threads
+  }
+}
+
+// T in {4, 6, 8}.  Returns false if this kernel cannot run (other T, no driver entry point, map encoding failed): the
+// caller then uses the non-persistent kernels.
+bool launch_hs_tma(int T, int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
+                   const Img& fy, const Img& ft, cudaStream_t s) {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  switch (T) {
+    case 4: return launch_T<4>(variant, ui, vi, uo, vo, fx, fy, ft, num_sms, s);
+    case 6: return launch_T<6>(variant, ui, vi, uo, vo, fx, fy, ft, num_sms, s);
+    case 8: return launch_T<8>(variant, ui, vi, uo, vo, fx, fy, ft, num_sms, s);
+    default: return false;
+  }
+}
+
+}  // namespace ofri
