@@ -559,11 +559,11 @@ static void launch_hs_regs_T(int variant, const Img& ui, const Img& vi, const Im
 
 static void launch_hs_fused(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo,
                             const Img& vo, const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
-  if (variant >= 8 && precise) variant = 2;   // the register-resident kernels are built for the fast arithmetic only
   if (variant >= 24) {                        // persistent TMA-fed register-resident kernel (ofri_hs_tma.cu)
-    if (launch_hs_tma(T, variant, ui, vi, uo, vo, fx, fy, ft, s)) return;
-    variant = 8;                              // other T / no tensor-map support: non-persistent register kernel
+    if (launch_hs_tma(T, variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, s)) return;
+    variant = 8;                              // other T / no tensor-map support: non-persistent kernels
   }
+  if (variant >= 8 && precise) variant = 2;   // the other register-resident kernels are built for the fast arithmetic only
   if (variant >= 16) {                        // packed-f32x2 register-resident kernel (ofri_hs_pk.cu)
     launch_hs_packed(T, variant, ui, vi, uo, vo, fx, fy, ft, s);
     return;

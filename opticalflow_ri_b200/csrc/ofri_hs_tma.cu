@@ -265,12 +265,182 @@ __device__ __forceinline__ void hs_tma_tile(const TmTile& tl, int W, int H, cons
   __syncthreads();   // the exchange buffers are free for the next tile
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// PRECISE tile body: the reference's arithmetic bit for bit (float64-accumulated stencil rounded once, separately
+// rounded float32 update with a correctly rounded division: hs_avg_cols_precise + hs_update_precise).  The strip's
+// U, V live in registers as DOUBLES (exact images of the float32 values), so a value is widened once per sweep
+// instead of once per use; halo columns are exchanged as doubles by shuffle, the rows above / below as float32
+// through the same shared exchange array.  Coefficient planes are the RAW fx, fy, ft; den and 1/den per strip cell
+// are computed once per launch.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_up_d(double x) {
+  int lo = __double2loint(x), hi = __double2hiint(x);
+  lo = __shfl_up_sync(0xffffffffu, lo, 1);
+  hi = __shfl_up_sync(0xffffffffu, hi, 1);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_down_d(double x) {
+  int lo = __double2loint(x), hi = __double2hiint(x);
+  lo = __shfl_down_sync(0xffffffffu, lo, 1);
+  hi = __shfl_down_sync(0xffffffffu, hi, 1);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ void row6_state_d(const double (&ru)[4], const double (&rv)[4], double (&du)[6],
+                                             double (&dv)[6]) {
+  du[1] = ru[0]; du[2] = ru[1]; du[3] = ru[2]; du[4] = ru[3];
+  dv[1] = rv[0]; dv[2] = rv[1]; dv[3] = rv[2]; dv[4] = rv[3];
+  du[0] = shfl_up_d(ru[3]);
+  du[5] = shfl_down_d(ru[0]);
+  dv[0] = shfl_up_d(rv[3]);
+  dv[5] = shfl_down_d(rv[0]);
+}
+__device__ __forceinline__ void row6_smem_d(const float* __restrict__ pu, const float* __restrict__ pv, double (&du)[6],
+                                            double (&dv)[6]) {
+  const float4 qu = *reinterpret_cast<const float4*>(pu);
+  const float4 qv = *reinterpret_cast<const float4*>(pv);
+  const float ul = __shfl_up_sync(0xffffffffu, qu.w, 1), ur = __shfl_down_sync(0xffffffffu, qu.x, 1);
+  const float vl = __shfl_up_sync(0xffffffffu, qv.w, 1), vr = __shfl_down_sync(0xffffffffu, qv.x, 1);
+  du[0] = (double)ul; du[1] = (double)qu.x; du[2] = (double)qu.y; du[3] = (double)qu.z; du[4] = (double)qu.w; du[5] = (double)ur;
+  dv[0] = (double)vl; dv[1] = (double)qv.x; dv[2] = (double)qv.y; dv[3] = (double)qv.z; dv[4] = (double)qv.w; dv[5] = (double)vr;
+}
+struct HsCoefP { float fx[4], fy[4], ft[4], den[4], rcp[4]; };
+__device__ __forceinline__ void row_update_d(const double (&uu)[6], const double (&um)[6], const double (&ud)[6],
+                                             const double (&vu)[6], const double (&vm)[6], const double (&vd)[6],
+                                             const HsCoefP& k, float (&ou)[4], float (&ov)[4]) {
+  double vsu[6], vsv[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    vsu[c] = dadd(uu[c], ud[c]);
+    vsv[c] = dadd(vu[c], vd[c]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float ua = hs_avg_cols_precise(vsu[q], vsu[q + 1], vsu[q + 2], um[q], um[q + 2]);
+    const float va = hs_avg_cols_precise(vsv[q], vsv[q + 1], vsv[q + 2], vm[q], vm[q + 2]);
+    hs_update_precise(ua, va, k.fx[q], k.fy[q], k.ft[q], k.den[q], k.rcp[q], &ou[q], &ov[q]);
+  }
+}
+
 template <int T, int R, int NRG>
+__device__ __forceinline__ void hs_tma_tile_precise(const TmTile& tl, int W, int H, const Img& uo, const Img& vo,
+                                                    const float* stage, float* xbuf, bool issue_next,
+                                                    const TmTile& nx, const CUtensorMap* mU, const CUtensorMap* mV,
+                                                    const CUtensorMap* mA, const CUtensorMap* mB,
+                                                    const CUtensorMap* mC, unsigned bar, float alpha2) {
+  using C = TmCfg<T, R, NRG>;
+  constexpr int SW = C::SW, SH = C::SH, HX = C::HX;
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int sx = 4 * lane, gx = tl.x0 + sx;
+  const int r0 = 1 + rg * R, gy0 = tl.y0 + r0;
+  auto X = [&](int buf, int plane, int g, int which) -> float* {
+    return xbuf + ((buf * 2 + plane) * C::XG + g) * 2 * SW + which * SW + sx;
+  };
+  double u[R][4], v[R][4];
+  HsCoefP k[R];
+  float4 eu0, ev0, eu1, ev1;      // float32 copies of the strip's first / last row (what gets published)
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int so = (r0 + j) * SW + sx;
+    const float4 qu = *reinterpret_cast<const float4*>(stage + 0 * C::PLANE + so);
+    const float4 qv = *reinterpret_cast<const float4*>(stage + 1 * C::PLANE + so);
+    const float4 a = *reinterpret_cast<const float4*>(stage + 2 * C::PLANE + so);
+    const float4 c = *reinterpret_cast<const float4*>(stage + 3 * C::PLANE + so);
+    const float4 d = *reinterpret_cast<const float4*>(stage + 4 * C::PLANE + so);
+    u[j][0] = (double)qu.x; u[j][1] = (double)qu.y; u[j][2] = (double)qu.z; u[j][3] = (double)qu.w;
+    v[j][0] = (double)qv.x; v[j][1] = (double)qv.y; v[j][2] = (double)qv.z; v[j][3] = (double)qv.w;
+    if (j == 0) { eu0 = qu; ev0 = qv; }
+    if (j == R - 1) { eu1 = qu; ev1 = qv; }
+    k[j].fx[0] = a.x; k[j].fx[1] = a.y; k[j].fx[2] = a.z; k[j].fx[3] = a.w;
+    k[j].fy[0] = c.x; k[j].fy[1] = c.y; k[j].fy[2] = c.z; k[j].fy[3] = c.w;
+    k[j].ft[0] = d.x; k[j].ft[1] = d.y; k[j].ft[2] = d.z; k[j].ft[3] = d.w;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      k[j].den[q] = hs_den(k[j].fx[q], k[j].fy[q], alpha2);
+      k[j].rcp[q] = rcp_rn(k[j].den[q]);
+    }
+  }
+  if (rg == 0) {
+    const float4 a = *reinterpret_cast<const float4*>(stage + 0 * C::PLANE + sx);
+    const float4 c = *reinterpret_cast<const float4*>(stage + 1 * C::PLANE + sx);
+    *reinterpret_cast<float4*>(X(0, 0, 0, 1)) = a;
+    *reinterpret_cast<float4*>(X(0, 1, 0, 1)) = c;
+    *reinterpret_cast<float4*>(X(1, 0, 0, 1)) = a;
+    *reinterpret_cast<float4*>(X(1, 1, 0, 1)) = c;
+  }
+  if (rg == NRG - 1) {
+    const float4 a = *reinterpret_cast<const float4*>(stage + 0 * C::PLANE + (SH - 1) * SW + sx);
+    const float4 c = *reinterpret_cast<const float4*>(stage + 1 * C::PLANE + (SH - 1) * SW + sx);
+    *reinterpret_cast<float4*>(X(0, 0, NRG + 1, 0)) = a;
+    *reinterpret_cast<float4*>(X(0, 1, NRG + 1, 0)) = c;
+    *reinterpret_cast<float4*>(X(1, 0, NRG + 1, 0)) = a;
+    *reinterpret_cast<float4*>(X(1, 1, NRG + 1, 0)) = c;
+  }
+  *reinterpret_cast<float4*>(X(0, 0, rg + 1, 0)) = eu0;
+  *reinterpret_cast<float4*>(X(0, 1, rg + 1, 0)) = ev0;
+  *reinterpret_cast<float4*>(X(0, 0, rg + 1, 1)) = eu1;
+  *reinterpret_cast<float4*>(X(0, 1, rg + 1, 1)) = ev1;
+  __syncthreads();
+  if (issue_next && threadIdx.x == 0) {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    mbar_expect_tx(bar, (unsigned)C::STAGE_BYTES);
+    const unsigned dst = smem_u32(stage);
+    tma_load_3d(dst + 0 * C::PLANE * 4, mU, nx.x0, nx.y0, nx.b, bar);
+    tma_load_3d(dst + 1 * C::PLANE * 4, mV, nx.x0, nx.y0, nx.b, bar);
+    tma_load_3d(dst + 2 * C::PLANE * 4, mA, nx.x0, nx.y0, nx.b, bar);
+    tma_load_3d(dst + 3 * C::PLANE * 4, mB, nx.x0, nx.y0, nx.b, bar);
+    tma_load_3d(dst + 4 * C::PLANE * 4, mC, nx.x0, nx.y0, nx.b, bar);
+  }
+  float* gU = uo.p + (long)tl.b * uo.stride;
+  float* gV = vo.p + (long)tl.b * vo.stride;
+  const bool in_cols = (sx >= HX) && (sx < SW - HX) && (gx < W);
+#pragma unroll 1
+  for (int s = 0; s < T; ++s) {
+    const int cur = s & 1;
+    const bool last = s + 1 == T;
+    double wu[3][6], wv[3][6];
+    row6_smem_d(X(cur, 0, rg, 1), X(cur, 1, rg, 1), wu[0], wv[0]);
+    row6_state_d(u[0], v[0], wu[1], wv[1]);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int A = j % 3, B = (j + 1) % 3, Cc = (j + 2) % 3;
+      if (j + 1 < R)
+        row6_state_d(u[j + 1], v[j + 1], wu[Cc], wv[Cc]);
+      else
+        row6_smem_d(X(cur, 0, rg + 2, 0), X(cur, 1, rg + 2, 0), wu[Cc], wv[Cc]);
+      float ou[4], ov[4];
+      row_update_d(wu[A], wu[B], wu[Cc], wv[A], wv[B], wv[Cc], k[j], ou, ov);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { u[j][q] = (double)ou[q]; v[j][q] = (double)ov[q]; }
+      if (j == 0) { eu0 = make_float4(ou[0], ou[1], ou[2], ou[3]); ev0 = make_float4(ov[0], ov[1], ov[2], ov[3]); }
+      if (j == R - 1) { eu1 = make_float4(ou[0], ou[1], ou[2], ou[3]); ev1 = make_float4(ov[0], ov[1], ov[2], ov[3]); }
+      if (last) {                                  // interior cells -> HBM straight from the float32 results
+        const int sy = r0 + j, gy = gy0 + j;
+        if (in_cols && (sy >= T) && (sy < SH - T) && (gy < H)) {
+          const long go = (long)gy * uo.pitch + gx;
+          *reinterpret_cast<float4*>(gU + go) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+          *reinterpret_cast<float4*>(gV + go) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        }
+      }
+    }
+    if (!last) {
+      const int nxt = cur ^ 1;
+      *reinterpret_cast<float4*>(X(nxt, 0, rg + 1, 0)) = eu0;
+      *reinterpret_cast<float4*>(X(nxt, 1, rg + 1, 0)) = ev0;
+      *reinterpret_cast<float4*>(X(nxt, 0, rg + 1, 1)) = eu1;
+      *reinterpret_cast<float4*>(X(nxt, 1, rg + 1, 1)) = ev1;
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+}
+
+template <int T, int R, int NRG, bool PRECISE>
 __global__ void __launch_bounds__(TmCfg<T, R, NRG>::NT, 1)
 hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CUtensorMap mV,
               const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
               const __grid_constant__ CUtensorMap mC, Img uo, Img vo, int W, int H, int tiles_x, int tiles_y,
-              int ntiles) {
+              int ntiles, float alpha2) {
   using C = TmCfg<T, R, NRG>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage = reinterpret_cast<float*>(smem_raw);
@@ -302,20 +472,23 @@ hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CU
     mbar_wait(bar, phase);
     phase ^= 1;
     if (edge) hs_tma_ghosts<T, R, NRG>(tl, W, H, stage);
-    hs_tma_tile<T, R, NRG>(tl, W, H, uo, vo, stage, xbuf, has_next, nx, &mU, &mV, &mA, &mB, &mC, bar);
+    if constexpr (PRECISE)
+      hs_tma_tile_precise<T, R, NRG>(tl, W, H, uo, vo, stage, xbuf, has_next, nx, &mU, &mV, &mA, &mB, &mC, bar, alpha2);
+    else
+      hs_tma_tile<T, R, NRG>(tl, W, H, uo, vo, stage, xbuf, has_next, nx, &mU, &mV, &mA, &mB, &mC, bar);
   }
 }
 
-template <int T, int R, int NRG>
+template <int T, int R, int NRG, bool PRECISE>
 static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx, const Img& fy,
-                       const Img& ft, int num_sms, cudaStream_t s) {
+                       const Img& ft, float alpha2, int num_sms, cudaStream_t s) {
   using C = TmCfg<T, R, NRG>;
   if (ui.W <= C::HX + 1 || ui.H <= T + 1) return false;   // the ghost frame mirrors HX columns / T rows of real cells
   CUtensorMap mU, mV, mA, mB, mC;
   if (!make_map(&mU, ui, C::SH) || !make_map(&mV, vi, C::SH) || !make_map(&mA, fx, C::SH) ||
       !make_map(&mB, fy, C::SH) || !make_map(&mC, ft, C::SH))
     return false;
-  auto kern = hs_tma_kernel<T, R, NRG>;
+  auto kern = hs_tma_kernel<T, R, NRG, PRECISE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
     cudaGetLastError();
     return false;
@@ -324,26 +497,29 @@ static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& v
   const long ntiles = (long)tiles_x * tiles_y * ui.batch;
   if (ntiles > 0x7fffffffL) return false;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-  kern<<<grid, C::NT, C::SMEM_BYTES, s>>>(mU, mV, mA, mB, mC, uo, vo, ui.W, ui.H, tiles_x, tiles_y, (int)ntiles);
+  kern<<<grid, C::NT, C::SMEM_BYTES, s>>>(mU, mV, mA, mB, mC, uo, vo, ui.W, ui.H, tiles_x, tiles_y, (int)ntiles,
+                                          alpha2);
   return true;
 }
 
 template <int T>
-static bool launch_T(int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
-                     const Img& fy, const Img& ft, int num_sms, cudaStream_t s) {
+static bool launch_T(int variant, bool precise, const Img& ui, const Img& vi, const Img& uo, const Img& vo,
+                     const Img& fx, const Img& fy, const Img& ft, float alpha2, int num_sms, cudaStream_t s) {
+  if (precise)   // doubles in registers: 4-row strips, 34 x 128 tile, 256 threads
+    return launch_cfg<T, 4, 8, true>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);
   switch (variant) {
     default:
-    case 24: return launch_cfg<T, 8, 8>(ui, vi, uo, vo, fx, fy, ft, num_sms, s);     // 66 x 128, 256 threads
-    case 25: return launch_cfg<T, 6, 8>(ui, vi, uo, vo, fx, fy, ft, num_sms, s);     // 50 x 128, 256 threads
-    case 26: return launch_cfg<T, 4, 12>(ui, vi, uo, vo, fx, fy, ft, num_sms, s);    // 50 x 128, 384 threads
-    case 27: return launch_cfg<T, 6, 10>(ui, vi, uo, vo, fx, fy, ft, num_sms, s);    // 62 x 128, 320 threads
+    case 24: return launch_cfg<T, 8, 8, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);     // 66 x 128, 256 threads
+    case 25: return launch_cfg<T, 6, 8, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);     // 50 x 128, 256 threads
+    case 26: return launch_cfg<T, 4, 12, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);    // 50 x 128, 384 threads
+    case 27: return launch_cfg<T, 6, 10, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);    // 62 x 128, 320 threads
   }
 }
 
 // T in {4, 6, 8}.  Returns false if this kernel cannot run (other T, no driver entry point, map encoding failed): the
 // caller then uses the non-persistent kernels.
-bool launch_hs_tma(int T, int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
-                   const Img& fy, const Img& ft, cudaStream_t s) {
+bool launch_hs_tma(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo, const Img& vo,
+                   const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -352,9 +528,9 @@ bool launch_hs_tma(int T, int variant, const Img& ui, const Img& vi, const Img& 
     if (num_sms <= 0) num_sms = 148;
   }
   switch (T) {
-    case 4: return launch_T<4>(variant, ui, vi, uo, vo, fx, fy, ft, num_sms, s);
-    case 6: return launch_T<6>(variant, ui, vi, uo, vo, fx, fy, ft, num_sms, s);
-    case 8: return launch_T<8>(variant, ui, vi, uo, vo, fx, fy, ft, num_sms, s);
+    case 4: return launch_T<4>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);
+    case 6: return launch_T<6>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);
+    case 8: return launch_T<8>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);
     default: return false;
   }
 }

@@ -76,8 +76,8 @@ int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb
 void launch_hs_packed(int T, int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
                       const Img& fy, const Img& ft, cudaStream_t s);
 // persistent TMA-fed register-resident fused sweeps (ofri_hs_tma.cu); false = not applicable, use another kernel
-bool launch_hs_tma(int T, int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
-                   const Img& fy, const Img& ft, cudaStream_t s);
+bool launch_hs_tma(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo, const Img& vo,
+                   const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s);
 // err[b] = (sqrt(sum (u-u0)^2) + sqrt(sum (v-v0)^2)) / (H*W); u0.p == nullptr means u0 = v0 = 0.  acc: [batch][2] f64 scratch
 void launch_hs_error(const Img& u, const Img& v, const Img& u0, const Img& v0, double* acc, float* err, int err_stride,
                      cudaStream_t s, LaunchCounter& lc);

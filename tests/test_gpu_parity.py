@@ -187,7 +187,7 @@ def test_hs_fused_bit_identical_to_simple(h, shape):
             h.set_option("hs_fuse", 0)
             Ur, Vr = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
             for T in (1, 2, 3, 4, 5, 6, 8):
-                for variant in (range(28) if precise == 0 else [0]):
+                for variant in (range(28) if precise == 0 else [0, 2, 24]):
                     h.set_option("hs_fuse", T)
                     h.set_option("hs_variant", variant)
                     U, V = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
@@ -198,7 +198,7 @@ def test_hs_fused_bit_identical_to_simple(h, shape):
                         raise AssertionError("precise=%d T=%d variant=%d shape=%s: %s" % (precise, T, variant, shape, e))
     finally:
         h.set_option("hs_fuse", 4)
-        h.set_option("hs_variant", 4)
+        h.set_option("hs_variant", 24)
         h.set_option("hs_precise", 1)
 
 
