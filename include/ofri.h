@@ -161,6 +161,34 @@ OFRI_API int ofri_hs_iterate(ofri_handle h, const float* u0, const float* v0, co
 OFRI_API int ofri_ls_coefficients(ofri_handle h, const float* im1, const float* im2, int batch, int H, int W, float hpar,
                          float* coef);
 
+/* ---- row-band domain decomposition: ONE very large frame pair over several GPUs -----------------------------------
+ * New work (the reference is single-process; BASELINE.json configs[4]).  One handle per GPU; the handles of one job
+ * share a communicator: NCCL (one process per GPU: rank 0 calls ofri_nccl_unique_id and ships the 128 bytes to the
+ * other ranks, e.g. with torch.distributed.broadcast) or "local" (one process, one host thread per band, any number
+ * of bands per GPU -- used by the band-invariance tests).  Rank r owns rows [own0, own1) of the frame and must supply
+ * rows [in0, in1) of both frames (owned rows plus the halo the pyramid needs); ofri_band_plan tells both.
+ * Requirements: k_levels == 1, warping == bilinear == 1 when pyramid_levels > 1, H divisible by
+ * nranks * 2^(pyramid_levels-1).  Owned rows of the result are bit-identical to ofri_pyramidal_flow_dev's. */
+typedef struct {
+  int32_t rank, nranks;
+  int32_t own0, own1;     /* rows of the frame this rank owns (and returns) */
+  int32_t in0, in1;       /* rows of the input frames this rank must be given */
+  int32_t ghost;          /* ghost rows per side of the per-level arrays */
+  int32_t exchange;       /* Horn-Schunck sweeps between two ghost-row exchanges */
+} ofri_band;
+OFRI_API int ofri_nccl_unique_id(void* out128);
+OFRI_API int ofri_comm_init_nccl(ofri_handle h, int rank, int nranks, const void* uid128);
+OFRI_API int ofri_local_group_create(int nranks, void** group);
+OFRI_API int ofri_local_group_destroy(void* group);
+OFRI_API int ofri_comm_init_local(ofri_handle h, void* group, int rank);   /* call from the thread that drives `rank` */
+OFRI_API int ofri_comm_destroy(ofri_handle h);
+OFRI_API int ofri_band_plan(ofri_handle h, int H, int W, const ofri_params* p, int rank, int nranks, ofri_band* out);
+/* d_im*_rows: DEVICE, rows [in0, in1) of the frames, dense (pitch W); d_u_rows / d_v_rows: DEVICE, rows [own0, own1);
+ * d_err_out: optional DEVICE [levels][2].  Collective: every rank of the communicator must call it.  Synchronises the
+ * handle's stream before returning. */
+OFRI_API int ofri_pyramidal_flow_banded_dev(ofri_handle h, const float* d_im1_rows, const float* d_im2_rows, int H, int W,
+                                   const ofri_params* p, float* d_u_rows, float* d_v_rows, float* d_err_out);
+
 #ifdef __cplusplus
 }
 #endif

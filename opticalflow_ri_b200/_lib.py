@@ -38,6 +38,11 @@ class Params(C.Structure):
                 ("main_algo", Algo), ("opt_algo", Algo)]
 
 
+class Band(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("own0", C.c_int32), ("own1", C.c_int32),
+                ("in0", C.c_int32), ("in1", C.c_int32), ("ghost", C.c_int32), ("exchange", C.c_int32)]
+
+
 _fp = C.POINTER(C.c_float)
 _H = C.c_void_p
 _SIGNATURES = {
@@ -69,6 +74,15 @@ _SIGNATURES = {
     "ofri_hs_derivatives": (C.c_int, [_H, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
     "ofri_hs_iterate": (C.c_int, [_H, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp]),
     "ofri_ls_coefficients": (C.c_int, [_H, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),
+    "ofri_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "ofri_comm_init_nccl": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
+    "ofri_local_group_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "ofri_local_group_destroy": (C.c_int, [C.c_void_p]),
+    "ofri_comm_init_local": (C.c_int, [_H, C.c_void_p, C.c_int]),
+    "ofri_comm_destroy": (C.c_int, [_H]),
+    "ofri_band_plan": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(Params), C.c_int, C.c_int, C.POINTER(Band)]),
+    "ofri_pyramidal_flow_banded_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Params),
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import ALGO_HS, ALGO_LS, ALGO_NONE, Algo, OfriError, Params
+from ._lib import ALGO_HS, ALGO_LS, ALGO_NONE, Algo, Band, OfriError, Params
 
 _EXC = {_lib.ERR_INVALID: ValueError, _lib.ERR_ALPHAS: IndexError, _lib.ERR_FILTER_OPT: TypeError,
         _lib.ERR_TOO_SMALL: ValueError, _lib.ERR_UNSUPPORTED: NotImplementedError, _lib.ERR_OOM: MemoryError}
@@ -172,6 +172,28 @@ class Handle:
         fn = self._L.ofri_pyramidal_flow_dev if device else self._L.ofri_pyramidal_flow
         self._check(fn(self._h, im1_ptr, im2_ptr, int(batch), int(H), int(W), C.byref(params), u_ptr, v_ptr, err_ptr))
 
+    # -- row-band mode: one very large pair over several handles / GPUs ----------------------------------------------
+    def comm_init_nccl(self, rank, nranks, uid_bytes):
+        buf = C.create_string_buffer(bytes(uid_bytes), 128)
+        self._check(self._L.ofri_comm_init_nccl(self._h, int(rank), int(nranks), buf))
+
+    def comm_init_local(self, group, rank):
+        self._check(self._L.ofri_comm_init_local(self._h, group, int(rank)))
+
+    def comm_destroy(self):
+        self._check(self._L.ofri_comm_destroy(self._h))
+
+    def band_plan(self, H, W, params, rank, nranks):
+        b = Band()
+        self._check(self._L.ofri_band_plan(self._h, int(H), int(W), C.byref(params), int(rank), int(nranks), C.byref(b)))
+        return b
+
+    def pyramidal_flow_banded_ptr(self, im1_rows_ptr, im2_rows_ptr, H, W, params, u_rows_ptr, v_rows_ptr, err_ptr=None):
+        """DEVICE pointers: rows [in0, in1) of the frames in, rows [own0, own1) of the flow out (see band_plan).
+        Collective over the handle's communicator."""
+        self._check(self._L.ofri_pyramidal_flow_banded_dev(self._h, im1_rows_ptr, im2_rows_ptr, int(H), int(W),
+                                                           C.byref(params), u_rows_ptr, v_rows_ptr, err_ptr))
+
     # -- adapters ------------------------------------------------------------------------------------------------
     def hs_compute(self, im1, im2, U0, V0, alpha, niter):
         a, single = _batched(im1)
@@ -277,6 +299,32 @@ class Handle:
         coef = np.empty((8, B, H, W), np.float32)
         self._check(self._L.ofri_ls_coefficients(self._h, _ptr(a), _ptr(b), B, H, W, float(np.float32(h)), _ptr(coef)))
         return coef[:, 0] if single else coef
+
+
+def nccl_unique_id():
+    """128 opaque bytes from ncclGetUniqueId (rank 0 creates them and ships them to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    rc = _lib.lib().ofri_nccl_unique_id(buf)
+    if rc != 0:
+        raise OfriError(rc, _lib.lib().ofri_last_error(None).decode())
+    return buf.raw
+
+
+class LocalGroup:
+    """Rendezvous object of the single-process 'local' communicator: N bands driven by N host threads."""
+
+    def __init__(self, nranks):
+        self._L = _lib.lib()
+        self.ptr = C.c_void_p()
+        rc = self._L.ofri_local_group_create(int(nranks), C.byref(self.ptr))
+        if rc != 0:
+            raise OfriError(rc, self._L.ofri_last_error(None).decode())
+        self.nranks = int(nranks)
+
+    def close(self):
+        if self.ptr:
+            self._L.ofri_local_group_destroy(self.ptr)
+            self.ptr = None
 
 
 _default = {}

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libofri.so")
-SOURCES = ["ofri_api.cu", "ofri_stages.cu", "ofri_hs.cu", "ofri_hs_pk.cu", "ofri_hs_tma.cu", "ofri_ls.cu"]
+SOURCES = ["ofri_api.cu", "ofri_stages.cu", "ofri_hs.cu", "ofri_hs_pk.cu", "ofri_hs_tma.cu", "ofri_ls.cu", "ofri_comm.cu"]
 HEADERS = ["ofri_internal.h", "ofri_pixel.cuh", "ofri_hs_common.cuh", "ofri_tables.h", os.path.join("..", "..", "include", "ofri.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--cudart", "static"]
@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % s)
-    cmd = [nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    cmd = [nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -46,6 +46,10 @@ struct ofri_ctx {
   // options
   int hs_fuse = 4, hs_variant = 24, ls_fuse = 2, ls_variant = 4, chunk_pairs = 0, timing = 0;
   int hs_precise = 1;   // 0 = fast f32/FMA everywhere, 1 = reference arithmetic on the coarse pyramid levels, 2 = everywhere
+  // row-band (domain-decomposed) mode
+  ofri::Comm* comm = nullptr;
+  int band_exchange = 16;   // Horn-Schunck sweeps between two ghost-row exchanges (rounded up to a multiple of hs_fuse)
+  int band_reach = 8;       // rows the warp may reach beyond a band's ghost frame (>= max |v| / 2 + 2)
   // timings of the last call
   std::vector<StageTime> times;
   std::vector<std::pair<std::string, float>> times_ms;
@@ -612,6 +616,376 @@ int finish(ofri_handle h) {
   if ((batch) < 1 || (H) < 1 || (W) < 1) return fail(h, OFRI_ERR_INVALID, "batch, H, W must be >= 1"); \
   if ((batch) > 65535) return fail(h, OFRI_ERR_INVALID, "batch > 65535 per call");
 
+
+// =====================================================================================================================
+// Row-band domain decomposition: ONE very large frame pair split over the ranks of a communicator.
+// =====================================================================================================================
+// Rank r owns rows [r H/n, (r+1) H/n) of the frame (and the halved ranges on the coarser pyramid levels).  Every
+// per-level array of a rank covers its EXTENDED band = owned rows +- G ghost rows (clipped at the image border) and is
+// treated by the stage kernels as a stand-alone image: the kernels need no band logic, a boundary rule applied at an
+// artificial band edge only spoils the outermost ghost rows, and every stage shrinks the valid part of the ghost frame
+// by its radius.  G = E + 2 + Rw covers: E Horn-Schunck sweeps between two ghost-row exchanges, the 2x2 derivative and
+// 3-tap Gaussian rows, and the rows the bilinear warp may reach (Rw, checked at run time).  What is NOT halo-local:
+//   * ghost rows of (U, V) are refreshed from the neighbours' owned rows every E sweeps (Comm::exchange);
+//   * Liu-Shen's image maxima (LS:96-97) and per-sweep residual sums (LS:79, 141) and Horn-Schunck's error sums
+//     (HS:100) are all-reduced, so every rank takes the same decisions and reports the same scalars;
+//   * the spline up-sample solves along whole columns: the owned coarse rows are all-gathered and every rank solves the
+//     (small) coarse system redundantly, then evaluates only its own band;
+//   * Pillow's resample and the warp use GLOBAL row coordinates (tap tables of the whole image; float32 rounding of
+//     y +- v/2 depends on the magnitude of y).
+// Owned rows are therefore bit-identical to the single-GPU result (tested with N virtual bands on one GPU).
+struct BandLevel { int Hl, Wl, own0, own1, ext0, ext1; };
+struct BandPlanInt {
+  int L = 0, E = 0, Rw = 0, G = 0, in0 = 0, in1 = 0;
+  BandLevel lv[16];
+};
+
+int make_band_plan(ofri_handle h, int H, int W, const ofri_params* p, int rank, int n, BandPlanInt* bp) {
+  int rc = check_params(h, p, H, W);
+  if (rc) return rc;
+  if (n < 1 || rank < 0 || rank >= n) return fail(h, OFRI_ERR_INVALID, "bad rank %d of %d", rank, n);
+  const int L = p->pyramid_levels;
+  if (p->k_levels != 1) return fail(h, OFRI_ERR_UNSUPPORTED, "row-band mode supports kLevels = 1 only");
+  if (L > 1 && (!p->warping || !p->bilinear))
+    return fail(h, OFRI_ERR_UNSUPPORTED, "row-band mode needs warping = biLinear = True");
+  const int fmax = 1 << (L - 1);
+  if (H % (n * fmax) != 0)
+    return fail(h, OFRI_ERR_UNSUPPORTED, "row-band mode needs H (%d) divisible by ranks x 2^(levels-1) = %d", H, n * fmax);
+  int T = h->hs_fuse > 0 ? (h->hs_fuse == 7 ? 6 : (h->hs_fuse > 8 ? 8 : h->hs_fuse)) : 1;
+  int E = h->band_exchange > 0 ? h->band_exchange : 16;
+  E = (E + T - 1) / T * T;
+  bp->L = L;
+  bp->E = E;
+  bp->Rw = h->band_reach > 0 ? h->band_reach : 8;
+  bp->G = E + 2 + bp->Rw;
+  double scale = 1.0 / std::pow(2.0, L - 1);
+  long in0 = H, in1 = 0;
+  for (int l = 0; l < L; ++l) {
+    const int f = 1 << (L - 1 - l);
+    BandLevel& b = bp->lv[l];
+    b.Hl = H / f;
+    b.Wl = l == L - 1 ? W : level_size(W, scale);
+    const int per = b.Hl / n;
+    if (n > 1 && per < E)
+      return fail(h, OFRI_ERR_TOO_SMALL, "row-band mode: level %d has %d rows per rank, fewer than the %d-row exchange", l + 1,
+                  per, E);
+    b.own0 = rank * per;
+    b.own1 = b.own0 + per;
+    b.ext0 = b.own0 - bp->G < 0 ? 0 : b.own0 - bp->G;
+    b.ext1 = b.own1 + bp->G > b.Hl ? b.Hl : b.own1 + bp->G;
+    long lo = (long)f * b.ext0 - (f > 1 ? 2L * f : 0), hi = (long)f * (b.ext1 - 1) + (f > 1 ? 3L * f : 1);
+    if (lo < in0) in0 = lo;
+    if (hi > in1) in1 = hi;
+    scale *= 2.0;
+  }
+  bp->in0 = in0 < 0 ? 0 : (int)in0;
+  bp->in1 = in1 > H ? H : (int)in1;
+  return OFRI_OK;
+}
+
+struct BandWs {
+  Img lvl1, lvl2, warp1, warp2, work1, work2, opt1, opt2, tmp, fx, fy, ft, U[2], V[2], U0, V0, Uacc, Vacc, us, vs, gU, gV;
+  LsPlanes ls;
+  ImgD M1, T1, M2;
+  double* hs_acc = nullptr;
+  double* ls_errs = nullptr;
+  int* ls_state = nullptr;
+  unsigned* ls_max = nullptr;
+  int* flag = nullptr;
+};
+void plan_band_ws(Bump& b, const BandPlanInt& bp, int W, const ofri_params* p, BandWs* ws) {
+  const BandLevel& f = bp.lv[bp.L - 1];
+  const int rows = f.ext1 - f.ext0, in_rows = bp.in1 - bp.in0;
+  const bool multi = bp.L > 1;
+  const bool has_opt = p->opt_algo.kind != OFRI_ALGO_NONE;
+  const bool has_ls = p->main_algo.kind == OFRI_ALGO_LS || p->opt_algo.kind == OFRI_ALGO_LS;
+  const bool has_hs = p->main_algo.kind == OFRI_ALGO_HS || p->opt_algo.kind == OFRI_ALGO_HS;
+  if (multi) {
+    ws->lvl1 = b.plane(1, rows, W); ws->lvl2 = b.plane(1, rows, W);
+    ws->warp1 = b.plane(1, rows, W); ws->warp2 = b.plane(1, rows, W);
+    ws->tmp = b.plane(1, in_rows, W);
+  }
+  ws->work1 = b.plane(1, rows, W);
+  ws->work2 = b.plane(1, rows, W);
+  if (has_opt) { ws->opt1 = b.plane(1, rows, W); ws->opt2 = b.plane(1, rows, W); }
+  if (has_hs) { ws->fx = b.plane(1, rows, W); ws->fy = b.plane(1, rows, W); ws->ft = b.plane(1, rows, W); }
+  for (int i = 0; i < 2; ++i) { ws->U[i] = b.plane(1, rows, W); ws->V[i] = b.plane(1, rows, W); }
+  ws->U0 = b.plane(1, rows, W);
+  ws->V0 = b.plane(1, rows, W);
+  ws->Uacc = b.plane(1, rows, W);
+  ws->Vacc = b.plane(1, rows, W);
+  if (multi) {
+    ws->us = b.plane(1, rows, W);
+    ws->vs = b.plane(1, rows, W);
+    const BandLevel& c = bp.lv[bp.L - 2];     // the largest coarse level
+    ws->gU = b.plane(1, c.Hl, c.Wl);
+    ws->gV = b.plane(1, c.Hl, c.Wl);
+    ws->M1 = b.planed(1, c.Hl, c.Wl);
+    ws->T1 = b.planed(1, rows, c.Wl);
+    ws->M2 = b.planed(1, rows, c.Wl);
+  }
+  if (has_ls) {
+    for (int c = 0; c < 8; ++c) ws->ls.c[c] = b.plane(1, rows, W);
+    int maxit = 1;
+    if (p->main_algo.kind == OFRI_ALGO_LS) maxit = p->main_algo.ls_maxiter;
+    if (p->opt_algo.kind == OFRI_ALGO_LS && p->opt_algo.ls_maxiter > maxit) maxit = p->opt_algo.ls_maxiter;
+    ws->ls_errs = (double*)b.take(sizeof(double) * 2 * (size_t)maxit);
+    ws->ls_state = (int*)b.take(sizeof(int) * 4);
+    ws->ls_max = (unsigned*)b.take(sizeof(unsigned) * 2);
+  }
+  ws->hs_acc = (double*)b.take(sizeof(double) * 2);
+  ws->flag = (int*)b.take(sizeof(int) * 4);
+}
+
+// ghost rows of one (U, V) pair <- the neighbours' owned rows; o0 / o1 = LOCAL row range the band owns
+int band_exchange_uv(ofri_handle h, const Img& U, const Img& V, int o0, int o1, int E) {
+  ofri::Comm* c = h->comm;
+  if (!c || c->nranks == 1) return OFRI_OK;
+  const long pitch = U.pitch;
+  const bool up = c->rank > 0, dn = c->rank < c->nranks - 1;
+  const float* su[2] = {U.p + (long)o0 * pitch, V.p + (long)o0 * pitch};
+  float* ru[2] = {up ? U.p + (long)(o0 - E) * pitch : U.p, up ? V.p + (long)(o0 - E) * pitch : V.p};
+  const float* sd[2] = {U.p + (long)(o1 - E) * pitch, V.p + (long)(o1 - E) * pitch};
+  float* rd[2] = {dn ? U.p + (long)o1 * pitch : U.p, dn ? V.p + (long)o1 * pitch : V.p};
+  if (c->exchange(2, su, ru, sd, rd, (size_t)E * pitch, h->stream))
+    return fail(h, OFRI_ERR_COMM, "ghost-row exchange failed: %s", c->error());
+  h->lc.n += 0;
+  return OFRI_OK;
+}
+
+__global__ void band_reach_kernel(Img vs, float limit, int* flag) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= vs.W || y >= vs.H) return;
+  float v = vs.p[(long)y * vs.pitch + x];
+  if (!(fabsf(v) * 0.5f + 2.0f <= limit)) atomicExch(flag, 1);
+}
+
+int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs& ws, const Img& im1, const Img& im2,
+                       const BandLevel& bl, int E, int cur, bool uv_zero, bool coarse_level, float* d_err,
+                       int* comm_rc) {
+  cudaStream_t s = h->stream;
+  ofri::Comm* c = h->comm;
+  const int rows = bl.ext1 - bl.ext0, Wl = bl.Wl;
+  const int o0 = bl.own0 - bl.ext0, o1 = bl.own1 - bl.ext0;
+  const double npix = (double)bl.Hl * (double)bl.Wl;
+  Img U[2] = {view(ws.U[0], rows, Wl), view(ws.U[1], rows, Wl)};
+  Img V[2] = {view(ws.V[0], rows, Wl), view(ws.V[1], rows, Wl)};
+  if (a.kind == OFRI_ALGO_HS) {
+    Img fx = view(ws.fx, rows, Wl), fy = view(ws.fy, rows, Wl), ft = view(ws.ft, rows, Wl);
+    {
+      Timed t(h, "hs_derivs");
+      launch_hs_derivs(im1, im2, fx, fy, ft, s, h->lc);
+    }
+    Img U0, V0;
+    if (!uv_zero && d_err) {
+      U0 = view(ws.U0, rows, Wl);
+      V0 = view(ws.V0, rows, Wl);
+      launch_copy(U0, U[cur], s, h->lc);
+      launch_copy(V0, V[cur], s, h->lc);
+    }
+    int res;
+    {
+      Timed t(h, "hs_iterate");
+      const bool precise = h->hs_precise >= 2 || (h->hs_precise == 1 && coarse_level);
+      const int niter = a.hs_niter;
+      const int c0 = cur;
+      HsHook hook = [&](int done, int which) {
+        if (*comm_rc) return;
+        if (done % E == 0 || done == niter) {
+          const int b = which ? (c0 ^ 1) : c0;
+          *comm_rc = band_exchange_uv(h, U[b], V[b], o0, o1, E);
+        }
+      };
+      res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], niter, h->hs_fuse,
+                              h->hs_variant, precise, s, h->lc, hook);
+    }
+    cur = res ? (cur ^ 1) : cur;
+    if (d_err) {
+      Timed t(h, "hs_error");
+      launch_hs_error_sums(U[cur], V[cur], U0, V0, ws.hs_acc, o0, o1, s, h->lc);
+      if (c && c->nranks > 1 && c->allreduce_sum(ws.hs_acc, 2, s)) *comm_rc = fail(h, OFRI_ERR_COMM, "%s", c->error());
+      launch_hs_error_finish(ws.hs_acc, d_err, 1, 1, npix, s, h->lc);
+    }
+    return cur;
+  }
+  // Liu-Shen: u = ROW component (our V), v = COLUMN component (our U)
+  LsPlanes co;
+  for (int k = 0; k < 8; ++k) co.c[k] = view(ws.ls.c[k], rows, Wl);
+  {
+    Timed t(h, "ls_coefficients");
+    Img m1 = im1, m2 = im2;                            // owned rows only: ghost rows may hold band-edge artefacts
+    m1.p += (size_t)o0 * m1.pitch; m1.H = o1 - o0;
+    m2.p += (size_t)o0 * m2.pitch; m2.H = o1 - o0;
+    launch_ls_max(m1, m2, ws.ls_max, s, h->lc);
+    if (c && c->nranks > 1 && c->allreduce_max_u32(ws.ls_max, 2, s)) *comm_rc = fail(h, OFRI_ERR_COMM, "%s", c->error());
+    launch_ls_coef(im1, im2, a.ls_h, co, ws.ls_max, s, h->lc, bl.ext0, bl.Hl);
+  }
+  {
+    Timed t(h, "ls_iterate");
+    LsBand band{o0, o1, npix};
+    const int c0 = cur;
+    LsHook hook = [&](int k0, int n, int written) {
+      if (*comm_rc || !c || c->nranks == 1) return;
+      if (n > 0 && c->allreduce_sum(ws.ls_errs + 2 * k0, 2 * (size_t)n, s)) {
+        *comm_rc = fail(h, OFRI_ERR_COMM, "%s", c->error());
+        return;
+      }
+      if (written == 0 || written == 2) *comm_rc = band_exchange_uv(h, U[c0], V[c0], o0, o1, E);
+      if (!*comm_rc && (written == 1 || written == 2)) *comm_rc = band_exchange_uv(h, U[c0 ^ 1], V[c0 ^ 1], o0, o1, E);
+    };
+    launch_ls_solve(V[cur], U[cur], V[cur ^ 1], U[cur ^ 1], co, a.ls_h, a.ls_maxiter, a.ls_tol, h->ls_fuse, h->ls_variant,
+                    ws.ls_errs, ws.ls_state, V[cur], U[cur], d_err, 1, nullptr, s, h->lc, &band, hook);
+    if (!*comm_rc) *comm_rc = band_exchange_uv(h, U[cur], V[cur], o0, o1, E);    // ghosts of the selected final state
+  }
+  return cur;
+}
+
+int run_pyramid_banded(ofri_handle h, const float* d_im1, const float* d_im2, int H, int W, const ofri_params* p,
+                       const BandPlanInt& bp, float* d_u, float* d_v, float* d_err, BandWs& ws) {
+  cudaStream_t s = h->stream;
+  ofri::Comm* c = h->comm;
+  const int L = bp.L, n = c ? c->nranks : 1;
+  const bool has_opt = p->opt_algo.kind != OFRI_ALGO_NONE;
+  const GaussTaps taps_main = make_taps(p->taps_main, p->n_taps_main);
+  const GaussTaps taps_opt = make_taps(p->taps_opt, p->n_taps_opt);
+  const int in_rows = bp.in1 - bp.in0;
+  Img in1 = dense(d_im1, 1, in_rows, W), in2 = dense(d_im2, 1, in_rows, W);
+  Img Uacc = ws.Uacc, Vacc = ws.Vacc, us = ws.us, vs = ws.vs;
+  int cur = 0, comm_rc = 0;
+  cudaMemsetAsync(ws.flag, 0, sizeof(int) * 4, s);
+  for (int l = 0; l < L; ++l) {
+    const BandLevel& bl = bp.lv[l];
+    const bool last = l == L - 1;
+    const bool local_scaling = last ? p->final_scaling != 0 : p->intermediate_scaling != 0;
+    const int rows = bl.ext1 - bl.ext0, Wl = bl.Wl;
+    const int o0 = bl.own0 - bl.ext0;
+    Img n1, n2;
+    if (last) {   // the frames themselves: a window of the input band
+      n1 = dense(d_im1 + (size_t)(bl.ext0 - bp.in0) * W, 1, rows, W);
+      n2 = dense(d_im2 + (size_t)(bl.ext0 - bp.in0) * W, 1, rows, W);
+    } else {
+      n1 = view(ws.lvl1, rows, Wl);
+      n2 = view(ws.lvl2, rows, Wl);
+      ResizeTaps tx, ty;
+      int rc = get_resize_taps(h, W, Wl, &tx);
+      if (rc) return rc;
+      rc = get_resize_taps(h, H, bl.Hl, &ty);
+      if (rc) return rc;
+      Timed t(h, "resize");
+      Img tmp = view(ws.tmp, in_rows, Wl);
+      launch_resize(in1, tmp, n1, tx, ty, s, h->lc, bp.in0, bl.ext0);
+      launch_resize(in2, tmp, n2, tx, ty, s, h->lc, bp.in0, bl.ext0);
+    }
+    Img w1 = n1, w2 = n2;
+    Img Ucur = view(ws.U[cur], rows, Wl), Vcur = view(ws.V[cur], rows, Wl);
+    if (l > 0) {
+      const BandLevel& pl = bp.lv[l - 1];
+      const int prow = pl.ext1 - pl.ext0;
+      Img ua = view(Uacc, prow, pl.Wl), va = view(Vacc, prow, pl.Wl);
+      Img gU = view(ws.gU, pl.Hl, pl.Wl), gV = view(ws.gV, pl.Hl, pl.Wl);
+      Img un = view(us, rows, Wl), vn = view(vs, rows, Wl);
+      {
+        Timed t(h, "gather");
+        const size_t cnt = (size_t)(pl.own1 - pl.own0) * ua.pitch;
+        const float* su = ua.p + (size_t)(pl.own0 - pl.ext0) * ua.pitch;
+        const float* sv = va.p + (size_t)(pl.own0 - pl.ext0) * va.pitch;
+        if (c && n > 1) {
+          if (c->allgather(su, gU.p, cnt, s) || c->allgather(sv, gV.p, cnt, s))
+            return fail(h, OFRI_ERR_COMM, "all-gather of the coarse flow failed: %s", c->error());
+        } else {
+          cudaMemcpyAsync(gU.p, su, cnt * sizeof(float), cudaMemcpyDeviceToDevice, s);
+          cudaMemcpyAsync(gV.p, sv, cnt * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        }
+      }
+      {
+        Timed t(h, "spline_upsample");
+        SplineSys sy, sx;
+        int rc = get_spline_sys(h, pl.Hl, &sy);
+        if (rc) return rc;
+        rc = get_spline_sys(h, pl.Wl, &sx);
+        if (rc) return rc;
+        float mx = 1.0f, my = 1.0f;
+        if (local_scaling) {
+          mx = (float)Wl / (float)pl.Wl;
+          my = (float)bl.Hl / (float)pl.Hl;
+        }
+        ImgD M1 = viewd(ws.M1, pl.Hl, pl.Wl), T1 = viewd(ws.T1, rows, pl.Wl), M2 = viewd(ws.M2, rows, pl.Wl);
+        launch_spline(gU, un, mx, sy, sx, M1, T1, M2, s, h->lc, bl.ext0, bl.Hl);
+        launch_spline(gV, vn, my, sy, sx, M1, T1, M2, s, h->lc, bl.ext0, bl.Hl);
+      }
+      {
+        Timed t(h, "warp");
+        dim3 b(32, 8), g((Wl + 31) / 32, (rows + 7) / 8, 1);
+        band_reach_kernel<<<g, b, 0, s>>>(vn, (float)bp.Rw, ws.flag);
+        h->lc.n += 1;
+        w1 = view(ws.warp1, rows, Wl);
+        w2 = view(ws.warp2, rows, Wl);
+        launch_warp_pair(n1, n2, un, vn, w1, w2, s, h->lc, bl.ext0, bl.ext0, bl.Hl);
+        std::swap(Uacc, us);
+        std::swap(Vacc, vs);
+      }
+    }
+    Img UaccL = view(Uacc, rows, Wl), VaccL = view(Vacc, rows, Wl);
+    if (l == 0) {
+      cudaMemsetAsync(UaccL.p, 0, sizeof(float) * (size_t)UaccL.stride, s);
+      cudaMemsetAsync(VaccL.p, 0, sizeof(float) * (size_t)VaccL.stride, s);
+    }
+    cudaMemsetAsync(Ucur.p, 0, sizeof(float) * (size_t)Ucur.stride, s);
+    cudaMemsetAsync(Vcur.p, 0, sizeof(float) * (size_t)Vcur.stride, s);
+    Img work1 = w1, work2 = w2;
+    if (p->n_taps_main > 0) {
+      Timed t(h, "gauss");
+      work1 = view(ws.work1, rows, Wl);
+      work2 = view(ws.work2, rows, Wl);
+      Img gt = view(ws.U0, rows, Wl);      // scratch of the generic two-pass filter (free until the adapters run)
+      launch_gauss(w1, gt, work1, taps_main, s, h->lc);
+      launch_gauss(w2, gt, work2, taps_main, s, h->lc);
+    }
+    Img o1 = n1, o2 = n2;
+    if (has_opt && p->n_taps_opt > 0) {
+      Timed t(h, "gauss");
+      o1 = view(ws.opt1, rows, Wl);
+      o2 = view(ws.opt2, rows, Wl);
+      Img gt = view(ws.U0, rows, Wl);
+      launch_gauss(n1, gt, o1, taps_opt, s, h->lc);
+      launch_gauss(n2, gt, o2, taps_opt, s, h->lc);
+    }
+    float* e_main = d_err ? d_err + 2 * l : nullptr;
+    cur = run_adapter_banded(h, p->main_algo, l, ws, work1, work2, bl, bp.E, cur, true, !last, e_main, &comm_rc);
+    if (comm_rc) return comm_rc;
+    if (has_opt) {
+      float* e_opt = d_err ? d_err + 2 * l + 1 : nullptr;
+      cur = run_adapter_banded(h, p->opt_algo, l, ws, o1, o2, bl, bp.E, cur, false, !last, e_opt, &comm_rc);
+      if (comm_rc) return comm_rc;
+    }
+    Ucur = view(ws.U[cur], rows, Wl);
+    Vcur = view(ws.V[cur], rows, Wl);
+    {
+      Timed t(h, "accumulate");
+      launch_axpy(UaccL, Ucur, s, h->lc);
+      launch_axpy(VaccL, Vcur, s, h->lc);
+    }
+    if (last) {
+      Img src_u = UaccL, src_v = VaccL;
+      src_u.p += (size_t)o0 * src_u.pitch;
+      src_v.p += (size_t)o0 * src_v.pitch;
+      src_u.H = src_v.H = bl.own1 - bl.own0;
+      launch_copy(dense(d_u, 1, bl.own1 - bl.own0, W), src_u, s, h->lc);
+      launch_copy(dense(d_v, 1, bl.own1 - bl.own0, W), src_v, s, h->lc);
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, OFRI_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return OFRI_OK;
+}
+
+size_t band_workspace_bytes(const BandPlanInt& bp, int W, const ofri_params* p) {
+  Bump dry(nullptr, 0, true);
+  BandWs ws;
+  plan_band_ws(dry, bp, W, p, &ws);
+  return dry.off + 4096;
+}
+
 }  // namespace
 
 // =====================================================================================================================
@@ -672,6 +1046,7 @@ int ofri_destroy(ofri_handle h) {
   for (auto& kv : h->splines) { cudaFree(kv.second.lo); cudaFree(kv.second.cp); cudaFree(kv.second.den); }
   if (h->arena) cudaFree(h->arena);
   if (h->stage) cudaFree(h->stage);
+  delete h->comm;
   for (int i = 0; i < 2; ++i) {
     cudaEventDestroy(h->ev_h2d[i]);
     cudaEventDestroy(h->ev_comp[i]);
@@ -716,6 +1091,8 @@ static int* option_slot(ofri_handle h, const char* key) {
   if (!strcmp(key, "ls_variant")) return &h->ls_variant;
   if (!strcmp(key, "chunk_pairs")) return &h->chunk_pairs;
   if (!strcmp(key, "timing")) return &h->timing;
+  if (!strcmp(key, "band_exchange")) return &h->band_exchange;
+  if (!strcmp(key, "band_reach")) return &h->band_reach;
   return nullptr;
 }
 int ofri_set_option(ofri_handle h, const char* key, int value) {
@@ -1064,6 +1441,87 @@ int ofri_ls_coefficients(ofri_handle h, const float* im1, const float* im2, int 
   for (int i = 0; i < 8; ++i)
     if ((rc = download(h, coef + (size_t)i * batch * H * W, co.c[i]))) return rc;
   return finish(h);
+}
+
+
+// ---- row-band mode ------------------------------------------------------------------------------------------------------
+int ofri_nccl_unique_id(void* out128) {
+  std::string err;
+  if (!out128) return fail(nullptr, OFRI_ERR_INVALID, "NULL pointer");
+  if (ofri::nccl_unique_id(out128, &err)) return fail(nullptr, OFRI_ERR_COMM, "%s", err.c_str());
+  return OFRI_OK;
+}
+int ofri_comm_init_nccl(ofri_handle h, int rank, int nranks, const void* uid128) {
+  OFRI_ENTER(h);
+  if (!uid128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, OFRI_ERR_INVALID, "bad communicator arguments");
+  std::string err;
+  ofri::Comm* c = ofri::make_nccl_comm(rank, nranks, uid128, &err);
+  if (!c) return fail(h, OFRI_ERR_COMM, "%s", err.c_str());
+  delete h->comm;
+  h->comm = c;
+  return OFRI_OK;
+}
+int ofri_local_group_create(int nranks, void** group) {
+  if (!group) return fail(nullptr, OFRI_ERR_INVALID, "NULL pointer");
+  *group = ofri::make_local_group(nranks);
+  return *group ? OFRI_OK : fail(nullptr, OFRI_ERR_INVALID, "bad group size %d", nranks);
+}
+int ofri_local_group_destroy(void* group) {
+  ofri::free_local_group((ofri::LocalGroup*)group);
+  return OFRI_OK;
+}
+int ofri_comm_init_local(ofri_handle h, void* group, int rank) {
+  OFRI_ENTER(h);
+  std::string err;
+  ofri::Comm* c = ofri::make_local_comm((ofri::LocalGroup*)group, rank, &err);
+  if (!c) return fail(h, OFRI_ERR_COMM, "%s", err.c_str());
+  delete h->comm;
+  h->comm = c;
+  return OFRI_OK;
+}
+int ofri_comm_destroy(ofri_handle h) {
+  OFRI_ENTER(h);
+  OFRI_CUDA(h, cudaStreamSynchronize(h->stream));
+  delete h->comm;
+  h->comm = nullptr;
+  return OFRI_OK;
+}
+int ofri_band_plan(ofri_handle h, int H, int W, const ofri_params* p, int rank, int nranks, ofri_band* out) {
+  OFRI_ENTER(h);
+  if (!out) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
+  BandPlanInt bp;
+  int rc = make_band_plan(h, H, W, p, rank, nranks, &bp);
+  if (rc) return rc;
+  const BandLevel& f = bp.lv[bp.L - 1];
+  out->rank = rank; out->nranks = nranks;
+  out->own0 = f.own0; out->own1 = f.own1;
+  out->in0 = bp.in0; out->in1 = bp.in1;
+  out->ghost = bp.G; out->exchange = bp.E;
+  return OFRI_OK;
+}
+int ofri_pyramidal_flow_banded_dev(ofri_handle h, const float* d_im1_rows, const float* d_im2_rows, int H, int W,
+                                   const ofri_params* p, float* d_u_rows, float* d_v_rows, float* d_err_out) {
+  OFRI_ENTER(h);
+  if (!d_im1_rows || !d_im2_rows || !d_u_rows || !d_v_rows) return fail(h, OFRI_ERR_INVALID, "NULL image / output pointer");
+  const int rank = h->comm ? h->comm->rank : 0, n = h->comm ? h->comm->nranks : 1;
+  BandPlanInt bp;
+  int rc = make_band_plan(h, H, W, p, rank, n, &bp);
+  if (rc) return rc;
+  rc = arena_reserve(h, band_workspace_bytes(bp, W, p));
+  if (rc) return rc;
+  Bump bump(h->arena, h->arena_cap, false);
+  BandWs ws;
+  plan_band_ws(bump, bp, W, p, &ws);
+  rc = run_pyramid_banded(h, d_im1_rows, d_im2_rows, H, W, p, bp, d_u_rows, d_v_rows, d_err_out, ws);
+  if (rc) return rc;
+  int flag = 0;      // one synchronisation at the end: did the warp stay inside the ghost frame?
+  OFRI_CUDA(h, cudaMemcpyAsync(&flag, ws.flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  OFRI_CUDA(h, cudaStreamSynchronize(h->stream));
+  collect_times(h);
+  if (flag)
+    return fail(h, OFRI_ERR_UNSUPPORTED, "row-band mode: the flow displaces rows by more than band_reach = %d; raise the "
+                "'band_reach' option", bp.Rw);
+  return OFRI_OK;
 }
 
 }  // extern "C"

@@ -605,7 +605,7 @@ static void launch_hs_fused(int T, int variant, bool precise, const Img& ui, con
 
 int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb, const Img& fx, const Img& fy,
                       const Img& ft, float alpha, int niter, int fuse, int variant, bool precise, cudaStream_t s,
-                      LaunchCounter& lc) {
+                      LaunchCounter& lc, const HsHook& hook) {
   const float alpha2 = alpha * alpha;   // f32 alpha**2 as in the numba signature (HornSchunck.py:52-55)
   int cur = 0;
   const Img* U[2] = {&ua, &ub};
@@ -641,6 +641,7 @@ int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb
     }
     cur ^= 1;
     lc.n += 1;
+    if (hook) hook(done, cur);
   }
   return cur;
 }
@@ -648,10 +649,10 @@ int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb
 // ---------------------------------------------------------------------------------------------------------------
 // error norm (HornSchunck.py:100)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void sqdiff_reduce_kernel(Img u, Img v, Img u0, Img v0, int has0, double* acc) {
+__global__ void sqdiff_reduce_kernel(Img u, Img v, Img u0, Img v0, int has0, double* acc, int y_lo, int y_hi) {
   const int b = blockIdx.z;
   double su = 0.0, sv = 0.0;
-  for (int y = blockIdx.y; y < u.H; y += gridDim.y) {
+  for (int y = y_lo + blockIdx.y; y < y_hi; y += gridDim.y) {
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < u.W; x += gridDim.x * blockDim.x) {
       float a = u.p[(long)b * u.stride + (long)y * u.pitch + x];
       float c = v.p[(long)b * v.stride + (long)y * v.pitch + x];
@@ -690,15 +691,24 @@ __global__ void hs_error_finish_kernel(const double* acc, float* err, int err_st
   if (b >= batch) return;
   err[(long)b * err_stride] = (float)((sqrt(acc[2 * b]) + sqrt(acc[2 * b + 1])) / npix);
 }
+void launch_hs_error_sums(const Img& u, const Img& v, const Img& u0, const Img& v0, double* acc, int y_lo, int y_hi,
+                          cudaStream_t s, LaunchCounter& lc) {
+  cudaMemsetAsync(acc, 0, sizeof(double) * 2 * u.batch, s);
+  int rows = y_hi - y_lo;
+  int gy = rows < 64 ? (rows > 0 ? rows : 1) : 64;
+  dim3 b(256), g((u.W + 255) / 256 > 4 ? 4 : (u.W + 255) / 256, gy, u.batch);
+  sqdiff_reduce_kernel<<<g, b, 0, s>>>(u, v, u0, v0, u0.p != nullptr ? 1 : 0, acc, y_lo, y_hi);
+  lc.n += 1;
+}
+void launch_hs_error_finish(const double* acc, float* err, int err_stride, int batch, double npix, cudaStream_t s,
+                            LaunchCounter& lc) {
+  hs_error_finish_kernel<<<(batch + 127) / 128, 128, 0, s>>>(acc, err, err_stride, batch, npix);
+  lc.n += 1;
+}
 void launch_hs_error(const Img& u, const Img& v, const Img& u0, const Img& v0, double* acc, float* err, int err_stride,
                      cudaStream_t s, LaunchCounter& lc) {
-  cudaMemsetAsync(acc, 0, sizeof(double) * 2 * u.batch, s);
-  int gy = u.H < 64 ? u.H : 64;
-  dim3 b(256), g((u.W + 255) / 256 > 4 ? 4 : (u.W + 255) / 256, gy, u.batch);
-  sqdiff_reduce_kernel<<<g, b, 0, s>>>(u, v, u0, v0, u0.p != nullptr ? 1 : 0, acc);
-  hs_error_finish_kernel<<<(u.batch + 127) / 128, 128, 0, s>>>(acc, err, err_stride, u.batch,
-                                                               (double)u.H * (double)u.W);
-  lc.n += 2;
+  launch_hs_error_sums(u, v, u0, v0, acc, 0, u.H, s, lc);
+  launch_hs_error_finish(acc, err, err_stride, u.batch, (double)u.H * (double)u.W, s, lc);
 }
 
 }  // namespace ofri

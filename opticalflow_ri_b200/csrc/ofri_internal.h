@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <functional>
+#include <string>
 #include "../../include/ofri.h"
 
 namespace ofri {
@@ -48,15 +50,31 @@ struct SplineSys {
 
 struct LaunchCounter { int64_t n = 0; };
 
+// Row-band mode of the Liu-Shen sweeps: the residual sums cover local rows [own_lo, own_hi) only (the rows this band
+// owns) and total_error is normalised by the pixel count of the WHOLE image.
+struct LsBand { int own_lo; int own_hi; double npix; };
+// Called (host side, between launches) after sweeps [k0, k0 + n) were enqueued; `written` = which ping-pong buffer
+// the launch wrote (0 = a, 1 = b, 2 = possibly both).  The band driver all-reduces errs[k0 .. k0+n) and exchanges the
+// ghost rows here; stream-ordered, no host synchronisation.
+typedef std::function<void(int k0, int n, int written)> LsHook;
+// Same for Horn-Schunck: after `done` sweeps in total, the current state is in buffer `cur` (0 = a, 1 = b).
+typedef std::function<void(int done, int cur)> HsHook;
+
+
 // ---- stages (ofri_stages.cu) ---------------------------------------------------------------------------------
 void launch_gauss(const Img& in, const Img& tmp, const Img& out, const GaussTaps& taps, cudaStream_t s, LaunchCounter& lc);
+// in_row0 / out_row0: global row of local row 0 of `in` / `out` when they are row bands of larger images (ty is
+// always the tap table of the WHOLE image)
 void launch_resize(const Img& in, const Img& tmp, const Img& out, const ResizeTaps& tx, const ResizeTaps& ty,
-                   cudaStream_t s, LaunchCounter& lc);
+                   cudaStream_t s, LaunchCounter& lc, int in_row0 = 0, int out_row0 = 0);
 // up-sample `in` (h x w) to `out` (H x W) and multiply by mul; scratch: M1 (h x w), T1 (H x w), M2 (H x w) f64
+// band form: `out` (and T1, M2) hold rows [row0, row0 + out.H) of the Hg-row result; `in` is always the whole coarse plane
 void launch_spline(const Img& in, const Img& out, float mul, const SplineSys& sy, const SplineSys& sx,
-                   const ImgD& M1, const ImgD& T1, const ImgD& M2, cudaStream_t s, LaunchCounter& lc);
+                   const ImgD& M1, const ImgD& T1, const ImgD& M2, cudaStream_t s, LaunchCounter& lc, int row0 = 0,
+                   int Hg = 0);
+// band form: us / vs / out hold rows [row0, ..) and im1 / im2 rows [img_row0, ..) of an image of Hg rows
 void launch_warp_pair(const Img& im1, const Img& im2, const Img& us, const Img& vs, const Img& out1, const Img& out2,
-                      cudaStream_t s, LaunchCounter& lc);
+                      cudaStream_t s, LaunchCounter& lc, int row0 = 0, int img_row0 = 0, int Hg = 0);
 void launch_warp_coords(const Img& img, const Img& cy, const Img& cx, const Img& out, cudaStream_t s, LaunchCounter& lc);
 void launch_axpy(const Img& acc, const Img& x, cudaStream_t s, LaunchCounter& lc);       // acc += x
 void launch_scale(const Img& x, float mul, cudaStream_t s, LaunchCounter& lc);            // x *= mul
@@ -71,7 +89,7 @@ void launch_hs_derivs(const Img& im1, const Img& im2, const Img& fx, const Img& 
 // precise = reference arithmetic bit for bit (f64-accumulated stencil, IEEE division) instead of the f32/FMA fast path.
 int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb, const Img& fx, const Img& fy,
                       const Img& ft, float alpha, int niter, int fuse, int variant, bool precise, cudaStream_t s,
-                      LaunchCounter& lc);
+                      LaunchCounter& lc, const HsHook& hook = HsHook());
 // packed-f32x2 register-resident fused sweeps (ofri_hs_pk.cu): T sweeps ui,vi -> uo,vo on prepared (a, b, c) planes
 void launch_hs_packed(int T, int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
                       const Img& fy, const Img& ft, cudaStream_t s);
@@ -81,9 +99,18 @@ bool launch_hs_tma(int T, int variant, bool precise, const Img& ui, const Img& v
 // err[b] = (sqrt(sum (u-u0)^2) + sqrt(sum (v-v0)^2)) / (H*W); u0.p == nullptr means u0 = v0 = 0.  acc: [batch][2] f64 scratch
 void launch_hs_error(const Img& u, const Img& v, const Img& u0, const Img& v0, double* acc, float* err, int err_stride,
                      cudaStream_t s, LaunchCounter& lc);
+// the two halves of launch_hs_error for row bands: sums over local rows [y_lo, y_hi) into acc (to be all-reduced),
+// then err = (sqrt(acc0) + sqrt(acc1)) / npix
+void launch_hs_error_sums(const Img& u, const Img& v, const Img& u0, const Img& v0, double* acc, int y_lo, int y_hi,
+                          cudaStream_t s, LaunchCounter& lc);
+void launch_hs_error_finish(const double* acc, float* err, int err_stride, int batch, double npix, cudaStream_t s,
+                            LaunchCounter& lc);
 
 // ---- Liu-Shen (ofri_ls.cu) -----------------------------------------------------------------------------------------
 struct LsPlanes { Img c[8]; };   // IIx, IIy, II, Ixt, Iyt, B11, B12, B22
+void launch_ls_max(const Img& im1, const Img& im2, unsigned* maxenc, cudaStream_t s, LaunchCounter& lc);
+void launch_ls_coef(const Img& im1, const Img& im2, float hpar, const LsPlanes& coef, const unsigned* maxenc,
+                    cudaStream_t s, LaunchCounter& lc, int row0 = 0, int Hg = 0);
 // maxenc: [batch][2] uint32 scratch (ordered-int encoded maxima of im1 / im2)
 void launch_ls_coefficients(const Img& im1, const Img& im2, float hpar, const LsPlanes& coef, unsigned* maxenc,
                             cudaStream_t s, LaunchCounter& lc);
@@ -92,7 +119,29 @@ void launch_ls_coefficients(const Img& im1, const Img& im2, float hpar, const Ls
 // errs: [batch][maxiter][2] f64 scratch; err_out[b*err_stride] = last total_error; iters_out[b] = sweeps run.
 void launch_ls_solve(const Img& ua, const Img& va, const Img& ub, const Img& vb, const LsPlanes& coef, float hpar,
                      int maxiter, double tol, int fuse, int variant, double* errs, int* state, const Img& uo,
-                     const Img& vo, float* err_out, int err_stride, int* iters_out, cudaStream_t s, LaunchCounter& lc);
+                     const Img& vo, float* err_out, int err_stride, int* iters_out, cudaStream_t s, LaunchCounter& lc,
+                     const LsBand* band = nullptr, const LsHook& hook = LsHook());
+
+// ---- communication back ends of the row-band driver (ofri_comm.cu) ------------------------------------------------
+// All operations are enqueued on stream s (plus host-side rendezvous for the local back end); 0 = ok, -1 = see error().
+struct Comm {
+  int rank = 0, nranks = 1;
+  virtual ~Comm() {}
+  // ghost rows: `count` floats per segment go from send_up[i] to rank-1 and from send_dn[i] to rank+1; recv_up[i] is
+  // filled by rank-1's send_dn[i], recv_dn[i] by rank+1's send_up[i].  Ranks 0 / n-1 have no upper / lower neighbour.
+  virtual int exchange(int nseg, const float* const* send_up, float* const* recv_up, const float* const* send_dn,
+                       float* const* recv_dn, size_t count, cudaStream_t s) = 0;
+  virtual int allreduce_sum(double* p, size_t n, cudaStream_t s) = 0;
+  virtual int allreduce_max_u32(unsigned* p, size_t n, cudaStream_t s) = 0;
+  virtual int allgather(const float* send, float* recv, size_t count, cudaStream_t s) = 0;   // recv: [nranks][count]
+  virtual const char* error() const = 0;
+};
+struct LocalGroup;
+int nccl_unique_id(void* out128, std::string* err);
+Comm* make_nccl_comm(int rank, int nranks, const void* uid128, std::string* err);
+LocalGroup* make_local_group(int n);
+void free_local_group(LocalGroup* g);
+Comm* make_local_comm(LocalGroup* g, int rank, std::string* err);
 
 const char* kernel_build_info();
 

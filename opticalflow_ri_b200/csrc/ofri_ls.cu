@@ -48,7 +48,9 @@ __global__ void ls_max_kernel(Img a, Img c, unsigned* maxenc) {
 // ---------------------------------------------------------------------------------------------------------------
 // coefficient planes (LS:96-97, 124-128, generate_invmatrix LS:47-73)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void ls_coef_kernel(Img im1, Img im2, float hpar, LsPlanes co, const unsigned* maxenc) {
+// row0 / Hg: the planes hold rows [row0, row0 + H) of an image of Hg rows (row bands; 0 / H otherwise): the count of
+// in-bounds neighbours (8 / 5 / 3) refers to the IMAGE border, not the band's
+__global__ void ls_coef_kernel(Img im1, Img im2, float hpar, LsPlanes co, const unsigned* maxenc, int row0, int Hg) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
   const int W = im1.W, H = im1.H;
   if (x >= W || y >= H) return;
@@ -62,7 +64,7 @@ __global__ void ls_coef_kernel(Img im1, Img im2, float hpar, LsPlanes co, const 
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       int yy = y + r - 1, xx = x + q - 1;
-      bool in = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+      bool in = (yy + row0 >= 0) && (yy + row0 < Hg) && (xx >= 0) && (xx < W);
       if (in && !(r == 1 && q == 1)) ++cnt;
       yy = clampi(yy, 0, H - 1);
       xx = clampi(xx, 0, W - 1);
@@ -82,16 +84,24 @@ __global__ void ls_coef_kernel(Img im1, Img im2, float hpar, LsPlanes co, const 
   co.c[6].p[o] = c.B12;
   co.c[7].p[o] = c.B22;
 }
-void launch_ls_coefficients(const Img& im1, const Img& im2, float hpar, const LsPlanes& coef, unsigned* maxenc,
-                            cudaStream_t s, LaunchCounter& lc) {
+void launch_ls_max(const Img& im1, const Img& im2, unsigned* maxenc, cudaStream_t s, LaunchCounter& lc) {
   cudaMemsetAsync(maxenc, 0, sizeof(unsigned) * 2 * im1.batch, s);   // 0 encodes below every float
   int gy = im1.H < 64 ? im1.H : 64;
   int gx = (im1.W + 255) / 256;
   if (gx > 4) gx = 4;
   ls_max_kernel<<<dim3(gx, gy, im1.batch), 256, 0, s>>>(im1, im2, maxenc);
+  lc.n += 1;
+}
+void launch_ls_coef(const Img& im1, const Img& im2, float hpar, const LsPlanes& coef, const unsigned* maxenc,
+                    cudaStream_t s, LaunchCounter& lc, int row0, int Hg) {
   dim3 b(32, 8), g((im1.W + 31) / 32, (im1.H + 7) / 8, im1.batch);
-  ls_coef_kernel<<<g, b, 0, s>>>(im1, im2, hpar, coef, maxenc);
-  lc.n += 2;
+  ls_coef_kernel<<<g, b, 0, s>>>(im1, im2, hpar, coef, maxenc, row0, Hg > 0 ? Hg : im1.H);
+  lc.n += 1;
+}
+void launch_ls_coefficients(const Img& im1, const Img& im2, float hpar, const LsPlanes& coef, unsigned* maxenc,
+                            cudaStream_t s, LaunchCounter& lc) {
+  launch_ls_max(im1, im2, maxenc, s, lc);
+  launch_ls_coef(im1, im2, hpar, coef, maxenc, s, lc, 0, 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -149,12 +159,12 @@ __device__ __forceinline__ void block_atomic_add2(double su, double sv, double* 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ls_sweep_simple_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, int k, int maxiter, double tol,
-                       double* errs, const int* state, int mode, int lookback) {
+                       double* errs, const int* state, int mode, int lookback, LsBand band) {
   __shared__ double sh[64];
   __shared__ int s_stop;
   const int b = blockIdx.z;
   const int W = u0.W, H = u0.H;
-  const double npix = (double)H * (double)W;
+  const double npix = band.npix;
   Img ui, vi, uo, vo;
   if (mode == 0) {
     if (k > 0) {
@@ -196,9 +206,11 @@ ls_sweep_simple_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, 
     ls_update(uc, vc, inb, c, hpar, &un, &vn);
     uo.p[(long)b * uo.stride + (long)y * uo.pitch + x] = un;
     vo.p[(long)b * vo.stride + (long)y * vo.pitch + x] = vn;
-    float eu = fsub(un, uc[1][1]), ev = fsub(vn, vc[1][1]);
-    du2 = (double)eu * (double)eu;
-    dv2 = (double)ev * (double)ev;
+    if (y >= band.own_lo && y < band.own_hi) {     // residual over the rows this band owns (all rows normally)
+      float eu = fsub(un, uc[1][1]), ev = fsub(vn, vc[1][1]);
+      du2 = (double)eu * (double)eu;
+      dv2 = (double)ev * (double)ev;
+    }
   }
   if (mode == 0) block_atomic_add2(du2, dv2, errs + ((long)b * maxiter + k) * 2, sh);
 }
@@ -315,7 +327,7 @@ __device__ __forceinline__ void ls_sweep(const float* __restrict__ cu, const flo
                                          float* __restrict__ nu, float* __restrict__ nv, const float* __restrict__ sC,
                                          int r0, int sx, const LsEdge& eg, float hpar, float* __restrict__ gU,
                                          float* __restrict__ gV, long gpitch, int gy0, int gx, int H, int W,
-                                         float& du2, float& dv2) {
+                                         int own_lo, int own_hi, float& du2, float& dv2) {
   using C = LsCfg<T, R, NRG, NG>;
   constexpr int SW = C::SW;
   float wu[3][6], wv[3][6];
@@ -339,7 +351,7 @@ __device__ __forceinline__ void ls_sweep(const float* __restrict__ cu, const flo
     // residual over the CTA's own output cells only (each pixel counted by exactly one CTA)
     const int sy = r0 + j, gy = gy0 + j;
     const bool own = in_cols && (sy >= T) && (sy < C::SH - T) && (gy < H);
-    if (own) {
+    if (own && gy >= own_lo && gy < own_hi) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (!EDGE || gx + q < W) {
@@ -363,7 +375,7 @@ __device__ __forceinline__ void ls_sweep(const float* __restrict__ cu, const flo
 template <int T, int R, int NRG, int NG, bool EDGE>
 __device__ __forceinline__ void ls_fused_body(const Img& ui, const Img& vi, const Img& uo, const Img& vo,
                                               const LsPlanes& co, float hpar, int k0, double* errs_pair, float* smem,
-                                              double* sh) {
+                                              double* sh, int own_lo, int own_hi) {
   using C = LsCfg<T, R, NRG, NG>;
   constexpr int SW = C::SW, SH = C::SH, HX = C::HX;
   const int b = blockIdx.z;
@@ -410,8 +422,8 @@ __device__ __forceinline__ void ls_fused_body(const Img& ui, const Img& vi, cons
     float* nu = smem + ((s + 1) & 1) * C::PLANE;
     float* nv = smem + (2 + ((s + 1) & 1)) * C::PLANE;
     float du2 = 0.0f, dv2 = 0.0f;
-    ls_sweep<T, R, NRG, NG, EDGE, false>(cu, cv, nu, nv, sC, r0, sx, eg, hpar, gU, gV, uo.pitch, y0 + r0, gx, H, W, du2,
-                                         dv2);
+    ls_sweep<T, R, NRG, NG, EDGE, false>(cu, cv, nu, nv, sC, r0, sx, eg, hpar, gU, gV, uo.pitch, y0 + r0, gx, H, W,
+                                         own_lo, own_hi, du2, dv2);
     block_atomic_add2((double)du2, (double)dv2, errs_pair + 2 * (k0 + s), sh);   // also the sweep barrier
   }
   {
@@ -420,20 +432,21 @@ __device__ __forceinline__ void ls_fused_body(const Img& ui, const Img& vi, cons
     const float* cv = smem + (2 + (s & 1)) * C::PLANE;
     float du2 = 0.0f, dv2 = 0.0f;
     ls_sweep<T, R, NRG, NG, EDGE, true>(cu, cv, nullptr, nullptr, sC, r0, sx, eg, hpar, gU, gV, uo.pitch, y0 + r0, gx, H,
-                                        W, du2, dv2);
+                                        W, own_lo, own_hi, du2, dv2);
     block_atomic_add2((double)du2, (double)dv2, errs_pair + 2 * (k0 + s), sh);
   }
 }
 
 template <int T, int R, int NRG, int NG, int MINB>
 __global__ void __launch_bounds__(LsCfg<T, R, NRG, NG>::NT, MINB)
-ls_fused_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, int k0, int maxiter, double tol, double* errs) {
+ls_fused_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, int k0, int maxiter, double tol, double* errs,
+                LsBand band) {
   using C = LsCfg<T, R, NRG, NG>;
   extern __shared__ __align__(16) float smem[];
   __shared__ double sh[64];
   __shared__ int s_stop;
   const int b = blockIdx.z;
-  const double npix = (double)u0.H * (double)u0.W;
+  const double npix = band.npix;
   double* errs_pair = errs + (long)b * maxiter * 2;
   if (k0 > 0) {   // stopping rule evaluated by one thread (f64 square roots), CTA-uniform result
     if (threadIdx.x == 0) s_stop = ls_stopped_before(errs_pair, k0, tol, npix, T) ? 1 : 0;
@@ -449,19 +462,20 @@ ls_fused_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, int k0,
   const int x0 = blockIdx.x * C::TW - C::HX, y0 = blockIdx.y * C::TH - T;
   const bool edge = (x0 < 0) || (x0 + C::SW > u0.W) || (y0 < 0) || (y0 + C::SH > u0.H);
   if (edge)
-    ls_fused_body<T, R, NRG, NG, true>(ui, vi, uo, vo, co, hpar, k0, errs_pair, smem, sh);
+    ls_fused_body<T, R, NRG, NG, true>(ui, vi, uo, vo, co, hpar, k0, errs_pair, smem, sh, band.own_lo, band.own_hi);
   else
-    ls_fused_body<T, R, NRG, NG, false>(ui, vi, uo, vo, co, hpar, k0, errs_pair, smem, sh);
+    ls_fused_body<T, R, NRG, NG, false>(ui, vi, uo, vo, co, hpar, k0, errs_pair, smem, sh, band.own_lo, band.own_hi);
 }
 
 template <int T, int R, int NRG, int NG, int MINB>
 static void launch_ls_fused_cfg(const Img& u0, const Img& v0, const Img& u1, const Img& v1, const LsPlanes& co,
-                                float hpar, int k0, int maxiter, double tol, double* errs, cudaStream_t s) {
+                                float hpar, int k0, int maxiter, double tol, double* errs, const LsBand& band,
+                                cudaStream_t s) {
   using C = LsCfg<T, R, NRG, NG>;
   auto kern = ls_fused_kernel<T, R, NRG, NG, MINB>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   dim3 g((u0.W + C::TW - 1) / C::TW, (u0.H + C::TH - 1) / C::TH, u0.batch);
-  kern<<<g, C::NT, C::SMEM_BYTES, s>>>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs);
+  kern<<<g, C::NT, C::SMEM_BYTES, s>>>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -517,34 +531,38 @@ __global__ void ls_select_kernel(Img u0, Img v0, Img u1, Img v1, Img uo, Img vo,
 template <int T>
 static void launch_ls_fused_T(int variant, const Img& u0, const Img& v0, const Img& u1, const Img& v1,
                               const LsPlanes& co, float hpar, int k0, int maxiter, double tol, double* errs,
-                              cudaStream_t s) {
+                              const LsBand& band, cudaStream_t s) {
   switch (variant) {
     default:
-    case 0: launch_ls_fused_cfg<T, 4, 4, 16, 4>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 18 x 64
-    case 1: launch_ls_fused_cfg<T, 4, 8, 16, 2>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 34 x 64
-    case 2: launch_ls_fused_cfg<T, 4, 4, 32, 2>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 18 x 128
-    case 3: launch_ls_fused_cfg<T, 3, 6, 16, 3>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 20 x 64
-    case 4: launch_ls_fused_cfg<T, 2, 8, 16, 4>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 18 x 64
-    case 5: launch_ls_fused_cfg<T, 6, 4, 16, 3>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;   // 26 x 64
+    case 0: launch_ls_fused_cfg<T, 4, 4, 16, 4>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 18 x 64
+    case 1: launch_ls_fused_cfg<T, 4, 8, 16, 2>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 34 x 64
+    case 2: launch_ls_fused_cfg<T, 4, 4, 32, 2>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 18 x 128
+    case 3: launch_ls_fused_cfg<T, 3, 6, 16, 3>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 20 x 64
+    case 4: launch_ls_fused_cfg<T, 2, 8, 16, 4>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 18 x 64
+    case 5: launch_ls_fused_cfg<T, 6, 4, 16, 3>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 26 x 64
   }
 }
 static void launch_ls_fused(int T, int variant, const Img& u0, const Img& v0, const Img& u1, const Img& v1,
                             const LsPlanes& co, float hpar, int k0, int maxiter, double tol, double* errs,
-                            cudaStream_t s) {
+                            const LsBand& band, cudaStream_t s) {
   switch (T) {
-    case 1: launch_ls_fused_T<1>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
-    case 2: launch_ls_fused_T<2>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
-    case 3: launch_ls_fused_T<3>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
-    default: launch_ls_fused_T<4>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, s); break;
+    case 1: launch_ls_fused_T<1>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
+    case 2: launch_ls_fused_T<2>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
+    case 3: launch_ls_fused_T<3>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
+    default: launch_ls_fused_T<4>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
   }
 }
 
 void launch_ls_solve(const Img& ua, const Img& va, const Img& ub, const Img& vb, const LsPlanes& coef, float hpar,
                      int maxiter, double tol, int fuse, int variant, double* errs, int* state, const Img& uo,
                      const Img& vo,
-                     float* err_out, int err_stride, int* iters_out, cudaStream_t s, LaunchCounter& lc) {
+                     float* err_out, int err_stride, int* iters_out, cudaStream_t s, LaunchCounter& lc,
+                     const LsBand* band_in, const LsHook& hook) {
   const int batch = ua.batch;
-  const double npix = (double)ua.H * (double)ua.W;
+  LsBand band;
+  band.own_lo = 0; band.own_hi = ua.H; band.npix = (double)ua.H * (double)ua.W;
+  if (band_in) band = *band_in;
+  const double npix = band.npix;
   cudaMemsetAsync(errs, 0, sizeof(double) * 2 * (size_t)maxiter * batch, s);
   bool can_fuse = fuse >= 1 && ua.W >= 2 && ua.H >= 2 && (ua.pitch % 4 == 0) && ua.pitch == va.pitch &&
                   ua.pitch == ub.pitch && ua.pitch == vb.pitch && ((uintptr_t)ua.p % 16 == 0) &&
@@ -559,8 +577,11 @@ void launch_ls_solve(const Img& ua, const Img& va, const Img& ub, const Img& vb,
   if (can_fuse && T >= 1) {
     nfull = maxiter / T;
     for (int i = 0; i < nfull; ++i) {
-      launch_ls_fused(T, variant, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, s);
+      launch_ls_fused(T, variant, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, band, s);
       lc.n += 1;
+      // launch i wrote buffer b (odd launches write a); band mode: sum the block's residuals over all bands and refresh
+      // the ghost rows of the buffer just written
+      if (hook) hook(i * T, T, (i & 1) ? 0 : 1);
     }
   } else {
     T = 1;
@@ -569,16 +590,18 @@ void launch_ls_solve(const Img& ua, const Img& va, const Img& ub, const Img& vb,
   for (int k = nfull * T, li = nfull; k < maxiter; ++k, ++li) {
     // the simple kernel derives the direction from k's parity, so feed it buffers swapped when (li - k) is odd
     if (((li - k) & 1) == 0)
-      ls_sweep_simple_kernel<<<gs, bs, 0, s>>>(ua, va, ub, vb, coef, hpar, k, maxiter, tol, errs, state, 0, T);
+      ls_sweep_simple_kernel<<<gs, bs, 0, s>>>(ua, va, ub, vb, coef, hpar, k, maxiter, tol, errs, state, 0, T, band);
     else
-      ls_sweep_simple_kernel<<<gs, bs, 0, s>>>(ub, vb, ua, va, coef, hpar, k, maxiter, tol, errs, state, 0, T);
+      ls_sweep_simple_kernel<<<gs, bs, 0, s>>>(ub, vb, ua, va, coef, hpar, k, maxiter, tol, errs, state, 0, T, band);
     lc.n += 1;
+    if (hook) hook(k, 1, (li & 1) ? 0 : 1);
   }
   ls_finalize_kernel<<<(batch + 127) / 128, 128, 0, s>>>(errs, state, batch, maxiter, tol, npix, T, nfull);
   lc.n += 1;
   for (int j = 0; j < T - 1 && nfull > 0; ++j) {   // conditional replay of an overshot fused block
-    ls_sweep_simple_kernel<<<gs, bs, 0, s>>>(ua, va, ub, vb, coef, hpar, j, maxiter, tol, errs, state, 1, T);
+    ls_sweep_simple_kernel<<<gs, bs, 0, s>>>(ua, va, ub, vb, coef, hpar, j, maxiter, tol, errs, state, 1, T, band);
     lc.n += 1;
+    if (hook) hook(-1, 0, 2);    // replay step: both buffers may have been written; refresh the ghost rows of both
   }
   ls_select_kernel<<<gs, bs, 0, s>>>(ua, va, ub, vb, uo, vo, state, errs, maxiter, npix, err_out, err_stride,
                                      iters_out);

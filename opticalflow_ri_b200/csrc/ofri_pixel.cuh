@@ -111,7 +111,12 @@ OFRI_HD float warp_coord(int idx, float flow, float sign) {
   double c = sign < 0.0f ? dsub((double)idx, (double)half) : dadd((double)idx, (double)half);
   return (float)c;
 }
-OFRI_HD float warp_sample(const float* img, long pitch, int H, int W, float cy, float cx) {
+// Band form (row-band domain decomposition): `img` holds rows [row0, row0 + H) of an image of Hg rows; cy is the GLOBAL
+// row coordinate (its float32 rounding depends on the magnitude of the row index, so it must be formed globally).
+// Rows are clamped to the image first (the reference's rule), then to the band (only reached when the band's halo is
+// too small for the displacement; the driver checks that).  row0 = 0, Hg = H is the whole-image case.
+OFRI_HD float warp_sample(const float* img, long pitch, int H, int W, float cy, float cx, int row0 = 0, int Hg = -1) {
+  if (Hg < 0) Hg = H;
   // np.int32(np.round(c)): half-to-even.  Clamp first so absurd / NaN coordinates saturate instead of trapping
   // (the reference's behaviour there is undefined; inside +-1e9 the result is identical).
   int iy = (int)fminf(fmaxf(rintf(cy), -1.0e9f), 1.0e9f);
@@ -122,9 +127,9 @@ OFRI_HD float warp_sample(const float* img, long pitch, int H, int W, float cy, 
   int nx = dx < 0.0 ? ix - 1 : ix + 1;
   dy = fabs(dy);
   dx = fabs(dx);
-  iy = clampi(iy, 0, H - 1);
+  iy = clampi(clampi(iy, 0, Hg - 1) - row0, 0, H - 1);
   ix = clampi(ix, 0, W - 1);
-  ny = clampi(ny, 0, H - 1);
+  ny = clampi(clampi(ny, 0, Hg - 1) - row0, 0, H - 1);
   nx = clampi(nx, 0, W - 1);
   double i00 = (double)img[(long)iy * pitch + ix];
   double i01 = (double)img[(long)iy * pitch + nx];

@@ -102,15 +102,20 @@ __global__ void resize_h_kernel(Img in, Img out, ResizeTaps t) {
   out.p[(long)b * out.stride + (long)y * out.pitch + ox] =
       resample_point(row, 1, t.xmin[ox], t.cnt[ox], t.w + (long)ox * t.kmax);
 }
-__global__ void resize_v_kernel(Img in, Img out, ResizeTaps t) {
+// in_row0 / out_row0: global row of local row 0 of `in` / `out` (row bands; 0 for whole images).  Output rows whose
+// taps are not all inside the band are written as 0 (they can only be ghost rows the driver never uses).
+__global__ void resize_v_kernel(Img in, Img out, ResizeTaps t, int in_row0, int out_row0) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
   if (x >= out.W || oy >= out.H) return;
-  const float* col = in.p + (long)b * in.stride + x;
-  out.p[(long)b * out.stride + (long)oy * out.pitch + x] =
-      resample_point(col, in.pitch, t.xmin[oy], t.cnt[oy], t.w + (long)oy * t.kmax);
+  const int og = oy + out_row0;
+  const int start = t.xmin[og] - in_row0, cnt = t.cnt[og];
+  float r = 0.0f;
+  if (start >= 0 && start + cnt <= in.H)
+    r = resample_point(in.p + (long)b * in.stride + x, in.pitch, start, cnt, t.w + (long)og * t.kmax);
+  out.p[(long)b * out.stride + (long)oy * out.pitch + x] = r;
 }
 void launch_resize(const Img& in, const Img& tmp, const Img& out, const ResizeTaps& tx, const ResizeTaps& ty,
-                   cudaStream_t s, LaunchCounter& lc) {
+                   cudaStream_t s, LaunchCounter& lc, int in_row0, int out_row0) {
   dim3 b(32, 8);
   // tmp: in.H x out.W
   Img t = tmp;
@@ -122,8 +127,8 @@ void launch_resize(const Img& in, const Img& tmp, const Img& out, const ResizeTa
   } else {
     t = in;
   }
-  if (out.H != in.H) {
-    resize_v_kernel<<<grid2d(out.W, out.H, in.batch, b), b, 0, s>>>(t, out, ty);
+  if (out.H != in.H || in_row0 != 0 || out_row0 != 0) {
+    resize_v_kernel<<<grid2d(out.W, out.H, in.batch, b), b, 0, s>>>(t, out, ty, in_row0, out_row0);
     lc.n += 1;
   } else {
     launch_copy(out, t, s, lc);
@@ -165,12 +170,13 @@ __global__ void spline_solve_kernel(const TIn* __restrict__ y, long y_elem, long
   mm[(long)(n - 1) * m_elem] = dsub(dmul(2.0, mm[(long)(n - 2) * m_elem]), mm[(long)(n - 3) * m_elem]);
 }
 // axis-0 evaluation: T1[k][x] for k < H from y[h][w] (f32) and M1[h][w]
-__global__ void spline_eval0_kernel(Img in, ImgD M1, ImgD T1, int H) {
+// rows [row0, row0 + T1.H) of the Hg-row result (row bands; row0 = 0, Hg = T1.H for whole images)
+__global__ void spline_eval0_kernel(Img in, ImgD M1, ImgD T1, int row0, int Hg) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
-  if (x >= in.W || k >= H) return;
+  if (x >= in.W || k >= T1.H) return;
   int i;
   double sfr;
-  spline_locate(k, in.H, H, &i, &sfr);
+  spline_locate(k + row0, in.H, Hg, &i, &sfr);
   const float* yp = in.p + (long)b * in.stride;
   const double* mp = M1.p + (long)b * M1.stride;
   double r = spline_eval((double)yp[(long)i * in.pitch + x], (double)yp[(long)(i + 1) * in.pitch + x],
@@ -191,14 +197,15 @@ __global__ void spline_eval1_kernel(ImgD T1, ImgD M2, Img out, float mul, int ap
   out.p[(long)b * out.stride + (long)k * out.pitch + l] = r;
 }
 void launch_spline(const Img& in, const Img& out, float mul, const SplineSys& sy, const SplineSys& sx, const ImgD& M1,
-                   const ImgD& T1, const ImgD& M2, cudaStream_t s, LaunchCounter& lc) {
+                   const ImgD& T1, const ImgD& M2, cudaStream_t s, LaunchCounter& lc, int row0, int Hg) {
   const int h = in.H, w = in.W, H = out.H;
+  if (Hg <= 0) Hg = H;
   // axis 0: one thread per column
   {
     dim3 b(128), g((w + 127) / 128, 1, in.batch);
     spline_solve_kernel<float><<<g, b, 0, s>>>(in.p, in.pitch, 1, in.stride, M1.p, M1.pitch, 1, M1.stride, h, w, sy);
     dim3 b2(32, 8);
-    spline_eval0_kernel<<<grid2d(w, H, in.batch, b2), b2, 0, s>>>(in, M1, T1, H);
+    spline_eval0_kernel<<<grid2d(w, H, in.batch, b2), b2, 0, s>>>(in, M1, T1, row0, Hg);
   }
   // axis 1: one thread per row of T1
   {
@@ -213,17 +220,18 @@ void launch_spline(const Img& in, const Img& out, float mul, const SplineSys& sy
 // ---------------------------------------------------------------------------------------------------------------
 // Bilinear warp (GPOF:70-116, 200-201)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void warp_pair_kernel(Img im1, Img im2, Img us, Img vs, Img o1, Img o2) {
+// us/vs/o1/o2: rows [row0, row0 + us.H) of the image; im1/im2: rows [img_row0, img_row0 + im1.H); Hg = image height
+__global__ void warp_pair_kernel(Img im1, Img im2, Img us, Img vs, Img o1, Img o2, int row0, int img_row0, int Hg) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
-  if (x >= im1.W || y >= im1.H) return;
+  if (x >= us.W || y >= us.H) return;
   float u = us.p[(long)b * us.stride + (long)y * us.pitch + x];
   float v = vs.p[(long)b * vs.stride + (long)y * vs.pitch + x];
-  float cy1 = warp_coord(y, v, -1.0f), cx1 = warp_coord(x, u, -1.0f);
-  float cy2 = warp_coord(y, v, +1.0f), cx2 = warp_coord(x, u, +1.0f);
+  float cy1 = warp_coord(y + row0, v, -1.0f), cx1 = warp_coord(x, u, -1.0f);
+  float cy2 = warp_coord(y + row0, v, +1.0f), cx2 = warp_coord(x, u, +1.0f);
   o1.p[(long)b * o1.stride + (long)y * o1.pitch + x] =
-      warp_sample(im1.p + (long)b * im1.stride, im1.pitch, im1.H, im1.W, cy1, cx1);
+      warp_sample(im1.p + (long)b * im1.stride, im1.pitch, im1.H, im1.W, cy1, cx1, img_row0, Hg);
   o2.p[(long)b * o2.stride + (long)y * o2.pitch + x] =
-      warp_sample(im2.p + (long)b * im2.stride, im2.pitch, im2.H, im2.W, cy2, cx2);
+      warp_sample(im2.p + (long)b * im2.stride, im2.pitch, im2.H, im2.W, cy2, cx2, img_row0, Hg);
 }
 __global__ void warp_coords_kernel(Img img, Img cy, Img cx, Img o) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
@@ -234,9 +242,10 @@ __global__ void warp_coords_kernel(Img img, Img cy, Img cx, Img o) {
       warp_sample(img.p + (long)b * img.stride, img.pitch, img.H, img.W, fy, fx);
 }
 void launch_warp_pair(const Img& im1, const Img& im2, const Img& us, const Img& vs, const Img& out1, const Img& out2,
-                      cudaStream_t s, LaunchCounter& lc) {
+                      cudaStream_t s, LaunchCounter& lc, int row0, int img_row0, int Hg) {
   dim3 b(32, 8);
-  warp_pair_kernel<<<grid2d(im1.W, im1.H, im1.batch, b), b, 0, s>>>(im1, im2, us, vs, out1, out2);
+  if (Hg <= 0) Hg = im1.H;
+  warp_pair_kernel<<<grid2d(us.W, us.H, us.batch, b), b, 0, s>>>(im1, im2, us, vs, out1, out2, row0, img_row0, Hg);
   lc.n += 1;
 }
 void launch_warp_coords(const Img& img, const Img& cy, const Img& cx, const Img& out, cudaStream_t s,

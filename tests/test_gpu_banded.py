@@ -1,0 +1,67 @@
+"""Row-band domain decomposition (BASELINE configs[4]) on ONE GPU: N virtual bands driven by N host threads
+over the library's local communicator must reproduce the single-band result BIT FOR BIT on every owned row -- ghost
+frames, ghost-row exchanges, global-coordinate resample / warp, all-reduced maxima and residuals, all-gathered spline."""
+import numpy as np
+import pytest
+
+import ofri_oracle as O
+
+pytestmark = pytest.mark.gpu
+HS_DEF = dict(warping=True, bilinear=True, final_scaling=True)
+
+
+@pytest.fixture(scope="module")
+def ofri():
+    import opticalflow_ri_b200 as o
+    return o
+
+
+def same(a, b, what):
+    if not np.array_equal(a, b):
+        d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+        rows = np.unique(np.nonzero(a != b)[0])
+        raise AssertionError("%s not bit-exact: max|d| = %g, %d px differ, rows %s..%s" %
+                             (what, d.max(), np.count_nonzero(a != b), rows[:3], rows[-3:]))
+
+
+CASES = {
+    "ex3": lambda o: o.make_params(o.hs_algo([45, 21], 40), o.ls_algo(5), filter_sigma=3.4, filter_opt_sigma=0.48,
+                                   pyramid_levels=2, **HS_DEF),
+    "hs_l1": lambda o: o.make_params(o.hs_algo([21], 50), filter_sigma=3.4, pyramid_levels=1, **HS_DEF),
+    "hs_l3": lambda o: o.make_params(o.hs_algo([45, 30, 21], 36), filter_sigma=3.4, pyramid_levels=3, **HS_DEF),
+    "ls_main": lambda o: o.make_params(o.ls_algo(0.1), filter_sigma=3.4, pyramid_levels=2),
+    "ls_stop": lambda o: o.make_params(o.hs_algo([45, 21], 20), o.ls_algo(5, 60, 2e-5), filter_sigma=3.4,
+                                       filter_opt_sigma=0.48, pyramid_levels=2, **HS_DEF),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("nb,shape", [(1, (128, 96)), (2, (256, 200)), (4, (512, 203))])
+def test_band_invariance_local(ofri, case, nb, shape):
+    from opticalflow_ri_b200 import banded
+    H, W = shape
+    I0, I1 = O.synthetic_piv_pair(H, W, seed=11)
+    mk = lambda: CASES[case](ofri)
+    h = ofri.Handle(0)
+    try:
+        Uref, Vref = h.pyramidal_flow(I0, I1, mk())
+    finally:
+        h.close()
+    U, V = banded.flow_banded_local(I0, I1, mk, nb)
+    same(U, Uref, "U %s nb=%d" % (case, nb))
+    same(V, Vref, "V %s nb=%d" % (case, nb))
+
+
+def test_band_plan_and_errors(ofri):
+    h = ofri.Handle(0)
+    try:
+        p = CASES["ex3"](ofri)
+        b = h.band_plan(1024, 1024, p, 1, 4)
+        assert (b.own0, b.own1) == (256, 512) and b.in0 < b.own0 - b.ghost and b.in1 > b.own1 + b.ghost
+        assert b.exchange % h.get_option("hs_fuse") == 0
+        with pytest.raises(NotImplementedError):      # 1000 is not divisible by 3 ranks x 2
+            h.band_plan(1000, 64, p, 0, 3)
+        with pytest.raises(ValueError):               # 8 coarse rows per rank < 16-row exchange
+            h.band_plan(64, 64, p, 0, 4)
+    finally:
+        h.close()
