@@ -31,7 +31,8 @@ struct StageTime { std::string name; cudaEvent_t e0, e1; };
 
 struct ofri_ctx {
   int device = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr, s_in = nullptr, s_out = nullptr, s_aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // U / V spline up-samples run concurrently on stream + s_aux
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   std::string err;
   // bump arena for per-call workspace (stream-ordered reuse)
@@ -284,7 +285,7 @@ int check_params(ofri_handle h, const ofri_params* p, int H, int W) {
 struct Workspace {
   Img lvl1, lvl2, warp1, warp2, work1, work2, opt1, opt2, tmp, fx, fy, ft, U[2], V[2], U0, V0, Uacc, Vacc, us, vs;
   LsPlanes ls;
-  ImgD M1, T1, M2;
+  ImgD M1, T1, M2, M1b, T1b, M2b;
   double* hs_acc = nullptr;
   double* ls_errs = nullptr;
   int* ls_state = nullptr;
@@ -315,6 +316,9 @@ void plan_workspace(Bump& b, int batch, int H, int W, const ofri_params* p, Work
     ws->M1 = b.planed(batch, hc, wc);
     ws->T1 = b.planed(batch, H, wc);
     ws->M2 = b.planed(batch, H, wc);
+    ws->M1b = b.planed(batch, hc, wc);
+    ws->T1b = b.planed(batch, H, wc);
+    ws->M2b = b.planed(batch, H, wc);
   }
   if (has_ls) {
     for (int c = 0; c < 8; ++c) ws->ls.c[c] = b.plane(batch, H, W);
@@ -440,9 +444,14 @@ int run_pyramid(ofri_handle h, const Img& im1, const Img& im2, const ofri_params
           my = (float)Hl / (float)prevH;
         }
         ImgD M1 = viewd(ws.M1, prevH, prevW), T1 = viewd(ws.T1, Hl, prevW), M2 = viewd(ws.M2, Hl, prevW);
-        // mul == 1 must still multiply when scaling is on (x * 1.0f is exact), so pass the flag through mul != 1
+        ImgD M1b = viewd(ws.M1b, prevH, prevW), T1b = viewd(ws.T1b, Hl, prevW), M2b = viewd(ws.M2b, Hl, prevW);
+        // the tridiagonal solves have one thread per line (latency bound): run the two components side by side
+        cudaEventRecord(h->ev_fork, s);
+        cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0);
         launch_spline(ua, un, mx, sy, sx, M1, T1, M2, s, h->lc);
-        launch_spline(va, vn, my, sy, sx, M1, T1, M2, s, h->lc);
+        launch_spline(va, vn, my, sy, sx, M1b, T1b, M2b, h->s_aux, h->lc);
+        cudaEventRecord(h->ev_join, h->s_aux);
+        cudaStreamWaitEvent(s, h->ev_join, 0);
       } else {
         launch_copy(un, ua, s, h->lc);
         launch_copy(vn, va, s, h->lc);
@@ -686,7 +695,7 @@ int make_band_plan(ofri_handle h, int H, int W, const ofri_params* p, int rank, 
 struct BandWs {
   Img lvl1, lvl2, warp1, warp2, work1, work2, opt1, opt2, tmp, fx, fy, ft, U[2], V[2], U0, V0, Uacc, Vacc, us, vs, gU, gV;
   LsPlanes ls;
-  ImgD M1, T1, M2;
+  ImgD M1, T1, M2, M1b, T1b, M2b;
   double* hs_acc = nullptr;
   double* ls_errs = nullptr;
   int* ls_state = nullptr;
@@ -723,6 +732,9 @@ void plan_band_ws(Bump& b, const BandPlanInt& bp, int W, const ofri_params* p, B
     ws->M1 = b.planed(1, c.Hl, c.Wl);
     ws->T1 = b.planed(1, rows, c.Wl);
     ws->M2 = b.planed(1, rows, c.Wl);
+    ws->M1b = b.planed(1, c.Hl, c.Wl);
+    ws->T1b = b.planed(1, rows, c.Wl);
+    ws->M2b = b.planed(1, rows, c.Wl);
   }
   if (has_ls) {
     for (int c = 0; c < 8; ++c) ws->ls.c[c] = b.plane(1, rows, W);
@@ -910,8 +922,13 @@ int run_pyramid_banded(ofri_handle h, const float* d_im1, const float* d_im2, in
           my = (float)bl.Hl / (float)pl.Hl;
         }
         ImgD M1 = viewd(ws.M1, pl.Hl, pl.Wl), T1 = viewd(ws.T1, rows, pl.Wl), M2 = viewd(ws.M2, rows, pl.Wl);
+        ImgD M1b = viewd(ws.M1b, pl.Hl, pl.Wl), T1b = viewd(ws.T1b, rows, pl.Wl), M2b = viewd(ws.M2b, rows, pl.Wl);
+        cudaEventRecord(h->ev_fork, s);
+        cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0);
         launch_spline(gU, un, mx, sy, sx, M1, T1, M2, s, h->lc, bl.ext0, bl.Hl);
-        launch_spline(gV, vn, my, sy, sx, M1, T1, M2, s, h->lc, bl.ext0, bl.Hl);
+        launch_spline(gV, vn, my, sy, sx, M1b, T1b, M2b, h->s_aux, h->lc, bl.ext0, bl.Hl);
+        cudaEventRecord(h->ev_join, h->s_aux);
+        cudaStreamWaitEvent(s, h->ev_join, 0);
       }
       {
         Timed t(h, "warp");
@@ -1024,7 +1041,8 @@ int ofri_create(int device, ofri_handle* out) {
   h->device = device;
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return fail(nullptr, OFRI_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
@@ -1033,6 +1051,8 @@ int ofri_create(int device, ofri_handle* out) {
     cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming);
   }
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   h->stream = h->own_stream;
   *out = h;
   return OFRI_OK;
@@ -1055,6 +1075,9 @@ int ofri_destroy(ofri_handle h) {
   cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->s_in);
   cudaStreamDestroy(h->s_out);
+  cudaStreamDestroy(h->s_aux);
+  cudaEventDestroy(h->ev_fork);
+  cudaEventDestroy(h->ev_join);
   delete h;
   return OFRI_OK;
 }

@@ -149,18 +149,24 @@ __global__ void spline_solve_kernel(const TIn* __restrict__ y, long y_elem, long
   const TIn* yy = y + (long)blockIdx.z * y_batch + (long)l * y_line;
   double* mm = M + (long)blockIdx.z * m_batch + (long)l * m_line;
   const int m = n - 2;
-  double y0 = (double)yy[0], y1 = (double)yy[y_elem], y2;
-  double dp = 0.0;
-  for (int i = 0; i < m; ++i) {
+  // The recurrences are sequential per line (one thread each, so a launch is latency bound): the loops are unrolled
+  // so that the loads of the next steps -- whose addresses do not depend on the recurrence -- are in flight early.
+  double y0 = (double)yy[0], y1 = (double)yy[y_elem], y2 = (double)yy[2 * y_elem];
+  double dp = ddiv(dmul(6.0, dadd(dsub(y0, dmul(2.0, y1)), y2)), sys.den[0]);
+  mm[m_elem] = dp;
+  y0 = y1;
+  y1 = y2;
+#pragma unroll 8
+  for (int i = 1; i < m; ++i) {
     y2 = (double)yy[(long)(i + 2) * y_elem];
     double rhs = dmul(6.0, dadd(dsub(y0, dmul(2.0, y1)), y2));
-    if (i == 0) dp = ddiv(rhs, sys.den[0]);
-    else dp = ddiv(dsub(rhs, dmul(sys.lo[i], dp)), sys.den[i]);
+    dp = ddiv(dsub(rhs, dmul(sys.lo[i], dp)), sys.den[i]);
     mm[(long)(i + 1) * m_elem] = dp;
     y0 = y1;
     y1 = y2;
   }
-  double next = mm[(long)m * m_elem];              // M[m] = dp[m-1]
+  double next = dp;                                // M[m] = dp[m-1]
+#pragma unroll 8
   for (int i = m - 2; i >= 0; --i) {
     double v = dsub(mm[(long)(i + 1) * m_elem], dmul(sys.cp[i], next));
     mm[(long)(i + 1) * m_elem] = v;
