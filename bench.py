@@ -32,6 +32,9 @@ H = W = 1024
 HS_NITER, HS_ALPHAS_IN_ORDER, LS_H, LS_ITERS, LEVELS = 600, [45.0, 21.0], 5.0, 60, 2
 FILTER, FILTER_OPT = 3.4, 0.48
 N_DISTINCT = 8            # distinct seeded synthetic pairs, tiled to fill the batch
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (64 pairs of 1024 x 1024, T = 4) from
+# the committed `ncu --set full` capture profiles/r1_ncu_hs_tma_fast_64pairs.txt; None until that capture exists
+ROOFLINE_TRAFFIC_BYTES_PER_LAUNCH = 1342233000 + 507894528   # read + write, 396 us launch
 
 
 def pix_iters_per_pair(h=H, w=W):
@@ -252,6 +255,8 @@ def run_ours(args):
     value = world * P * args.steps / (ms_max / 1e3)
 
     # ---- roofline of the dominant kernel, live: one instrumented step with per-stage CUDA events -------------------
+    # Stage timers bracket exactly the launches of one kernel family on the launching stream.  Algorithmic bytes
+    # (DESIGN.md section 4): fused Horn-Schunck sweeps 28 B / pixel / launch, fused Liu-Shen sweeps 48 B / pixel / launch.
     roof = None
     stage_ms = {}
     if rank == 0:
@@ -262,19 +267,48 @@ def run_ours(args):
         stage_ms = h.stage_timings()
         h.set_option("timing", 0)
         T = h.get_option("hs_fuse")
+        Tl = max(h.get_option("ls_fuse"), 1)
         peak, peak_src = measured_peak()
-        if stage_ms.get("hs_iterate"):
-            px = [int(np.round(H * 0.5)) * int(np.round(W * 0.5)), H * W]
-            nl = -(-HS_NITER // max(T, 1))
-            algo_bytes = sum(28.0 * p * P * nl for p in px)
-            ach = algo_bytes / (stage_ms["hs_iterate"] / 1e3) / 1e9
-            roof = {"bound": "hbm", "kernel": "hs_fused_kernel<T=%d> (fused Horn-Schunck Jacobi sweeps)" % T,
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": 28.0 * H * W * min(P, 64),
-                    "avg_launch_ms": stage_ms["hs_iterate"] / (2 * nl * -(-P // 64)),
-                    "note": "28 B/px/launch (read U,V,fx,fy,ft; write U,V) x pixels of all launches / CUDA-event time of "
-                            "the hs_iterate stage over one full step; T sweeps per launch"}
+        px_fine, px_coarse = H * W, int(np.round(H * 0.5)) * int(np.round(W * 0.5))
+        nl = -(-HS_NITER // max(T, 1))            # launches per level
+        chunk = min(P, 64)                        # pairs per launch (library chunking)
+        nchunks = -(-P // chunk)
+
+        def entry(kernel, stage, bytes_px, px_levels, launches_per_level, sweeps):
+            ms = stage_ms.get(stage)
+            if not ms:
+                return None
+            algo = sum(bytes_px * px * P * launches_per_level for px in px_levels)
+            ach = algo / (ms / 1e3) / 1e9
+            nlaunch = launches_per_level * len(px_levels) * nchunks
+            return {"kernel": kernel, "stage": stage, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "stage_ms": ms, "launches": nlaunch, "avg_launch_ms": ms / nlaunch,
+                    "algorithmic_bytes_per_launch": algo / nlaunch,
+                    "gpix_sweeps_per_s": sum(px_levels) * P * sweeps / (ms / 1e3) / 1e9,
+                    "frac_in_unfused_bytes": sum(px_levels) * P * sweeps * bytes_px / (ms / 1e3) / 1e9 / peak}
+
+        precise_mode = h.get_option("hs_precise")
+        fast_levels = [px_fine] if precise_mode == 1 else ([px_coarse, px_fine] if precise_mode == 0 else [])
+        prec_levels = [px_coarse] if precise_mode == 1 else ([] if precise_mode == 0 else [px_coarse, px_fine])
+        kernels = [k for k in (
+            entry("hs_tma_kernel<T=%d,R=8,NRG=8,fast> (persistent TMA-fed fused Horn-Schunck sweeps, finest level)" % T,
+                  "hs_iterate", 28.0, fast_levels, nl, HS_NITER),
+            entry("hs_tma_kernel<T=%d,R=4,NRG=8,precise> (same, reference arithmetic, coarse level)" % T,
+                  "hs_iterate_precise", 28.0, prec_levels, nl, HS_NITER),
+            entry("ls_fused_kernel<T=%d> (fused Liu-Shen sweeps, both levels)" % Tl,
+                  "ls_iterate", 48.0, [px_coarse, px_fine], -(-LS_ITERS // Tl), LS_ITERS)) if k]
+        if kernels:
+            dom = max(kernels, key=lambda k: k["stage_ms"])
+            roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
+                    "frac": dom["frac"], "traffic": ROOFLINE_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                    "avg_launch_ms": dom["avg_launch_ms"], "share_of_step": dom["stage_ms"] / sum(stage_ms.values()),
+                    "note": "achieved = algorithmic bytes of the kernel's launches in one step / their CUDA-event time "
+                            "(stage timer on the launching stream); 28 B/px/launch = read U,V,a,b,c + write U,V, for T "
+                            "fused sweeps; frac_in_unfused_bytes = the same sweeps/s expressed in the 28 B/px/sweep an "
+                            "unfused (T=1) sweep moves; traffic = dram read+write bytes per launch from the committed "
+                            "ncu capture (profiles/), null until captured for this launch shape",
+                    "kernels": kernels}
     # ---- end-to-end through the host-pointer C-ABI call (pinned host buffers) -----------------------------------------
     Pe = min(P, args.e2e_pairs)
     ha = torch.from_numpy(a_np[:Pe]).pin_memory()

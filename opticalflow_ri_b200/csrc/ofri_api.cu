@@ -361,10 +361,10 @@ int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws
     }
     int res;
     {
-      Timed t(h, "hs_iterate");
       // rounding differences made on a coarse level are amplified by the warp + solve of the finer levels (up to
       // x50 for weakly regularised problems), so the coarse levels default to the reference's exact arithmetic
       const bool precise = h->hs_precise >= 2 || (h->hs_precise == 1 && coarse_level);
+      Timed t(h, precise ? "hs_iterate_precise" : "hs_iterate");
       res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], a.hs_niter,
                               h->hs_fuse, h->hs_variant, precise, s, h->lc);
     }
@@ -797,8 +797,8 @@ int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs
     }
     int res;
     {
-      Timed t(h, "hs_iterate");
       const bool precise = h->hs_precise >= 2 || (h->hs_precise == 1 && coarse_level);
+      Timed t(h, precise ? "hs_iterate_precise" : "hs_iterate");
       const int niter = a.hs_niter;
       const int c0 = cur;
       HsHook hook = [&](int done, int which) {

@@ -333,7 +333,6 @@ static void launch_hs_fused_T(int variant, const Img& ui, const Img& vi, const I
     switch (variant) {
       default:
       case 0: launch_hs_fused_cfg<T, 4, 8, 32, true, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-      case 1: launch_hs_fused_cfg<T, 2, 16, 32, true, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
       case 2: launch_hs_fused_cfg<T, 4, 8, 16, true, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
     }
     return;
@@ -341,13 +340,8 @@ static void launch_hs_fused_T(int variant, const Img& ui, const Img& vi, const I
     switch (variant) {
       default:
       case 0: launch_hs_fused_cfg<T, 4, 8, 32, false, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-      case 1: launch_hs_fused_cfg<T, 4, 10, 32, false, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
       case 2: launch_hs_fused_cfg<T, 6, 6, 32, false, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-      case 3: launch_hs_fused_cfg<T, 3, 10, 32, false, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
       case 4: launch_hs_fused_cfg<T, 4, 8, 16, false, 4>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-      case 5: launch_hs_fused_cfg<T, 4, 10, NG64, false, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-      case 6: launch_hs_fused_cfg<T, 2, 16, 32, false, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-      case 7: launch_hs_fused_cfg<T, 8, 4, 32, false, 3>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
     }
   }
 }
@@ -547,13 +541,7 @@ static void launch_hs_regs_T(int variant, const Img& ui, const Img& vi, const Im
   switch (variant) {
     default:
     case 8: launch_hs_regs_cfg<T, 4, 8, PRECISE, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;     // 34 x 128, 256 thr
-    case 9: launch_hs_regs_cfg<T, 4, 16, PRECISE, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 66 x 128, 512 thr
     case 10: launch_hs_regs_cfg<T, 8, 8, PRECISE, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 66 x 128, 256 thr
-    case 11: launch_hs_regs_cfg<T, 6, 8, PRECISE, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 50 x 128, 256 thr
-    case 12: launch_hs_regs_cfg<T, 8, 4, PRECISE, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 34 x 128, 128 thr
-    case 13: launch_hs_regs_cfg<T, 6, 4, PRECISE, 3>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 26 x 128, 128 thr
-    case 14: launch_hs_regs_cfg<T, 4, 4, PRECISE, 4>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 18 x 128, 128 thr
-    case 15: launch_hs_regs_cfg<T, 6, 10, PRECISE, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;   // 62 x 128, 320 thr
   }
 }
 

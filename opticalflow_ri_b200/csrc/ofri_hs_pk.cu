@@ -264,13 +264,7 @@ static void launch_T(int variant, const Img& ui, const Img& vi, const Img& uo, c
   switch (variant) {
     default:
     case 16: launch_cfg<T, 4, 8, 2>(ui, vi, uo, vo, fx, fy, ft, s); break;     // 34 x 128, 256 threads, 2 CTAs / SM
-    case 17: launch_cfg<T, 4, 16, 1>(ui, vi, uo, vo, fx, fy, ft, s); break;    // 66 x 128, 512 threads
     case 18: launch_cfg<T, 8, 8, 1>(ui, vi, uo, vo, fx, fy, ft, s); break;     // 66 x 128, 256 threads
-    case 19: launch_cfg<T, 6, 8, 1>(ui, vi, uo, vo, fx, fy, ft, s); break;     // 50 x 128, 256 threads
-    case 20: launch_cfg<T, 8, 4, 2>(ui, vi, uo, vo, fx, fy, ft, s); break;     // 34 x 128, 128 threads, 2 CTAs / SM
-    case 21: launch_cfg<T, 6, 4, 3>(ui, vi, uo, vo, fx, fy, ft, s); break;     // 26 x 128, 128 threads, 3 CTAs / SM
-    case 22: launch_cfg<T, 4, 4, 4>(ui, vi, uo, vo, fx, fy, ft, s); break;     // 18 x 128, 128 threads, 4 CTAs / SM
-    case 23: launch_cfg<T, 6, 10, 1>(ui, vi, uo, vo, fx, fy, ft, s); break;    // 62 x 128, 320 threads
   }
 }
 

@@ -187,7 +187,7 @@ def test_hs_fused_bit_identical_to_simple(h, shape):
             h.set_option("hs_fuse", 0)
             Ur, Vr = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
             for T in (1, 2, 3, 4, 5, 6, 8):
-                for variant in (range(28) if precise == 0 else [0, 2, 24]):
+                for variant in ((0, 2, 4, 8, 10, 16, 18, 24, 25, 26, 27) if precise == 0 else (0, 2, 24)):
                     h.set_option("hs_fuse", T)
                     h.set_option("hs_variant", variant)
                     U, V = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
