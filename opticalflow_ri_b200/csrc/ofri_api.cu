@@ -45,7 +45,7 @@ struct ofri_ctx {
   std::map<int, DevSplineSys> splines;
   LaunchCounter lc;
   // options
-  int hs_fuse = 4, hs_variant = 24, ls_fuse = 2, ls_variant = 4, chunk_pairs = 0, timing = 0;
+  int hs_fuse = 4, hs_variant = 24, ls_fuse = 2, ls_variant = 8, chunk_pairs = 0, timing = 0;
   int hs_precise = 1;   // 0 = fast f32/FMA everywhere, 1 = reference arithmetic on the coarse pyramid levels, 2 = everywhere
   // row-band (domain-decomposed) mode
   ofri::Comm* comm = nullptr;

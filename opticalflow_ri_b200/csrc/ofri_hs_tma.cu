@@ -22,71 +22,10 @@
 // HBM reads of tile i+1 therefore run under the arithmetic of tile i, with a single CTA (8-12 warps, up to 255
 // registers per thread) per SM and no redundant staging of state through shared memory during the sweeps.
 // Algorithmic HBM traffic: 28 B per pixel per launch (read U, V, a, b, c; write U, V) for T sweeps.
-#include <cuda.h>
-
 #include "ofri_hs_common.cuh"
+#include "ofri_tma.cuh"
 
 namespace ofri {
-
-namespace {
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-    cudaGetLastError();
-  }
-  return fn;
-}
-
-// 3-D map over a plane stack: dims (W, H, batch), strides (pitch, stride) floats, box (128, box_rows, 1), zero OOB fill
-bool make_map(CUtensorMap* m, const Img& img, int box_rows) {
-  EncodeTiledFn enc = encode_fn();
-  if (!enc) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)img.W, (cuuint64_t)img.H, (cuuint64_t)img.batch};
-  cuuint64_t strides[2] = {(cuuint64_t)img.pitch * 4, (cuuint64_t)img.stride * 4};
-  cuuint32_t box[3] = {128, (cuuint32_t)box_rows, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, img.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
-      "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(z), "r"(bar)
-      : "memory");
-}
-
-}  // namespace
 
 template <int T, int R, int NRG>
 struct TmCfg {

@@ -143,6 +143,10 @@ LocalGroup* make_local_group(int n);
 void free_local_group(LocalGroup* g);
 Comm* make_local_comm(LocalGroup* g, int rank, std::string* err);
 
+// persistent TMA-fed fused Liu-Shen block (ofri_ls_tma.cu): T sweeps ui, vi -> uo, vo; false = not applicable
+bool launch_ls_tma(int T, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const LsPlanes& co, float hpar,
+                   int k0, int maxiter, double tol, double* errs, const LsBand& band, cudaStream_t s);
+
 const char* kernel_build_info();
 
 }  // namespace ofri

@@ -13,6 +13,7 @@
 // Algorithmic HBM traffic of a sweep launch: 48 B per pixel (read u, v and 8 coefficient planes; write u, v).
 #include "ofri_internal.h"
 #include "ofri_pixel.cuh"
+#include "ofri_ls_common.cuh"
 
 namespace ofri {
 
@@ -107,25 +108,6 @@ void launch_ls_coefficients(const Img& im1, const Img& im2, float hpar, const Ls
 // ---------------------------------------------------------------------------------------------------------------
 // stopping rule helpers.  state[pair*4 + {0: replay source buffer, 1: replay count, 2: final buffer, 3: iters}]
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double ls_total_error(const double* e, double npix) {
-  // two separate square roots, then the sum (LS:79); f32 rounding of each norm as numba's np.linalg.norm returns f32
-  return ((double)(float)sqrt(e[0]) + (double)(float)sqrt(e[1])) / npix;
-}
-// true iff the pair must NOT run sweep k (k >= 1): some earlier sweep already met the tolerance.  Launches are
-// issued in order and a stopped pair writes nothing (its sums stay 0 -> error 0 -> "stopped"), so it suffices to
-// look back over the sweeps of the previous launch (`lookback` = the fuse factor): this also catches a trip in the
-// MIDDLE of a fused block whose later sweeps went back above the tolerance.
-__device__ __forceinline__ bool ls_stopped_before(const double* errs_pair, int k, double tol, double npix,
-                                                  int lookback) {
-  int first = k - lookback;
-  if (first < 0) first = 0;
-  for (int i = first; i < k; ++i) {
-    double te = ls_total_error(errs_pair + 2 * i, npix);
-    if (!(te > tol)) return true;
-  }
-  return false;
-}
-
 // block-level f64 sum of two values, one atomicAdd per CTA
 __device__ __forceinline__ void block_atomic_add2(double su, double sv, double* dst, double* sh /* >= 64 */) {
   for (int o = 16; o > 0; o >>= 1) {
@@ -244,83 +226,6 @@ struct LsCfg {
   static constexpr int SMEM_BYTES = 12 * PLANE * 4;    // u[2], v[2], 8 coefficient planes
   static_assert((NG == 16 || NG == 32) && NT % 32 == 0 && T <= HX && TW > 0 && TH > 0 && NT <= 1024, "bad tile");
 };
-
-struct LsEdge {
-  bool left_edge;
-  int right_j, top_j, bot_j;
-};
-
-// one shared row of this thread's strip: columns sx-1 .. sx+4 of u and v; EDGE: 'nearest' clamp in x
-template <bool EDGE>
-__device__ __forceinline__ void ls_row6(const float* __restrict__ pu, const float* __restrict__ pv, const LsEdge& eg,
-                                        float (&du)[6], float (&dv)[6]) {
-  float4 qu = *reinterpret_cast<const float4*>(pu);
-  float4 qv = *reinterpret_cast<const float4*>(pv);
-  du[1] = qu.x; du[2] = qu.y; du[3] = qu.z; du[4] = qu.w;
-  dv[1] = qv.x; dv[2] = qv.y; dv[3] = qv.z; dv[4] = qv.w;
-  du[0] = __shfl_up_sync(0xffffffffu, qu.w, 1);
-  du[5] = __shfl_down_sync(0xffffffffu, qu.x, 1);
-  dv[0] = __shfl_up_sync(0xffffffffu, qv.w, 1);
-  dv[5] = __shfl_down_sync(0xffffffffu, qv.x, 1);
-  if (EDGE) {   // the left neighbour of column 0 is column 0; the right neighbour of column W-1 is column W-1
-    if (eg.left_edge) { du[0] = du[1]; dv[0] = dv[1]; }
-    if (eg.right_j == 0) { du[2] = du[1]; dv[2] = dv[1]; }
-    if (eg.right_j == 1) { du[3] = du[2]; dv[3] = dv[2]; }
-    if (eg.right_j == 2) { du[4] = du[3]; dv[4] = dv[3]; }
-    if (eg.right_j == 3) { du[5] = du[4]; dv[5] = dv[4]; }
-  }
-}
-
-// 4 pixels of one strip row.  (uu, um, ud) = window rows above / at / below, already clamped in x (and in y by the
-// caller's choice of rows).  ztop / zbot: the row above / below lies outside the image (zero padding of H8).
-template <bool EDGE>
-__device__ __forceinline__ void ls_row_update(const float (&uu)[6], const float (&um)[6], const float (&ud)[6],
-                                              const float (&vu)[6], const float (&vm)[6], const float (&vd)[6],
-                                              const float* __restrict__ sC, int plane, int so, float hpar, bool ztop,
-                                              bool zbot, const LsEdge& eg, float (&ou)[4], float (&ov)[4]) {
-  float4 q0 = *reinterpret_cast<const float4*>(sC + 0 * plane + so);
-  float4 q1 = *reinterpret_cast<const float4*>(sC + 1 * plane + so);
-  float4 q2 = *reinterpret_cast<const float4*>(sC + 2 * plane + so);
-  float4 q3 = *reinterpret_cast<const float4*>(sC + 3 * plane + so);
-  float4 q4 = *reinterpret_cast<const float4*>(sC + 4 * plane + so);
-  float4 q5 = *reinterpret_cast<const float4*>(sC + 5 * plane + so);
-  float4 q6 = *reinterpret_cast<const float4*>(sC + 6 * plane + so);
-  float4 q7 = *reinterpret_cast<const float4*>(sC + 7 * plane + so);
-  const float c0[4] = {q0.x, q0.y, q0.z, q0.w}, c1[4] = {q1.x, q1.y, q1.z, q1.w};
-  const float c2[4] = {q2.x, q2.y, q2.z, q2.w}, c3[4] = {q3.x, q3.y, q3.z, q3.w};
-  const float c4[4] = {q4.x, q4.y, q4.z, q4.w}, c5[4] = {q5.x, q5.y, q5.z, q5.w};
-  const float c6[4] = {q6.x, q6.y, q6.z, q6.w}, c7[4] = {q7.x, q7.y, q7.z, q7.w};
-  // zero-padded column sums for H8 (interior: identical to the clamped values)
-  float zsu[6], zsv[6], zmu[6], zmv[6];
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    float a = uu[c], d = ud[c], e = vu[c], f = vd[c];
-    if (EDGE) {
-      if (ztop) { a = 0.0f; e = 0.0f; }
-      if (zbot) { d = 0.0f; f = 0.0f; }
-    }
-    zsu[c] = fadd(a, d);
-    zsv[c] = fadd(e, f);
-    zmu[c] = um[c];
-    zmv[c] = vm[c];
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float vlu = zsu[j], vru = zsu[j + 2], wu_ = zmu[j], eu_ = zmu[j + 2];
-    float vlv = zsv[j], vrv = zsv[j + 2], wv_ = zmv[j], ev_ = zmv[j + 2];
-    if (EDGE) {
-      if (eg.left_edge && j == 0) { vlu = 0.0f; vlv = 0.0f; wu_ = 0.0f; wv_ = 0.0f; }
-      if (eg.right_j == j) { vru = 0.0f; vrv = 0.0f; eu_ = 0.0f; ev_ = 0.0f; }
-    }
-    float h8u = ls_h8_cols(vlu, zsu[j + 1], vru, wu_, eu_);
-    float h8v = ls_h8_cols(vlv, zsv[j + 1], vrv, wv_, ev_);
-    LsNb nu{uu[j + 1], ud[j + 1], um[j], um[j + 2], uu[j], uu[j + 2], ud[j], ud[j + 2]};
-    LsNb nv{vu[j + 1], vd[j + 1], vm[j], vm[j + 2], vu[j], vu[j + 2], vd[j], vd[j + 2]};
-    LsCoef c;
-    c.IIx = c0[j]; c.IIy = c1[j]; c.II = c2[j]; c.Ixt = c3[j]; c.Iyt = c4[j]; c.B11 = c5[j]; c.B12 = c6[j]; c.B22 = c7[j];
-    ls_update2(nu, nv, h8u, h8v, c, hpar, &ou[j], &ov[j]);
-  }
-}
 
 template <int T, int R, int NRG, int NG, bool EDGE, bool LAST>
 __device__ __forceinline__ void ls_sweep(const float* __restrict__ cu, const float* __restrict__ cv,
@@ -577,7 +482,11 @@ void launch_ls_solve(const Img& ua, const Img& va, const Img& ub, const Img& vb,
   if (can_fuse && T >= 1) {
     nfull = maxiter / T;
     for (int i = 0; i < nfull; ++i) {
-      launch_ls_fused(T, variant, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, band, s);
+      bool done = false;
+      if (variant >= 8)      // persistent TMA-fed register-resident kernel (ofri_ls_tma.cu); launch i reads buffer (i & 1)
+        done = (i & 1) ? launch_ls_tma(T, ub, vb, ua, va, coef, hpar, i * T, maxiter, tol, errs, band, s)
+                       : launch_ls_tma(T, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, band, s);
+      if (!done) launch_ls_fused(T, variant >= 8 ? 4 : variant, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, band, s);
       lc.n += 1;
       // launch i wrote buffer b (odd launches write a); band mode: sum the block's residuals over all bands and refresh
       // the ghost rows of the buffer just written

@@ -276,7 +276,7 @@ def test_ls_fused_bit_identical_and_midblock_stop(h, shape):
             h.set_option("ls_fuse", 0)
             Ur, Vr, er, itr = h.ls_compute(g1, g2, U0, V0, 5, maxiter=maxiter, tol=tol)
             for T in (1, 2, 3, 4):
-                for lv in range(6):
+                for lv in (0, 1, 2, 3, 4, 5, 8):
                     h.set_option("ls_fuse", T)
                     h.set_option("ls_variant", lv)
                     U, V, e, it = h.ls_compute(g1, g2, U0, V0, 5, maxiter=maxiter, tol=tol)
@@ -290,7 +290,7 @@ def test_ls_fused_bit_identical_and_midblock_stop(h, shape):
                     np.testing.assert_allclose(e, er, rtol=1e-5)
     finally:
         h.set_option("ls_fuse", 2)
-        h.set_option("ls_variant", 4)
+        h.set_option("ls_variant", 8)
 
 
 def test_ls_stop_rule_vs_oracle(h):
