@@ -148,7 +148,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = args.cpu_cores or os.cpu_count() or 1
     steps = max(1, args.steps)
     vals = []
     last = None
@@ -363,6 +363,7 @@ def main():
     ap.add_argument("--e2e-pairs", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=384)
+    ap.add_argument("--cpu-cores", type=int, default=0, help="host processes of the reference arm (0 = all cores)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--hs-fuse", type=int, default=None)
     ap.add_argument("--hs-variant", type=int, default=None)

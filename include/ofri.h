@@ -183,6 +183,9 @@ OFRI_API int ofri_local_group_destroy(void* group);
 OFRI_API int ofri_comm_init_local(ofri_handle h, void* group, int rank);   /* call from the thread that drives `rank` */
 OFRI_API int ofri_comm_destroy(ofri_handle h);
 OFRI_API int ofri_band_plan(ofri_handle h, int H, int W, const ofri_params* p, int rank, int nranks, ofri_band* out);
+/* the same without a handle / GPU (planning on a loader or scheduler host): options passed explicitly, 0 = default */
+OFRI_API int ofri_band_plan_host(int H, int W, const ofri_params* p, int rank, int nranks, int hs_fuse, int band_exchange,
+                        int band_reach, ofri_band* out);
 /* d_im*_rows: DEVICE, rows [in0, in1) of the frames, dense (pitch W); d_u_rows / d_v_rows: DEVICE, rows [own0, own1);
  * d_err_out: optional DEVICE [levels][2].  Collective: every rank of the communicator must call it.  Synchronises the
  * handle's stream before returning. */

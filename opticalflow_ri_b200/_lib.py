@@ -81,6 +81,8 @@ _SIGNATURES = {
     "ofri_comm_init_local": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "ofri_comm_destroy": (C.c_int, [_H]),
     "ofri_band_plan": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(Params), C.c_int, C.c_int, C.POINTER(Band)]),
+    "ofri_band_plan_host": (C.c_int, [C.c_int, C.c_int, C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(Band)]),
     "ofri_pyramidal_flow_banded_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Params),
                                                  C.c_void_p, C.c_void_p, C.c_void_p]),
 }

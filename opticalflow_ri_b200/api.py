@@ -301,6 +301,18 @@ class Handle:
         return coef[:, 0] if single else coef
 
 
+def band_plan_host(H, W, params, rank, nranks, hs_fuse=4, band_exchange=0, band_reach=0):
+    """Row-band plan without a GPU (ofri_band_plan_host): which rows a rank owns and which input rows it needs."""
+    b = Band()
+    L = _lib.lib()
+    rc = L.ofri_band_plan_host(int(H), int(W), C.byref(params), int(rank), int(nranks), int(hs_fuse), int(band_exchange),
+                               int(band_reach), C.byref(b))
+    if rc != 0:
+        msg = L.ofri_last_error(None).decode()
+        raise _EXC.get(rc, OfriError)(msg) if rc in _EXC else OfriError(rc, msg)
+    return b
+
+
 def nccl_unique_id():
     """128 opaque bytes from ncclGetUniqueId (rank 0 creates them and ships them to the other ranks)."""
     buf = C.create_string_buffer(128)

@@ -649,7 +649,14 @@ struct BandPlanInt {
   BandLevel lv[16];
 };
 
+int make_band_plan_opts(ofri_handle h, int H, int W, const ofri_params* p, int rank, int n, int hs_fuse,
+                        int band_exchange, int band_reach, BandPlanInt* bp);
 int make_band_plan(ofri_handle h, int H, int W, const ofri_params* p, int rank, int n, BandPlanInt* bp) {
+  return make_band_plan_opts(h, H, W, p, rank, n, h->hs_fuse, h->band_exchange, h->band_reach, bp);
+}
+// h may be NULL (host-only planning: errors then go to the global message)
+int make_band_plan_opts(ofri_handle h, int H, int W, const ofri_params* p, int rank, int n, int hs_fuse,
+                        int band_exchange, int band_reach, BandPlanInt* bp) {
   int rc = check_params(h, p, H, W);
   if (rc) return rc;
   if (n < 1 || rank < 0 || rank >= n) return fail(h, OFRI_ERR_INVALID, "bad rank %d of %d", rank, n);
@@ -660,12 +667,12 @@ int make_band_plan(ofri_handle h, int H, int W, const ofri_params* p, int rank, 
   const int fmax = 1 << (L - 1);
   if (H % (n * fmax) != 0)
     return fail(h, OFRI_ERR_UNSUPPORTED, "row-band mode needs H (%d) divisible by ranks x 2^(levels-1) = %d", H, n * fmax);
-  int T = h->hs_fuse > 0 ? (h->hs_fuse == 7 ? 6 : (h->hs_fuse > 8 ? 8 : h->hs_fuse)) : 1;
-  int E = h->band_exchange > 0 ? h->band_exchange : 16;
+  int T = hs_fuse > 0 ? (hs_fuse == 7 ? 6 : (hs_fuse > 8 ? 8 : hs_fuse)) : 1;
+  int E = band_exchange > 0 ? band_exchange : 16;
   E = (E + T - 1) / T * T;
   bp->L = L;
   bp->E = E;
-  bp->Rw = h->band_reach > 0 ? h->band_reach : 8;
+  bp->Rw = band_reach > 0 ? band_reach : 8;
   bp->G = E + 2 + bp->Rw;
   double scale = 1.0 / std::pow(2.0, L - 1);
   long in0 = H, in1 = 0;
@@ -1514,6 +1521,19 @@ int ofri_band_plan(ofri_handle h, int H, int W, const ofri_params* p, int rank, 
   if (!out) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
   BandPlanInt bp;
   int rc = make_band_plan(h, H, W, p, rank, nranks, &bp);
+  if (rc) return rc;
+  const BandLevel& f = bp.lv[bp.L - 1];
+  out->rank = rank; out->nranks = nranks;
+  out->own0 = f.own0; out->own1 = f.own1;
+  out->in0 = bp.in0; out->in1 = bp.in1;
+  out->ghost = bp.G; out->exchange = bp.E;
+  return OFRI_OK;
+}
+int ofri_band_plan_host(int H, int W, const ofri_params* p, int rank, int nranks, int hs_fuse, int band_exchange,
+                        int band_reach, ofri_band* out) {
+  if (!out) return fail(nullptr, OFRI_ERR_INVALID, "NULL pointer");
+  BandPlanInt bp;
+  int rc = make_band_plan_opts(nullptr, H, W, p, rank, nranks, hs_fuse, band_exchange, band_reach, &bp);
   if (rc) return rc;
   const BandLevel& f = bp.lv[bp.L - 1];
   out->rank = rank; out->nranks = nranks;
