@@ -23,7 +23,7 @@ std::mutex g_err_mutex;
 std::string g_last_error;   // errors without a handle (ofri_create)
 
 struct DevResizeTaps { int* xmin = nullptr; int* cnt = nullptr; double* w = nullptr; int kmax = 0; };
-struct DevSplineSys { double* lo = nullptr; double* cp = nullptr; double* den = nullptr; };
+struct DevSplineSys { double* lo = nullptr; double* cp = nullptr; double* den = nullptr; int conv = 0; double den_c = 0, cp_c = 0; };
 
 struct StageTime { std::string name; cudaEvent_t e0, e1; };
 
@@ -186,12 +186,19 @@ int get_spline_sys(ofri_handle h, int n, SplineSys* out) {
     OFRI_CUDA(h, cudaMemcpy(d.lo, t.lo.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
     OFRI_CUDA(h, cudaMemcpy(d.cp, t.cp.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
     OFRI_CUDA(h, cudaMemcpy(d.den, t.den.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+    d.conv = t.conv;
+    d.den_c = t.den[t.conv < m ? t.conv : m - 1];
+    d.cp_c = t.cp[t.conv < m ? t.conv : m - 1];
     it = h->splines.emplace(n, d).first;
   }
   out->lo = it->second.lo;
   out->cp = it->second.cp;
   out->den = it->second.den;
   out->n = n;
+  out->conv = it->second.conv;
+  out->den_c = it->second.den_c;
+  out->cp_c = it->second.cp_c;
+  out->rcp_c = 1.0 / it->second.den_c;
   return OFRI_OK;
 }
 

@@ -46,6 +46,8 @@ struct SplineSys {
   const double* cp = nullptr;
   const double* den = nullptr;
   int n = 0;
+  int conv = 0;              // rows [conv, n-3) of the reduced system share (den_c, cp_c) and lo == 1
+  double den_c = 0.0, cp_c = 0.0, rcp_c = 0.0;   // rcp_c = RN(1 / den_c)
 };
 
 struct LaunchCounter { int64_t n = 0; };

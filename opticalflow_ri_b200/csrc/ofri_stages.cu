@@ -149,15 +149,61 @@ __global__ void spline_solve_kernel(const TIn* __restrict__ y, long y_elem, long
   const TIn* yy = y + (long)blockIdx.z * y_batch + (long)l * y_line;
   double* mm = M + (long)blockIdx.z * m_batch + (long)l * m_line;
   const int m = n - 2;
-  // The recurrences are sequential per line (one thread each, so a launch is latency bound): the loops are unrolled
-  // so that the loads of the next steps -- whose addresses do not depend on the recurrence -- are in flight early.
+  // The recurrences are sequential per line (one thread each): a launch is bound by the latency of one step.  After a
+  // short head the rows of the system share one (den, cp) pair (SplineSys::conv), so the steady-state step keeps its
+  // constants in registers, divides by the constant with a reciprocal + two FMA corrections (correctly rounded: the
+  // same quotient as the IEEE division of the head, without its special-case call that stops the compiler from
+  // moving loads), and fetches its inputs CH steps ahead.
+  constexpr int CH = 8;
   double y0 = (double)yy[0], y1 = (double)yy[y_elem], y2 = (double)yy[2 * y_elem];
   double dp = ddiv(dmul(6.0, dadd(dsub(y0, dmul(2.0, y1)), y2)), sys.den[0]);
   mm[m_elem] = dp;
   y0 = y1;
   y1 = y2;
-#pragma unroll 8
-  for (int i = 1; i < m; ++i) {
+  const int conv = sys.conv < 1 ? 1 : sys.conv;
+  int i = 1;
+  for (; i < m && i < conv; ++i) {                   // head: tabulated constants, IEEE division
+    y2 = (double)yy[(long)(i + 2) * y_elem];
+    double rhs = dmul(6.0, dadd(dsub(y0, dmul(2.0, y1)), y2));
+    dp = ddiv(dsub(rhs, dmul(sys.lo[i], dp)), sys.den[i]);
+    mm[(long)(i + 1) * m_elem] = dp;
+    y0 = y1;
+    y1 = y2;
+  }
+  {
+    const double den = sys.den_c, rcp = sys.rcp_c;
+    // steady state (lo == 1): CH steps per trip; the loads of trip k+1 are issued before the arithmetic of trip k
+    double yb[CH], yn[CH];
+    if (i + CH <= m - 1) {
+#pragma unroll
+      for (int q = 0; q < CH; ++q) yb[q] = (double)yy[(long)(i + q + 2) * y_elem];
+    }
+    for (; i + CH <= m - 1; i += CH) {
+      const bool more = i + 2 * CH <= m - 1;
+      if (more) {
+#pragma unroll
+        for (int q = 0; q < CH; ++q) yn[q] = (double)yy[(long)(i + CH + q + 2) * y_elem];
+      }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        double rhs = dmul(6.0, dadd(dsub(y0, dmul(2.0, y1)), yb[q]));
+        double t = dsub(rhs, dp);
+        double qq = dmul(t, rcp);
+        double e = fma(-den, qq, t);
+        qq = fma(e, rcp, qq);
+        e = fma(-den, qq, t);
+        dp = fma(e, rcp, qq);
+        mm[(long)(i + q + 1) * m_elem] = dp;
+        y0 = y1;
+        y1 = yb[q];
+      }
+      if (more) {
+#pragma unroll
+        for (int q = 0; q < CH; ++q) yb[q] = yn[q];
+      }
+    }
+  }
+  for (; i < m; ++i) {                               // tail (and the special last row)
     y2 = (double)yy[(long)(i + 2) * y_elem];
     double rhs = dmul(6.0, dadd(dsub(y0, dmul(2.0, y1)), y2));
     dp = ddiv(dsub(rhs, dmul(sys.lo[i], dp)), sys.den[i]);
@@ -166,8 +212,33 @@ __global__ void spline_solve_kernel(const TIn* __restrict__ y, long y_elem, long
     y1 = y2;
   }
   double next = dp;                                // M[m] = dp[m-1]
-#pragma unroll 8
-  for (int i = m - 2; i >= 0; --i) {
+  i = m - 2;
+  {
+    const double cp = sys.cp_c;
+    double mb[CH], mn[CH];                           // steady state of the back substitution, same pipelining
+    if (i - CH + 1 >= conv) {
+#pragma unroll
+      for (int q = 0; q < CH; ++q) mb[q] = mm[(long)(i - q + 1) * m_elem];
+    }
+    for (; i - CH + 1 >= conv; i -= CH) {
+      const bool more = i - 2 * CH + 1 >= conv;
+      if (more) {
+#pragma unroll
+        for (int q = 0; q < CH; ++q) mn[q] = mm[(long)(i - CH - q + 1) * m_elem];
+      }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        double v = dsub(mb[q], dmul(cp, next));
+        mm[(long)(i - q + 1) * m_elem] = v;
+        next = v;
+      }
+      if (more) {
+#pragma unroll
+        for (int q = 0; q < CH; ++q) mb[q] = mn[q];
+      }
+    }
+  }
+  for (; i >= 0; --i) {
     double v = dsub(mm[(long)(i + 1) * m_elem], dmul(sys.cp[i], next));
     mm[(long)(i + 1) * m_elem] = v;
     next = v;
