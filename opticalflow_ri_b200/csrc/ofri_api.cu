@@ -584,7 +584,7 @@ int ensure_stage(ofri_handle h, size_t bytes) {
   return OFRI_OK;
 }
 
-int pick_chunk(ofri_handle h, int batch, int H, int W, const ofri_params* p, size_t extra_per_pair) {
+int pick_chunk(ofri_handle h, int batch, int H, int W, const ofri_params* p, size_t extra_per_pair, int cap = 64) {
   if (h->chunk_pairs > 0) return h->chunk_pairs < batch ? h->chunk_pairs : batch;
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
@@ -592,7 +592,7 @@ int pick_chunk(ofri_handle h, int batch, int H, int W, const ofri_params* p, siz
   size_t per_pair = workspace_bytes(1, H, W, p) + extra_per_pair;
   long n = (long)(budget / (per_pair ? per_pair : 1));
   if (n < 1) n = 1;
-  if (n > 64) n = 64;          // enough to fill 148 SMs many times over; keeps the working set bounded
+  if (n > cap) n = cap;        // enough to fill 148 SMs many times over; keeps the working set bounded
   return (int)(n < batch ? n : batch);
 }
 
@@ -850,12 +850,19 @@ int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs
     Timed t(h, "ls_iterate");
     LsBand band{o0, o1, npix};
     const int c0 = cur;
+    // The ghost frame holds E valid rows after an exchange and every sweep spoils one more: refresh it only when the
+    // next block would run out (the residual sums, in contrast, are needed by the very next launch's stopping rule).
+    const int Tl = h->ls_fuse > 4 ? 4 : (h->ls_fuse < 1 ? 1 : h->ls_fuse);
+    int spoiled = 0;
     LsHook hook = [&](int k0, int n, int written) {
       if (*comm_rc || !c || c->nranks == 1) return;
       if (n > 0 && c->allreduce_sum(ws.ls_errs + 2 * k0, 2 * (size_t)n, s)) {
         *comm_rc = fail(h, OFRI_ERR_COMM, "%s", c->error());
         return;
       }
+      spoiled += n;
+      if (written != 2 && spoiled + Tl <= E) return;
+      spoiled = 0;
       if (written == 0 || written == 2) *comm_rc = band_exchange_uv(h, U[c0], V[c0], o0, o1, E);
       if (!*comm_rc && (written == 1 || written == 2)) *comm_rc = band_exchange_uv(h, U[c0 ^ 1], V[c0 ^ 1], o0, o1, E);
     };
@@ -1198,7 +1205,8 @@ int ofri_pyramidal_flow(ofri_handle h, const float* im1, const float* im2, int b
   const size_t err_b = sizeof(float) * err_stride;
   // per pair staging: 2 inputs + 2 outputs + errors, double buffered
   const size_t slot_per_pair = 4 * plane_b + ((err_b + 255) & ~(size_t)255);
-  const int chunk = pick_chunk(h, batch, H, W, p, 2 * slot_per_pair);
+  // smaller chunks than the device-pointer path: the first H2D and the last D2H of a call are not overlapped
+  const int chunk = pick_chunk(h, batch, H, W, p, 2 * slot_per_pair, 32);
   rc = arena_reserve(h, workspace_bytes(chunk, H, W, p));
   if (rc) return rc;
   const size_t slot_b = ((slot_per_pair * chunk) + 255) & ~(size_t)255;

@@ -209,10 +209,13 @@ OFRI_HD void hs_update_n(float ua, float va, float a, float b, float c, float* u
 //   relative, i.e. the float32 results agree except in ~1e-9 of the evaluations (double-rounding ties).
 //   update: numba evaluates every f32 operation separately rounded, with a true division (HornSchunck.py:55-58).
 OFRI_HD float hs_den(float fx, float fy, float alpha2) { return fadd(fadd(alpha2, fmul(fx, fx)), fmul(fy, fy)); }
+// w6 = 2 w12 exactly, so w6 E + w12 C = w12 (2E + C): X = 2E + C is exact in f64 whenever the eight neighbours span
+// fewer than ~29 binary orders of magnitude, and then w12 X -- one rounding -- equals the value above (two exact products,
+// one rounded sum) bit for bit; one DFMA + one DMUL instead of two DMUL + one DADD.
 OFRI_HD float hs_avg_cols_precise(double vsl, double vsc, double vsr, double ml, double mr) {
   double E = dadd(vsc, dadd(ml, mr));
   double C = dadd(vsl, vsr);
-  return (float)dadd(dmul(E, (double)0.16666667f), dmul(C, (double)0.083333336f));
+  return (float)dmul(fma(2.0, E, C), (double)0.083333336f);
 }
 // RN(s / den) from rcp = RN(1/den): product, then two residual corrections (the sequence the hardware division
 // expands to, without its range checks: den >= alpha^2 is always a normal number here)
