@@ -49,8 +49,9 @@ typedef enum {
   OFRI_ERR_ALPHAS = -5,        /* HS alpha list exhausted (IndexError at HornSchunck.py:36) */
   OFRI_ERR_FILTER_OPT = -6,    /* optional adapter given without FILTER_OPT (TypeError at GPOF:380) */
   OFRI_ERR_TOO_SMALL = -7,     /* a pyramid level has < 4 samples on an axis (scipy raises in the spline) */
-  OFRI_ERR_UNSUPPORTED = -8,   /* branch outside the native path (biLinear=False "Liu-Shen warp", GPOF:204-221) */
-  OFRI_ERR_COMM = -9           /* NCCL / multi-GPU error */
+  OFRI_ERR_UNSUPPORTED = -8,   /* combination outside the native path (e.g. row-band mode with kLevels > 1) */
+  OFRI_ERR_COMM = -9,          /* NCCL / multi-GPU error */
+  OFRI_ERR_INDEX = -10         /* biLinear=False warp: a scatter target left the frame (IndexError at GPOF:207) */
 } ofri_status;
 
 typedef enum { OFRI_ALGO_NONE = -1, OFRI_ALGO_HS = 0, OFRI_ALGO_LS = 1 } ofri_algo_kind;
@@ -82,7 +83,7 @@ typedef struct {
   int32_t  pyramid_levels;           /* pyramidalLevels */
   int32_t  k_levels;                 /* kLevels */
   int32_t  warping;                  /* warping */
-  int32_t  bilinear;                 /* biLinear (must be 1 when warping) */
+  int32_t  bilinear;                 /* biLinear: 1 = symmetric bilinear warp, 0 = "Liu-Shen warp" of frame 1 (GPOF:204-221) */
   int32_t  intermediate_scaling;     /* pyramidalIntermediateScaling */
   int32_t  final_scaling;            /* pyramidalScaling */
   int32_t  n_taps_main;              /* FILTER taps (3 in the reference), 0 = off */
@@ -92,6 +93,10 @@ typedef struct {
   float    taps_opt[OFRI_MAX_GAUSS_TAPS];
   ofri_algo main_algo;               /* mainOFlowAlgoAdapter */
   ofri_algo opt_algo;                /* optionalOFlowAlgoAdapter (kind = OFRI_ALGO_NONE if absent) */
+  /* biLinear=False only: taps of gaussian_filter(x, 0.6*3, truncate=4.0/0.6*3) (GPOF:210-212; 73 taps), generated by
+   * the caller like the other taps; n_taps_lsw == 0 lets the library generate them (ofri_gaussian_taps) */
+  int32_t  n_taps_lsw;
+  float    taps_lsw[OFRI_MAX_GAUSS_TAPS];
 } ofri_params;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */
@@ -150,6 +155,11 @@ OFRI_API int ofri_warp_bilinear(ofri_handle h, const float* img, const float* cy
 /* the symmetric pair warp of updateNextPyramidalLevel (GPOF:200-201): im1 at (y-v/2, x-u/2), im2 at (y+v/2, x+u/2) */
 OFRI_API int ofri_warp_pair(ofri_handle h, const float* im1, const float* im2, const float* us, const float* vs,
                    int batch, int H, int W, float* out1, float* out2);
+/* the biLinear=False "Liu-Shen warp" of frame 1 by the (already up-sampled) flow (GPOF:190-196, 204-221); taps = the
+ * 73-tap kernel of gaussian_filter(x, 0.6*3, truncate=4.0/0.6*3) or NULL (generated by the library);
+ * OFRI_ERR_INDEX when a scatter target leaves the frame */
+OFRI_API int ofri_liu_shen_warp(ofri_handle h, const float* im1, const float* us, const float* vs, int batch, int H, int W,
+                       const float* taps, int n_taps, float* out);
 /* computeDerivatives as reached from compute(im1, im2) (HornSchunck.py:84, 107-127) */
 OFRI_API int ofri_hs_derivatives(ofri_handle h, const float* im1, const float* im2, int batch, int H, int W,
                         float* fx, float* fy, float* ft);

@@ -13,8 +13,8 @@ OFRI_MAX_ALPHAS = 64
 ALGO_NONE, ALGO_HS, ALGO_LS = -1, 0, 1
 
 OK = 0
-ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_ALPHAS, ERR_FILTER_OPT, ERR_TOO_SMALL, ERR_UNSUPPORTED, ERR_COMM = \
-    -1, -2, -3, -4, -5, -6, -7, -8, -9
+ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_ALPHAS, ERR_FILTER_OPT, ERR_TOO_SMALL, ERR_UNSUPPORTED, ERR_COMM, \
+    ERR_INDEX = -1, -2, -3, -4, -5, -6, -7, -8, -9, -10
 
 
 class OfriError(RuntimeError):
@@ -35,7 +35,8 @@ class Params(C.Structure):
                 ("bilinear", C.c_int32), ("intermediate_scaling", C.c_int32), ("final_scaling", C.c_int32),
                 ("n_taps_main", C.c_int32), ("n_taps_opt", C.c_int32), ("refilter_k", C.c_int32),
                 ("taps_main", C.c_float * OFRI_MAX_GAUSS_TAPS), ("taps_opt", C.c_float * OFRI_MAX_GAUSS_TAPS),
-                ("main_algo", Algo), ("opt_algo", Algo)]
+                ("main_algo", Algo), ("opt_algo", Algo), ("n_taps_lsw", C.c_int32),
+                ("taps_lsw", C.c_float * OFRI_MAX_GAUSS_TAPS)]
 
 
 class Band(C.Structure):
@@ -71,6 +72,7 @@ _SIGNATURES = {
     "ofri_spline_upsample": (C.c_int, [_H, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),
     "ofri_warp_bilinear": (C.c_int, [_H, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "ofri_warp_pair": (C.c_int, [_H, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
+    "ofri_liu_shen_warp": (C.c_int, [_H, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp]),
     "ofri_hs_derivatives": (C.c_int, [_H, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
     "ofri_hs_iterate": (C.c_int, [_H, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp]),
     "ofri_ls_coefficients": (C.c_int, [_H, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),

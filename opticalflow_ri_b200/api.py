@@ -8,7 +8,8 @@ from . import _lib
 from ._lib import ALGO_HS, ALGO_LS, ALGO_NONE, Algo, Band, OfriError, Params
 
 _EXC = {_lib.ERR_INVALID: ValueError, _lib.ERR_ALPHAS: IndexError, _lib.ERR_FILTER_OPT: TypeError,
-        _lib.ERR_TOO_SMALL: ValueError, _lib.ERR_UNSUPPORTED: NotImplementedError, _lib.ERR_OOM: MemoryError}
+        _lib.ERR_TOO_SMALL: ValueError, _lib.ERR_UNSUPPORTED: NotImplementedError, _lib.ERR_OOM: MemoryError,
+        _lib.ERR_INDEX: IndexError}
 
 
 def _f32(a):
@@ -84,6 +85,13 @@ def make_params(main, optional=None, filter_sigma=0.0, filter_opt_sigma=None, py
         for i, v in enumerate(t):
             p.taps_main[i] = v
     p.refilter_k = int(filter_sigma > 1)                            # GPOF:396
+    if warping and not bilinear:                                    # GPOF:210-212: gaussian_filter(x, 0.6*3, truncate=4/0.6*3)
+        mask_size = 3
+        sg, tr = 0.6 * mask_size, 4.0 / 0.6 * mask_size
+        t = gaussian_taps(sg, 2 * int(tr * sg + 0.5) + 1)
+        p.n_taps_lsw = len(t)
+        for i, v in enumerate(t):
+            p.taps_lsw[i] = v
     if optional is not None and optional.kind != ALGO_NONE:
         if filter_opt_sigma is None:                                # GPOF:380 compares None > 1e-3
             raise TypeError("'>' not supported between instances of 'NoneType' and 'float'")
@@ -271,6 +279,19 @@ class Handle:
         o2 = np.empty_like(a)
         self._check(self._L.ofri_warp_pair(self._h, _ptr(a), _ptr(b), _ptr(u), _ptr(v), B, H, W, _ptr(o1), _ptr(o2)))
         return (o1[0], o2[0]) if single else (o1, o2)
+
+    def liu_shen_warp(self, im1, us, vs):
+        """The biLinear=False warp of frame 1 (reference GPOF:190-196, 204-221); IndexError like the reference."""
+        a, single = _batched(im1)
+        u, _ = _batched(us)
+        v, _ = _batched(vs)
+        B, H, W = a.shape
+        mask_size = 3
+        sg, tr = 0.6 * mask_size, 4.0 / 0.6 * mask_size
+        t = gaussian_taps(sg, 2 * int(tr * sg + 0.5) + 1)
+        out = np.empty_like(a)
+        self._check(self._L.ofri_liu_shen_warp(self._h, _ptr(a), _ptr(u), _ptr(v), B, H, W, _ptr(t), len(t), _ptr(out)))
+        return out[0] if single else out
 
     def hs_derivatives(self, im1, im2):
         a, single = _batched(im1)

@@ -17,6 +17,8 @@
 
 using namespace ofri;
 
+extern "C" int ofri_gaussian_taps(double sigma, int n_taps, float* taps_out);
+
 namespace {
 
 std::mutex g_err_mutex;
@@ -250,8 +252,8 @@ int check_params(ofri_handle h, const ofri_params* p, int H, int W) {
                 sizeof(ofri_params));
   if (p->pyramid_levels < 1 || p->pyramid_levels > 16) return fail(h, OFRI_ERR_INVALID, "Invalid scale level");
   if (p->k_levels < 0) return fail(h, OFRI_ERR_INVALID, "k_levels < 0");
-  if (p->warping && !p->bilinear)
-    return fail(h, OFRI_ERR_UNSUPPORTED, "biLinear=False (Liu-Shen warp, GPOF:204-221) is not on the native path");
+  if (p->n_taps_lsw < 0 || p->n_taps_lsw > OFRI_MAX_GAUSS_TAPS || (p->n_taps_lsw && !(p->n_taps_lsw & 1)))
+    return fail(h, OFRI_ERR_INVALID, "bad Gaussian tap count");
   if (p->n_taps_main < 0 || p->n_taps_main > OFRI_MAX_GAUSS_TAPS || p->n_taps_opt < 0 ||
       p->n_taps_opt > OFRI_MAX_GAUSS_TAPS || (p->n_taps_main && !(p->n_taps_main & 1)) ||
       (p->n_taps_opt && !(p->n_taps_opt & 1)))
@@ -283,6 +285,8 @@ int check_params(ofri_handle h, const ofri_params* p, int H, int W) {
       return fail(h, OFRI_ERR_TOO_SMALL, "pyramid level %d is %d x %d; the cubic spline needs >= 4 samples", l, hl, wl);
     int hk = (p->n_taps_main > p->n_taps_opt ? p->n_taps_main : p->n_taps_opt) / 2;
     if (hl < hk || wl < hk) return fail(h, OFRI_ERR_TOO_SMALL, "level %d smaller than the Gaussian half-width", l);
+    if (p->warping && !p->bilinear && (l > 1 || p->k_levels > 1) && (hl < 36 || wl < 36))
+      return fail(h, OFRI_ERR_TOO_SMALL, "level %d smaller than the 73-tap Gaussian of the Liu-Shen warp", l);
     scale *= 2.0;
   }
   return OFRI_OK;
@@ -291,12 +295,14 @@ int check_params(ofri_handle h, const ofri_params* p, int H, int W) {
 // ---- the driver ------------------------------------------------------------------------------------------------------------
 struct Workspace {
   Img lvl1, lvl2, warp1, warp2, work1, work2, opt1, opt2, tmp, fx, fy, ft, U[2], V[2], U0, V0, Uacc, Vacc, us, vs;
+  Img lsw_sc, lsw_out;      // biLinear = False: scattered frame, warped copy of the k > 0 branch
   LsPlanes ls;
   ImgD M1, T1, M2, M1b, T1b, M2b;
   double* hs_acc = nullptr;
   double* ls_errs = nullptr;
   int* ls_state = nullptr;
   unsigned* ls_max = nullptr;
+  int* lsw_flag = nullptr;
 };
 
 void plan_workspace(Bump& b, int batch, int H, int W, const ofri_params* p, Workspace* ws) {
@@ -337,6 +343,12 @@ void plan_workspace(Bump& b, int batch, int H, int W, const ofri_params* p, Work
     ws->ls_max = (unsigned*)b.take(sizeof(unsigned) * 2 * batch);
   }
   ws->hs_acc = (double*)b.take(sizeof(double) * 2 * batch);
+  if (p->warping && !p->bilinear && (multi || p->k_levels > 1)) {
+    if (!multi) { ws->lvl1 = b.plane(batch, H, W); }
+    ws->lsw_sc = b.plane(batch, H, W);
+    ws->lsw_out = b.plane(batch, H, W);
+  }
+  ws->lsw_flag = (int*)b.take(sizeof(int) * 4);
 }
 
 GaussTaps make_taps(const float* k, int n) {
@@ -406,6 +418,15 @@ int run_pyramid(ofri_handle h, const Img& im1, const Img& im2, const ofri_params
   const bool has_opt = p->opt_algo.kind != OFRI_ALGO_NONE;
   const GaussTaps taps_main = make_taps(p->taps_main, p->n_taps_main);
   const GaussTaps taps_opt = make_taps(p->taps_opt, p->n_taps_opt);
+  GaussTaps taps_lsw = make_taps(p->taps_lsw, p->n_taps_lsw);
+  if (p->warping && !p->bilinear && p->n_taps_lsw == 0) {                   // gaussian_filter(x, 0.6*3, truncate=4/0.6*3)
+    float t73[OFRI_MAX_GAUSS_TAPS];
+    const double sg = 0.6 * 3, tr = 4.0 / 0.6 * 3;
+    const int K = 2 * (int)(tr * sg + 0.5) + 1;
+    ofri_gaussian_taps(sg, K, t73);
+    taps_lsw = make_taps(t73, K);
+  }
+  cudaMemsetAsync(ws.lsw_flag, 0, sizeof(int) * 4, s);
   const int err_stride = L * KL * 2;
   double scale = 1.0 / std::pow(2.0, L - 1);
   int prevH = 0, prevW = 0;
@@ -464,7 +485,20 @@ int run_pyramid(ofri_handle h, const Img& im1, const Img& im2, const ofri_params
         launch_copy(vn, va, s, h->lc);
         if (local_scaling) { /* factor is exactly 1 */ }
       }
-      if (p->warping) {
+      if (p->warping && !p->bilinear) {                                    // "Liu-Shen warp" (GPOF:204-221)
+        Timed t(h, "warp");
+        // the reference warps frame 1 IN PLACE (so the optional adapter and the k-loop see the warped frame too) and
+        // leaves frame 2 alone; here the warped frame replaces the level's frame 1 (the caller's array is not touched)
+        Img n1m = view(ws.lvl1, Hl, Wl);
+        launch_liu_shen_warp(n1, un, vn, n1m, (int*)ws.warp2.p, view(ws.work1, Hl, Wl), view(ws.work2, Hl, Wl),
+                             view(ws.U0, Hl, Wl), view(ws.V0, Hl, Wl), view(ws.lsw_sc, Hl, Wl), view(ws.tmp, Hl, Wl),
+                             taps_lsw, ws.lsw_flag, s, h->lc);
+        n1 = n1m;
+        w1 = n1;
+        w2 = n2;
+        std::swap(Uacc, us);
+        std::swap(Vacc, vs);
+      } else if (p->warping) {
         Timed t(h, "warp");
         w1 = view(ws.warp1, Hl, Wl);
         w2 = view(ws.warp2, Hl, Wl);
@@ -511,9 +545,17 @@ int run_pyramid(ofri_handle h, const Img& im1, const Img& im2, const ofri_params
         if (p->warping) {
           // same-size "transition": usNew = Uaccum (no spline, no scaling), re-warp the level images
           Timed t(h, "warp");
-          w1 = view(ws.warp1, Hl, Wl);
-          w2 = view(ws.warp2, Hl, Wl);
-          launch_warp_pair(n1, n2, UaccL, VaccL, w1, w2, s, h->lc);
+          if (p->bilinear) {
+            w1 = view(ws.warp1, Hl, Wl);
+            w2 = view(ws.warp2, Hl, Wl);
+            launch_warp_pair(n1, n2, UaccL, VaccL, w1, w2, s, h->lc);
+          } else {                                                         // warps a COPY of frame 1 this time (GPOF:394)
+            w1 = view(ws.lsw_out, Hl, Wl);
+            w2 = n2;
+            launch_liu_shen_warp(n1, UaccL, VaccL, w1, (int*)ws.warp2.p, view(ws.work1, Hl, Wl), view(ws.work2, Hl, Wl),
+                                 view(ws.U0, Hl, Wl), view(ws.V0, Hl, Wl), view(ws.lsw_sc, Hl, Wl), view(ws.tmp, Hl, Wl),
+                                 taps_lsw, ws.lsw_flag, s, h->lc);
+          }
           cudaMemsetAsync(Ucur.p, 0, sizeof(float) * (size_t)Ucur.stride * Ucur.batch, s);
           cudaMemsetAsync(Vcur.p, 0, sizeof(float) * (size_t)Vcur.stride * Vcur.batch, s);
           uv_zero = true;
@@ -559,6 +601,16 @@ int run_pyramid(ofri_handle h, const Img& im1, const Img& im2, const ofri_params
   launch_copy(vo, view(Vacc, H, W), s, h->lc);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, OFRI_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return OFRI_OK;
+}
+
+// biLinear = False: did a scatter target leave the frame (the reference raises IndexError at GPOF:207)?  Synchronises.
+int check_lsw_flag(ofri_handle h, const ofri_params* p, const Workspace& ws) {
+  if (!(p->warping && !p->bilinear && (p->pyramid_levels > 1 || p->k_levels > 1))) return OFRI_OK;
+  int flag = 0;
+  OFRI_CUDA(h, cudaMemcpyAsync(&flag, ws.lsw_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  OFRI_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (flag) return fail(h, OFRI_ERR_INDEX, "index out of bounds: the Liu-Shen warp moved a pixel outside the frame");
   return OFRI_OK;
 }
 
@@ -1189,6 +1241,7 @@ int ofri_pyramidal_flow_dev(ofri_handle h, const float* d_im1, const float* d_im
                      dense(d_u_out + b0 * plane, nb, H, W), dense(d_v_out + b0 * plane, nb, H, W),
                      d_err_out ? d_err_out + (size_t)b0 * err_stride : nullptr, ws);
     if (rc) return rc;
+    if ((rc = check_lsw_flag(h, p, ws))) return rc;
   }
   return OFRI_OK;
 }
@@ -1237,6 +1290,7 @@ int ofri_pyramidal_flow(ofri_handle h, const float* im1, const float* im2, int b
     rc = run_pyramid(h, dense(d_i1, nb, H, W), dense(d_i2, nb, H, W), p, dense(d_u, nb, H, W), dense(d_v, nb, H, W),
                      err_out ? d_e : nullptr, ws);
     if (rc) return rc;
+    if ((rc = check_lsw_flag(h, p, ws))) return rc;
     OFRI_CUDA(h, cudaEventRecord(h->ev_comp[slot], s));
     OFRI_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
     OFRI_CUDA(h, cudaMemcpyAsync(u_out + b0 * plane, d_u, plane_b * nb, cudaMemcpyDeviceToHost, h->s_out));
@@ -1431,6 +1485,38 @@ int ofri_warp_pair(ofri_handle h, const float* im1, const float* im2, const floa
   launch_warp_pair(a, c, u, v, o1, o2, h->stream, h->lc);
   if ((rc = download(h, out1, o1)) || (rc = download(h, out2, o2))) return rc;
   return finish(h);
+}
+
+int ofri_liu_shen_warp(ofri_handle h, const float* im1, const float* us, const float* vs, int batch, int H, int W,
+                       const float* taps, int n_taps, float* out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!im1 || !us || !vs || !out) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
+  float t73[OFRI_MAX_GAUSS_TAPS];
+  if (!taps) {
+    const double sg = 0.6 * 3, tr = 4.0 / 0.6 * 3;
+    n_taps = 2 * (int)(tr * sg + 0.5) + 1;
+    ofri_gaussian_taps(sg, n_taps, t73);
+    taps = t73;
+  }
+  if (n_taps < 1 || n_taps > OFRI_MAX_GAUSS_TAPS || !(n_taps & 1)) return fail(h, OFRI_ERR_INVALID, "bad tap count");
+  if (H < n_taps / 2 || W < n_taps / 2) return fail(h, OFRI_ERR_TOO_SMALL, "image smaller than the kernel half-width");
+  int rc = arena_reserve(h, (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 11 + 4096);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img i1 = b.plane(batch, H, W), u = b.plane(batch, H, W), v = b.plane(batch, H, W), o = b.plane(batch, H, W),
+      win = b.plane(batch, H, W), dU = b.plane(batch, H, W), dV = b.plane(batch, H, W), fU = b.plane(batch, H, W),
+      fV = b.plane(batch, H, W), sc = b.plane(batch, H, W), tmp = b.plane(batch, H, W);
+  int* flag = (int*)b.take(sizeof(int) * 4);
+  if ((rc = upload(h, i1, im1)) || (rc = upload(h, u, us)) || (rc = upload(h, v, vs))) return rc;
+  cudaMemsetAsync(flag, 0, sizeof(int) * 4, h->stream);
+  launch_liu_shen_warp(i1, u, v, o, (int*)win.p, dU, dV, fU, fV, sc, tmp, make_taps(taps, n_taps), flag, h->stream, h->lc);
+  if ((rc = download(h, out, o))) return rc;
+  int hf = 0;
+  OFRI_CUDA(h, cudaMemcpyAsync(&hf, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if ((rc = finish(h))) return rc;
+  if (hf) return fail(h, OFRI_ERR_INDEX, "index out of bounds: the Liu-Shen warp moved a pixel outside the frame");
+  return OFRI_OK;
 }
 
 int ofri_hs_derivatives(ofri_handle h, const float* im1, const float* im2, int batch, int H, int W, float* fx,

@@ -77,6 +77,10 @@ void launch_spline(const Img& in, const Img& out, float mul, const SplineSys& sy
 // band form: us / vs / out hold rows [row0, ..) and im1 / im2 rows [img_row0, ..) of an image of Hg rows
 void launch_warp_pair(const Img& im1, const Img& im2, const Img& us, const Img& vs, const Img& out1, const Img& out2,
                       cudaStream_t s, LaunchCounter& lc, int row0 = 0, int img_row0 = 0, int Hg = 0);
+// biLinear = False "Liu-Shen warp" of frame 1 (GPOF:190-196, 204-221); *flag is set if a scatter target leaves the frame
+void launch_liu_shen_warp(const Img& im1, const Img& us, const Img& vs, const Img& out, int* winner, const Img& dU,
+                          const Img& dV, const Img& fU, const Img& fV, const Img& sc, const Img& tmp,
+                          const GaussTaps& taps, int* flag, cudaStream_t s, LaunchCounter& lc);
 void launch_warp_coords(const Img& img, const Img& cy, const Img& cx, const Img& out, cudaStream_t s, LaunchCounter& lc);
 void launch_axpy(const Img& acc, const Img& x, cudaStream_t s, LaunchCounter& lc);       // acc += x
 void launch_scale(const Img& x, float mul, cudaStream_t s, LaunchCounter& lc);            // x *= mul

@@ -333,6 +333,75 @@ void launch_warp_coords(const Img& img, const Img& cy, const Img& cx, const Img&
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// "Liu-Shen warp" (biLinear = False; GPOF:190-196, 204-221): integer-shift scatter of frame 1 along the rounded flow,
+// then the optical-flow equation with the Gaussian-smoothed sub-pixel parts.
+// ---------------------------------------------------------------------------------------------------------------
+// Scatter `im1[vsSwap, usSwap] = im1[ysMesh, xsMesh]`: sources are visited in row-major order and the last writer of
+// a target wins -> atomicMax of the source's linear index per target.  Negative targets wrap around (numpy indexing);
+// targets >= size or < -size raise IndexError in the reference -> flag.  Also emits the sub-pixel parts.
+__global__ void lsw_prepare_kernel(Img us, Img vs, int* winner, Img dU, Img dV, int* flag) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  const int W = us.W, H = us.H;
+  if (x >= W || y >= H) return;
+  const float u = us.p[(long)b * us.stride + (long)y * us.pitch + x];
+  const float v = vs.p[(long)b * vs.stride + (long)y * vs.pitch + x];
+  const float fu = floorf(fadd(u, 0.5f)), fv = floorf(fadd(v, 0.5f));
+  dU.p[(long)b * dU.stride + (long)y * dU.pitch + x] = fsub(u, fu);
+  dV.p[(long)b * dV.stride + (long)y * dV.pitch + x] = fsub(v, fv);
+  double txd = dadd((double)x, (double)fu), tyd = dadd((double)y, (double)fv);     // int32 + float32 -> float64 -> int32
+  if (!(txd >= -(double)W && txd < (double)W && tyd >= -(double)H && tyd < (double)H)) {
+    atomicExch(flag, 1);
+    return;
+  }
+  int tx = (int)txd, ty = (int)tyd;
+  if (tx < 0) tx += W;
+  if (ty < 0) ty += H;
+  atomicMax(winner + (long)b * H * W + (long)ty * W + tx, y * W + x);
+}
+__global__ void lsw_gather_kernel(Img im1, const int* winner, Img out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  const int W = im1.W, H = im1.H;
+  if (x >= W || y >= H) return;
+  const float* I = im1.p + (long)b * im1.stride;
+  const int w = winner[(long)b * H * W + (long)y * W + x];
+  const int sy = w >= 0 ? w / W : y, sx = w >= 0 ? w - (w / W) * W : x;     // untouched targets keep their value
+  out.p[(long)b * out.stride + (long)y * out.pitch + x] = I[(long)sy * im1.pitch + sx];
+}
+// im1[0:-1,0:-1] -= (tempDx + tempDy) with tempDx = I[y,x+1] dU[y,x+1] - I[y,x] dU[y,x], tempDy likewise along y (f32)
+__global__ void lsw_ofeq_kernel(Img in, Img dU, Img dV, Img out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;
+  const int W = in.W, H = in.H;
+  if (x >= W || y >= H) return;
+  const float* I = in.p + (long)b * in.stride;
+  const float* A = dU.p + (long)b * dU.stride;
+  const float* B = dV.p + (long)b * dV.stride;
+  float r = I[(long)y * in.pitch + x];
+  if (x < W - 1 && y < H - 1) {
+    const float c = r;
+    const float tdx = fsub(fmul(I[(long)y * in.pitch + x + 1], A[(long)y * dU.pitch + x + 1]), fmul(c, A[(long)y * dU.pitch + x]));
+    const float tdy = fsub(fmul(I[(long)(y + 1) * in.pitch + x], B[(long)(y + 1) * dV.pitch + x]), fmul(c, B[(long)y * dV.pitch + x]));
+    r = fsub(c, fadd(tdx, tdy));
+  }
+  out.p[(long)b * out.stride + (long)y * out.pitch + x] = r;
+}
+// im1 -> out.  Scratch: winner [batch][H][W] ints, dU / dV (raw sub-pixel parts), fU / fV (filtered), sc (scattered
+// frame), tmp (Gaussian scratch); taps = the 73-tap kernel of gaussian_filter(x, 0.6*3, truncate=4/0.6*3).
+void launch_liu_shen_warp(const Img& im1, const Img& us, const Img& vs, const Img& out, int* winner, const Img& dU,
+                          const Img& dV, const Img& fU, const Img& fV, const Img& sc, const Img& tmp,
+                          const GaussTaps& taps, int* flag, cudaStream_t s, LaunchCounter& lc) {
+  dim3 b(32, 8);
+  dim3 g = grid2d(im1.W, im1.H, im1.batch, b);
+  cudaMemsetAsync(winner, 0xff, sizeof(int) * (size_t)im1.H * im1.W * im1.batch, s);
+  lsw_prepare_kernel<<<g, b, 0, s>>>(us, vs, winner, dU, dV, flag);
+  lsw_gather_kernel<<<g, b, 0, s>>>(im1, winner, sc);
+  lc.n += 2;
+  launch_gauss(dU, tmp, fU, taps, s, lc);
+  launch_gauss(dV, tmp, fV, taps, s, lc);
+  lsw_ofeq_kernel<<<g, b, 0, s>>>(sc, fU, fV, out);
+  lc.n += 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // element-wise helpers
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void axpy_kernel(Img acc, Img x) {

@@ -14,8 +14,10 @@ the level stages run as GPU kernels and the adapter's own compute() is called wi
 Behaviour mirrored from the reference (line numbers of its GenericPyramidalOpticalFlow.py): adapter-default override
 304-327; level sizes int32(round(n*scale)) from the ORIGINAL frames 336-343; 'Invalid scale level' 345; level
 transition 118-235 (bilinear branch); pre-filters 368-386 (the optional adapter sees the UNWARPED level images);
-k-loop with re-warp 389-404; accumulation 413-414.  The biLinear=False "Liu-Shen warp" branch (204-221) is not on the
-native path and raises NotImplementedError."""
+k-loop with re-warp 389-404; accumulation 413-414; biLinear=False "Liu-Shen warp" 190-196 / 204-221 (frame 1 only;
+IndexError when the rounded flow moves a pixel past the right / bottom border, wrap-around at the left / top border).
+One deliberate difference: with this package's adapters the caller's im1 array is never modified (the reference's
+Liu-Shen warp overwrites it in place at the last pyramid level)."""
 import numpy as np
 
 import _native
@@ -51,7 +53,9 @@ def updateNextPyramidalLevel(im1IterNext, im1IterPrev, im2IterNext, Uaccum, Vacc
     if not warping:
         return im1IterNext, im2IterNext, zeros, zeros.copy(), usNew, vsNew
     if not biLinear:
-        raise NotImplementedError("biLinear=False (Liu-Shen warp) is not part of the native path")
+        log('Warping: Liu-Shen')
+        im1IterNext[...] = h.liu_shen_warp(im1IterNext, usNew, vsNew)      # in place, like the reference (:207-221)
+        return im1IterNext, im2IterNext, usNew, vsNew, zeros, zeros.copy()
     log('Warping: BiLinear')
     w1, w2 = h.warp_pair(im1IterNext, im2IterNext, usNew, vsNew)
     return w1, w2, usNew, vsNew, zeros, zeros.copy()
@@ -99,8 +103,6 @@ def _run(im1, im2, FILTER, main, pyramidalLevels, kLevels, FILTER_OPT, optional,
     kLevels = int(kLevels)
     if pyramidalLevels < 1:
         raise Exception('Invalid scale level: ' + str(1.0 / (2.0 ** (pyramidalLevels - 1))))
-    if warping and not biLinear:
-        raise NotImplementedError("biLinear=False (Liu-Shen warp, reference :204-221) is not part of the native path")
     if optional is not None and FILTER_OPT is None:
         raise TypeError("'>' not supported between instances of 'NoneType' and 'float'")
     if _is_native(main) and (optional is None or _is_native(optional)):

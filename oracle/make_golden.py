@@ -249,5 +249,54 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--lswarp" not in sys.argv:
     main()
+
+
+def main_lswarp():
+    """`python oracle/make_golden.py --lswarp`: goldens of the biLinear=False "Liu-Shen warp" branch (GPOF:190-221),
+    written to tests/golden/configs_lswarp.npz (kept separate so the other files need not be regenerated)."""
+    GPOF, HS, LS, GF, GKBE, WRAP = import_reference()
+    a8, b8 = load_bundled()
+    I0, I1 = a8.astype(np.float32), b8.astype(np.float32)
+    c0 = np.ascontiguousarray(I0[150:350, 100:332])
+    c1 = np.ascontiguousarray(I1[150:350, 100:332])
+
+    def run(im0, im1, FILTER, main, L=1, k=1, FILTER_OPT=None, opt=None, **kw):
+        a, b = im0.copy(), im1.copy()                 # the branch mutates its input frame in place
+        with quiet():
+            U, V = GPOF.genericPyramidalOpticalFlow(a, b, FILTER, main, L, k, FILTER_OPT, opt, **kw)
+        return np.asarray(U, dtype=np.float32), np.asarray(V, dtype=np.float32), a
+
+    g = {"crop0": c0, "crop1": c1}
+    # stage level: one transition with a smooth flow field (integer shifts, wrap-around at the left border, collisions)
+    rng = np.random.default_rng(9)
+    yy, xx = np.mgrid[0:100, 0:116].astype(np.float32)
+    # targets must stay inside the frame at the right / bottom border (the reference raises IndexError otherwise) but may
+    # be negative at the left / top border (numpy wraps them around)
+    Ua = (-3.7 * (1 - ((yy - 49.5) / 50) ** 2) - 0.4 + 0.3 * np.sin(xx / 9)).astype(np.float32)
+    Va = (0.8 * (1 - 2 * yy / 99) * np.cos(xx / 13) ** 2 - 0.9 * (yy < 3)).astype(np.float32)
+    n1 = c0.copy()
+    with quiet():
+        w1, w2, ua, va, u0, v0 = GPOF.updateNextPyramidalLevel(n1, np.zeros((100, 116), np.float32), c1.copy(), Ua.copy(),
+                                                               Va.copy(), None, None, True, False, True)
+    g["st_Ua"], g["st_Va"], g["st_w1"], g["st_w2"], g["st_ua"], g["st_va"] = Ua, Va, np.float32(w1), np.float32(w2), ua, va
+    U, V, _ = run(c0, c1, 3.4, LS.LiuShenOpticalFlowAlgoAdapter(0.1), 2, 1, biLinear=False)
+    g["lsmain_U"], g["lsmain_V"] = U, V
+    U, V, a = run(c0, c1, 3.4, HS.HSOpticalFlowAlgoAdapter([21, 45], 100, False), 2, 1, 0.48,
+                  LS.LiuShenOpticalFlowAlgoAdapter(5), biLinear=False, pyramidalScaling=True)
+    g["hsnodef_U"], g["hsnodef_V"], g["hsnodef_im1_after"] = U, V, a
+    U, V, _ = run(c0, c1, 3.4, LS.LiuShenOpticalFlowAlgoAdapter(1.0), 3, 1, biLinear=False)
+    g["l3_U"], g["l3_V"] = U, V
+    # kLevels = 2 on this pair drives a scatter target past the bottom border: the reference raises IndexError
+    try:
+        run(c0, c1, 3.4, HS.HSOpticalFlowAlgoAdapter([21, 21, 45, 45], 60, False), 2, 2, biLinear=False, pyramidalScaling=True)
+        g["k2_raises_index_error"] = np.int32(0)
+    except IndexError:
+        g["k2_raises_index_error"] = np.int32(1)
+    np.savez_compressed(os.path.join(OUT, "configs_lswarp.npz"), **g)
+    print("configs_lswarp.npz", os.path.getsize(os.path.join(OUT, "configs_lswarp.npz")))
+
+
+if __name__ == "__main__" and "--lswarp" in sys.argv:
+    main_lswarp()

@@ -292,6 +292,41 @@ def upsample_flow(Uacc, Vacc, H, W, scale: bool):
 # --------------------------------------------------------------------------------------
 # scipy.ndimage.convolve restated (f64 accumulate in kernel memory order, f32 store)
 # --------------------------------------------------------------------------------------
+def liu_shen_warp(im1: np.ndarray, us: np.ndarray, vs: np.ndarray) -> np.ndarray:
+    """The biLinear=False branch of updateNextPyramidalLevel (GPOF:190-196, 204-221): integer-shift SCATTER of frame 1
+    along the rounded flow, then the optical-flow equation with the Gaussian-smoothed sub-pixel parts.
+
+    Scatter: `im1[vsSwap, usSwap] = im1[ysMesh, xsMesh]` -- the right-hand side is a copy, sources are visited in
+    row-major order and the LAST writer of a target wins; negative targets wrap around (numpy indexing), targets
+    >= size (or < -size) raise IndexError.  Only frame 1 is warped.  Returns the new frame (the reference mutates its
+    argument in place)."""
+    im1 = np.ascontiguousarray(im1, dtype=F32)
+    H, W = im1.shape
+    fu = np.floor(us.astype(F32) + F32(0.5))                     # usNew + 0.5 stays float32 (NEP 50 weak scalar)
+    fv = np.floor(vs.astype(F32) + F32(0.5))
+    xs, ys = np.meshgrid(np.arange(W, dtype=np.int32), np.arange(H, dtype=np.int32))
+    tx = (xs.astype(F64) + fu.astype(F64)).astype(np.int64)      # int32 + float32 -> float64 -> np.int32()
+    ty = (ys.astype(F64) + fv.astype(F64)).astype(np.int64)
+    if (tx >= W).any() or (tx < -W).any() or (ty >= H).any() or (ty < -H).any():
+        raise IndexError("Liu-Shen warp: scatter target outside the frame")
+    tx = np.where(tx < 0, tx + W, tx)
+    ty = np.where(ty < 0, ty + H, ty)
+    winner = np.full(H * W, -1, dtype=np.int64)
+    np.maximum.at(winner, (ty * W + tx).ravel(), np.arange(H * W, dtype=np.int64))     # last writer in row-major order
+    flat = im1.ravel()
+    out = np.where(winner >= 0, flat[np.maximum(winner, 0)], flat).reshape(H, W).astype(F32)
+    dU = (us - fu).astype(F32)
+    dV = (vs - fv).astype(F32)
+    mask_size = 3                                                # GPOF:210-212: sigma = 0.6*3, truncate = 4.0/0.6*3 -> 73 taps
+    dU = gaussian_filter_truncate(dU, 0.6 * mask_size, 4.0 / 0.6 * mask_size)
+    dV = gaussian_filter_truncate(dV, 0.6 * mask_size, 4.0 / 0.6 * mask_size)
+    tdx = (out[0:-1, 1:] * dU[0:-1, 1:] - out[0:-1, 0:-1] * dU[0:-1, 0:-1]).astype(F32)
+    tdy = (out[1:, 0:-1] * dV[1:, 0:-1] - out[0:-1, 0:-1] * dV[0:-1, 0:-1]).astype(F32)
+    res = out.copy()
+    res[0:-1, 0:-1] = (out[0:-1, 0:-1] - (tdx + tdy).astype(F32)).astype(F32)
+    return res
+
+
 def _pad(a: np.ndarray, mode: str) -> np.ndarray:
     if mode == "mirror":      # scipy 'mirror' == numpy 'reflect' (edge not repeated)
         return np.pad(a, 1, mode="reflect")
@@ -514,8 +549,6 @@ def pyramidal_flow(im1, im2, FILTER, main, pyramidalLevels=1, kLevels=1, FILTER_
             pyramidalIntermediateScaling = d["intermediateScaling"]
         if d.get("scaling") is not None:
             pyramidalScaling = d["scaling"]
-    if warping and not biLinear:
-        raise NotImplementedError("Liu-Shen warp branch (GPOF:204-221) is outside the oracle's scope")
     if optional is not None and FILTER_OPT is None:
         raise TypeError("'>' not supported between instances of 'NoneType' and 'float'")   # GPOF:380
     scale = 1.0 / (2.0 ** (pyramidalLevels - 1))
@@ -536,7 +569,15 @@ def pyramidal_flow(im1, im2, FILTER, main, pyramidalLevels=1, kLevels=1, FILTER_
         Hl, Wl = n1.shape
         if level > 1:
             us, vs = upsample_flow(Uacc, Vacc, Hl, Wl, local_scaling)
-            if warping:
+            if warping and not biLinear:                          # GPOF:204-221: frame 1 is warped IN PLACE, frame 2 is not
+                n1 = liu_shen_warp(n1, us, vs)
+                if level == pyramidalLevels:
+                    im1 = n1                                      # ... which at the last level is the caller's frame
+                w1, w2 = n1, n2
+                U = np.zeros((Hl, Wl), dtype=F32)
+                V = np.zeros((Hl, Wl), dtype=F32)
+                Uacc, Vacc = us, vs
+            elif warping:
                 w1, w2 = warp_pair(n1, n2, us, vs)
                 U = np.zeros((Hl, Wl), dtype=F32)
                 V = np.zeros((Hl, Wl), dtype=F32)
@@ -566,7 +607,10 @@ def pyramidal_flow(im1, im2, FILTER, main, pyramidalLevels=1, kLevels=1, FILTER_
             if k > 0:                                             # GPOF:392-404
                 if warping:
                     us, vs = upsample_flow(Uacc, Vacc, Hl, Wl, False)
-                    w1, w2 = warp_pair(n1, n2, us, vs)
+                    if biLinear:
+                        w1, w2 = warp_pair(n1, n2, us, vs)
+                    else:
+                        w1, w2 = liu_shen_warp(n1, us, vs), n2    # warps a COPY this time (GPOF:394)
                     U = np.zeros((Hl, Wl), dtype=F32)
                     V = np.zeros((Hl, Wl), dtype=F32)
                     Uacc, Vacc = us, vs

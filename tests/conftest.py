@@ -32,6 +32,11 @@ def configs_bundled():
 
 
 @pytest.fixture(scope="session")
+def lswarp():
+    return np.load(os.path.join(GOLDEN, "configs_lswarp.npz"))
+
+
+@pytest.fixture(scope="session")
 def bundled_pair():
     b = np.load(os.path.join(GOLDEN, "bundled_pair.npz"))
     return b["im0"].astype(np.float32), b["im1"].astype(np.float32)

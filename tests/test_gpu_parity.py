@@ -415,7 +415,7 @@ def test_error_codes(h, ofri):
         h.pyramidal_flow(z, z, ofri.make_params(ofri.hs_algo([21], 5), pyramid_levels=2, **HS_DEF))
     with pytest.raises(ValueError):       # 16 -> 2 px at level 1 of 4: too small for the cubic spline
         h.pyramidal_flow(z, z, ofri.make_params(ofri.hs_algo([1, 1, 1, 1], 5), pyramid_levels=4, **HS_DEF))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):       # Liu-Shen warp: the 73-tap Gaussian does not fit a 16 x 16 level
         h.pyramidal_flow(z, z, ofri.make_params(ofri.ls_algo(5), pyramid_levels=2, bilinear=False))
 
 
@@ -466,6 +466,43 @@ def test_full_size_properties_1024(h, ofri):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# biLinear = False: the "Liu-Shen warp" branch (GPOF:190-196, 204-221)
+# ---------------------------------------------------------------------------------------------------------------
+def test_liu_shen_warp_stage_golden(h, lswarp):
+    g = lswarp
+    H, W = g["crop0"].shape
+    us = h.spline_upsample(g["st_Ua"], H, W, np.float32(np.float32(W) / np.float32(g["st_Ua"].shape[1])))
+    vs = h.spline_upsample(g["st_Va"], H, W, np.float32(np.float32(H) / np.float32(g["st_Va"].shape[0])))
+    same(us, g["st_ua"])
+    same(vs, g["st_va"])
+    same(h.liu_shen_warp(g["crop0"], us, vs), g["st_w1"])       # scatter (wrap-around, collisions) + 73-tap Gaussian + OF equation
+    bad = us.copy()
+    bad[150, W - 1] = 0.7                                        # pushes a pixel past the right border
+    with pytest.raises(IndexError):
+        h.liu_shen_warp(g["crop0"], bad, vs)
+
+
+def test_liu_shen_warp_driver_goldens(h, ofri, lswarp):
+    g = lswarp
+    c0, c1 = g["crop0"], g["crop1"]
+    keep = c0.copy()
+    U, V = flow(h, ofri, c0, c1, 3.4, ofri.ls_algo(0.1), 2, bilinear=False)
+    close(U, g["lsmain_U"], TOL_FLOW)
+    close(V, g["lsmain_V"], TOL_FLOW)
+    U, V = flow(h, ofri, c0, c1, 3.4, ofri.hs_algo([45, 21], 100), 2, 1, 0.48, ofri.ls_algo(5), bilinear=False,
+                final_scaling=True)
+    close(U, g["hsnodef_U"], TOL_FLOW)
+    close(V, g["hsnodef_V"], TOL_FLOW)
+    U, V = flow(h, ofri, c0, c1, 3.4, ofri.ls_algo(1.0), 3, bilinear=False)
+    close(U, g["l3_U"], TOL_FLOW)
+    close(V, g["l3_V"], TOL_FLOW)
+    assert int(g["k2_raises_index_error"]) == 1
+    with pytest.raises(IndexError):           # the reference raises here too (a target leaves the frame at the bottom)
+        flow(h, ofri, c0, c1, 3.4, ofri.hs_algo([45, 45, 21, 21], 60), 2, 2, bilinear=False, final_scaling=True)
+    same(c0, keep)                            # unlike the reference, the caller's frame is left alone
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # drop-in modules: the reference's example / benchmark call shapes, unchanged
 # ---------------------------------------------------------------------------------------------------------------
 def test_dropin_example3_and_wrapper(ofri, configs_bundled, bundled_pair, configs_small):
@@ -510,6 +547,37 @@ def test_dropin_example3_and_wrapper(ofri, configs_bundled, bundled_pair, config
     out = GF.gaussian_filterPx(img, 3.4, 3)
     assert out is img
     same(img, st["gauss_out_g34_3"])
+
+
+def test_dropin_liu_shen_warp(ofri, lswarp):
+    """biLinear=False through the drop-in modules: native adapters (one call) and a foreign adapter (generic path, where
+    the warp mutates the level frame in place exactly like the reference)."""
+    sys.path.insert(0, ofri.SRC_DIR)
+    try:
+        from GenericPyramidalOpticalFlow import genericPyramidalOpticalFlow
+        from PhysicsBasedOpticalFlowLiuShen import LiuShenOpticalFlowAlgoAdapter
+    finally:
+        sys.path.remove(ofri.SRC_DIR)
+    g = lswarp
+    U, V = genericPyramidalOpticalFlow(g["crop0"].copy(), g["crop1"].copy(), 3.4, LiuShenOpticalFlowAlgoAdapter(0.1), 2, 1,
+                                       biLinear=False)
+    close(U, g["lsmain_U"], TOL_FLOW)
+    close(V, g["lsmain_V"], TOL_FLOW)
+
+    class ForeignLS(object):                     # the ORACLE's Liu-Shen wrapped as a third-party plugin
+        def compute(self, im1, im2, U, V):
+            Un, Vn, err, _ = O.ls_compute(im1, im2, 0.1, U, V)
+            return Un, Vn, err
+
+        def getAlgoName(self):
+            return "foreign LS"
+
+        def hasGenericPyramidalDefaults(self):
+            return False
+
+    U, V = genericPyramidalOpticalFlow(g["crop0"].copy(), g["crop1"].copy(), 3.4, ForeignLS(), 2, 1, biLinear=False)
+    same(U, g["lsmain_U"])                       # GPU stages bit-exact + oracle LS bit-exact
+    same(V, g["lsmain_V"])
 
 
 def test_dropin_foreign_adapter_generic_path(ofri, configs_small):

@@ -99,8 +99,8 @@ def test_dropin_modules_import_and_mirror_reference_api(ofri):
         G.genericPyramidalOpticalFlow(z, z, 3.4, hs, 2, 1, None, ls)
     with pytest.raises(IndexError):
         G.genericPyramidalOpticalFlow(z, z, 3.4, HS.HSOpticalFlowAlgoAdapter([21], 10), 2, 1)
-    with pytest.raises(NotImplementedError):
-        G.genericPyramidalOpticalFlow(z, z, 3.4, LS.LiuShenOpticalFlowAlgoAdapter(5), 2, 1, biLinear=False)
+    with pytest.raises(Exception, match="Invalid scale level"):
+        G.genericPyramidalOpticalFlow(z, z, 3.4, LS.LiuShenOpticalFlowAlgoAdapter(5), 0, 1)
 
 
 def test_gkbe_dropin_matches_golden(ofri, stages):
