@@ -84,23 +84,38 @@ OFRI_HD float resample_point(const float* line, long stride, int xmin, int cnt, 
 }
 
 // ---- not-a-knot cubic spline evaluation (FITPACK bispev restated) ------------------------------
-// position of output sample k of N over n input samples: i = floor(k n / N), s = frac, clamped to the last knot
-OFRI_HD void spline_locate(int k, int n, int N, int* i_out, double* s_out) {
+// Correctly rounded x / d for a divisor d known in advance, r = RN(1/d): quotient estimate + two FMA residual
+// corrections (the tail of every IEEE division routine; exact for the normal-range operands that occur here) -- the
+// same double as ddiv(x, d), at a fraction of the cost.
+OFRI_HD double ddiv_const(double x, double d, double r) {
+  double q = dmul(x, r);
+  double e = fma(-d, q, x);
+  q = fma(e, r, q);
+  e = fma(-d, q, x);
+  return fma(e, r, q);
+}
+// position of output sample k of N over n input samples: i = floor(k n / N), s = frac, clamped to the last knot;
+// rN = RN(1 / N)
+OFRI_HD void spline_locate(int k, int n, int N, double rN, int* i_out, double* s_out) {
   long long num = (long long)k * (long long)n;
   long long i = num / N;
-  double s = ddiv((double)(num - i * N), (double)N);
+  double s = ddiv_const((double)(num - i * N), (double)N, rN);
   if (i >= n - 1) { i = n - 2; s = 1.0; }
   *i_out = (int)i;
   *s_out = s;
 }
+OFRI_HD void spline_locate(int k, int n, int N, int* i_out, double* s_out) {
+  spline_locate(k, n, N, ddiv(1.0, (double)N), i_out, s_out);
+}
 OFRI_HD double spline_eval(double yi, double yj, double Mi, double Mj, double s) {
+  const double r6 = 0.16666666666666666;      // RN(1/6)
   double t = dsub(1.0, s);
   double t3 = dmul(dmul(t, t), t);
   double s3 = dmul(dmul(s, s), s);
-  double a = ddiv(dmul(Mi, t3), 6.0);
-  double b = ddiv(dmul(Mj, s3), 6.0);
-  double c = dmul(dsub(yi, ddiv(Mi, 6.0)), t);
-  double d = dmul(dsub(yj, ddiv(Mj, 6.0)), s);
+  double a = ddiv_const(dmul(Mi, t3), 6.0, r6);
+  double b = ddiv_const(dmul(Mj, s3), 6.0, r6);
+  double c = dmul(dsub(yi, ddiv_const(Mi, 6.0, r6)), t);
+  double d = dmul(dsub(yj, ddiv_const(Mj, 6.0, r6)), s);
   return dadd(dadd(dadd(a, b), c), d);
 }
 
