@@ -295,7 +295,7 @@ def run_ours(args):
                   "hs_iterate", 28.0, fast_levels, nl, HS_NITER),
             entry("hs_tma_kernel<T=%d,R=4,NRG=8,precise> (same, reference arithmetic, coarse level)" % T,
                   "hs_iterate_precise", 28.0, prec_levels, nl, HS_NITER),
-            entry("ls_fused_kernel<T=%d> (fused Liu-Shen sweeps, both levels)" % Tl,
+            entry("ls_tma_kernel<T=%d,R=4,NRG=8> (persistent TMA-fed fused Liu-Shen sweeps, both levels)" % Tl,
                   "ls_iterate", 48.0, [px_coarse, px_fine], -(-LS_ITERS // Tl), LS_ITERS)) if k]
         if kernels:
             dom = max(kernels, key=lambda k: k["stage_ms"])

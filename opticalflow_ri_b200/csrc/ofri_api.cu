@@ -51,7 +51,7 @@ struct ofri_ctx {
   int hs_precise = 1;   // 0 = fast f32/FMA everywhere, 1 = reference arithmetic on the coarse pyramid levels, 2 = everywhere
   // row-band (domain-decomposed) mode
   ofri::Comm* comm = nullptr;
-  int band_exchange = 16;   // Horn-Schunck sweeps between two ghost-row exchanges (rounded up to a multiple of hs_fuse)
+  int band_exchange = 32;   // Horn-Schunck sweeps between two ghost-row exchanges (rounded up to a multiple of hs_fuse)
   int band_reach = 8;       // rows the warp may reach beyond a band's ghost frame (>= max |v| / 2 + 2)
   // timings of the last call
   std::vector<StageTime> times;
@@ -727,7 +727,7 @@ int make_band_plan_opts(ofri_handle h, int H, int W, const ofri_params* p, int r
   if (H % (n * fmax) != 0)
     return fail(h, OFRI_ERR_UNSUPPORTED, "row-band mode needs H (%d) divisible by ranks x 2^(levels-1) = %d", H, n * fmax);
   int T = hs_fuse > 0 ? (hs_fuse == 7 ? 6 : (hs_fuse > 8 ? 8 : hs_fuse)) : 1;
-  int E = band_exchange > 0 ? band_exchange : 16;
+  int E = band_exchange > 0 ? band_exchange : 32;
   E = (E + T - 1) / T * T;
   bp->L = L;
   bp->E = E;

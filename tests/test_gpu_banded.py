@@ -61,7 +61,7 @@ def test_band_plan_and_errors(ofri):
         assert b.exchange % h.get_option("hs_fuse") == 0
         with pytest.raises(NotImplementedError):      # 1000 is not divisible by 3 ranks x 2
             h.band_plan(1000, 64, p, 0, 3)
-        with pytest.raises(ValueError):               # 8 coarse rows per rank < 16-row exchange
+        with pytest.raises(ValueError):               # 8 coarse rows per rank < the exchange interval
             h.band_plan(64, 64, p, 0, 4)
     finally:
         h.close()

@@ -14,6 +14,12 @@ from HornSchunck import HSOpticalFlowAlgoAdapter  # noqa: E402
 from PhysicsBasedOpticalFlowLiuShen import LiuShenOpticalFlowAlgoAdapter  # noqa: E402
 from opticalflow_ri_b200.synthetic import synthetic_piv_pair  # noqa: E402
 
+import opticalflow_ri_b200 as ofri  # noqa: E402
+_h = ofri.default_handle(0)
+for k in ("hs_fuse", "hs_variant", "ls_fuse", "ls_variant"):
+    if os.environ.get(k.upper()):
+        _h.set_option(k, int(os.environ[k.upper()]))
+print({k: _h.get_option(k) for k in ("hs_fuse", "hs_variant", "ls_fuse", "ls_variant")})
 for n in (512, 1024, 2048):
     a, b = synthetic_piv_pair(n, n, 0)
     ts = []

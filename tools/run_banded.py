@@ -38,7 +38,7 @@ def main():
     ap.add_argument("--check-size", type=int, default=2048)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--hs-niter", type=int, default=600)
-    ap.add_argument("--exchange", type=int, default=0, help="HS sweeps between ghost-row exchanges (0 = default 16)")
+    ap.add_argument("--exchange", type=int, default=0, help="HS sweeps between ghost-row exchanges (0 = default 32)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
