@@ -35,6 +35,8 @@ struct ofri_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr, s_in = nullptr, s_out = nullptr, s_aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // U / V spline up-samples run concurrently on stream + s_aux
+  cudaStream_t s_comm = nullptr;                      // row-band mode: ghost-row exchanges overlapping interior tiles
+  cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   std::string err;
   // bump arena for per-call workspace (stream-ordered reuse)
@@ -816,8 +818,9 @@ void plan_band_ws(Bump& b, const BandPlanInt& bp, int W, const ofri_params* p, B
 }
 
 // ghost rows of one (U, V) pair <- the neighbours' owned rows; o0 / o1 = LOCAL row range the band owns
-int band_exchange_uv(ofri_handle h, const Img& U, const Img& V, int o0, int o1, int E) {
+int band_exchange_uv(ofri_handle h, const Img& U, const Img& V, int o0, int o1, int E, cudaStream_t stream = nullptr) {
   ofri::Comm* c = h->comm;
+  if (!stream) stream = h->stream;
   if (!c || c->nranks == 1) return OFRI_OK;
   const long pitch = U.pitch;
   const bool up = c->rank > 0, dn = c->rank < c->nranks - 1;
@@ -825,7 +828,7 @@ int band_exchange_uv(ofri_handle h, const Img& U, const Img& V, int o0, int o1, 
   float* ru[2] = {up ? U.p + (long)(o0 - E) * pitch : U.p, up ? V.p + (long)(o0 - E) * pitch : V.p};
   const float* sd[2] = {U.p + (long)(o1 - E) * pitch, V.p + (long)(o1 - E) * pitch};
   float* rd[2] = {dn ? U.p + (long)o1 * pitch : U.p, dn ? V.p + (long)o1 * pitch : V.p};
-  if (c->exchange(2, su, ru, sd, rd, (size_t)E * pitch, h->stream))
+  if (c->exchange(2, su, ru, sd, rd, (size_t)E * pitch, stream))
     return fail(h, OFRI_ERR_COMM, "ghost-row exchange failed: %s", c->error());
   h->lc.n += 0;
   return OFRI_OK;
@@ -867,15 +870,26 @@ int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs
       Timed t(h, precise ? "hs_iterate_precise" : "hs_iterate");
       const int niter = a.hs_niter;
       const int c0 = cur;
-      HsHook hook = [&](int done, int which) {
-        if (*comm_rc) return;
-        if (done % E == 0 || done == niter) {
-          const int b = which ? (c0 ^ 1) : c0;
-          *comm_rc = band_exchange_uv(h, U[b], V[b], o0, o1, E);
-        }
+      // every E sweeps: the tiles producing the rows the neighbours need run first, the exchange of the buffer just
+      // written then proceeds on the communication stream under the interior tiles (HsSplit, ofri_internal.h)
+      HsSplit split;
+      split.every = E;
+      split.mid_lo = o0 + E;
+      split.mid_hi = o1 - E;
+      split.begin = [&](int which) {
+        if (*comm_rc || !c || c->nranks == 1) return;
+        const int b = which ? (c0 ^ 1) : c0;
+        cudaEventRecord(h->ev_c0, s);
+        cudaStreamWaitEvent(h->s_comm, h->ev_c0, 0);
+        *comm_rc = band_exchange_uv(h, U[b], V[b], o0, o1, E, h->s_comm);
+        cudaEventRecord(h->ev_c1, h->s_comm);
+      };
+      split.end = [&]() {
+        if (!c || c->nranks == 1) return;
+        cudaStreamWaitEvent(s, h->ev_c1, 0);
       };
       res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], niter, h->hs_fuse,
-                              h->hs_variant, precise, s, h->lc, hook);
+                              h->hs_variant, precise, s, h->lc, HsHook(), &split);
     }
     cur = res ? (cur ^ 1) : cur;
     if (d_err) {
@@ -1115,7 +1129,8 @@ int ofri_create(int device, ofri_handle* out) {
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return fail(nullptr, OFRI_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
@@ -1126,6 +1141,8 @@ int ofri_create(int device, ofri_handle* out) {
   }
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_c0, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_c1, cudaEventDisableTiming);
   h->stream = h->own_stream;
   *out = h;
   return OFRI_OK;
@@ -1149,6 +1166,9 @@ int ofri_destroy(ofri_handle h) {
   cudaStreamDestroy(h->s_in);
   cudaStreamDestroy(h->s_out);
   cudaStreamDestroy(h->s_aux);
+  cudaStreamDestroy(h->s_comm);
+  cudaEventDestroy(h->ev_c0);
+  cudaEventDestroy(h->ev_c1);
   cudaEventDestroy(h->ev_fork);
   cudaEventDestroy(h->ev_join);
   delete h;

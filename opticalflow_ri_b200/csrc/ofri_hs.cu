@@ -545,16 +545,19 @@ static void launch_hs_regs_T(int variant, const Img& ui, const Img& vi, const Im
   }
 }
 
-static void launch_hs_fused(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo,
-                            const Img& vo, const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
+// returns true if the launch honoured `sub` (only the TMA kernel can run a subset of the tile rows)
+static bool launch_hs_fused(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo,
+                            const Img& vo, const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s,
+                            const HsTileRows* sub = nullptr) {
   if (variant >= 24) {                        // persistent TMA-fed register-resident kernel (ofri_hs_tma.cu)
-    if (launch_hs_tma(T, variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, s)) return;
+    if (launch_hs_tma(T, variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, s, sub)) return true;
     variant = 8;                              // other T / no tensor-map support: non-persistent kernels
   }
+  if (sub && !sub->inside) return false;      // the other kernels always run whole launches: do it in the second part
   if (variant >= 8 && precise) variant = 2;   // the other register-resident kernels are built for the fast arithmetic only
   if (variant >= 16) {                        // packed-f32x2 register-resident kernel (ofri_hs_pk.cu)
     launch_hs_packed(T, variant, ui, vi, uo, vo, fx, fy, ft, s);
-    return;
+    return true;
   }
   if (variant >= 8) {
 #define OFRI_HR_T(TT) \
@@ -569,7 +572,7 @@ static void launch_hs_fused(int T, int variant, bool precise, const Img& ui, con
       default: launch_hs_regs_T<8, false>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
     }
 #undef OFRI_HR_T
-    return;
+    return true;
   }
 #define OFRI_HS_T(TT)                                                                             \
   case TT:                                                                                        \
@@ -589,11 +592,12 @@ static void launch_hs_fused(int T, int variant, bool precise, const Img& ui, con
       break;
   }
 #undef OFRI_HS_T
+  return true;
 }
 
 int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb, const Img& fx, const Img& fy,
                       const Img& ft, float alpha, int niter, int fuse, int variant, bool precise, cudaStream_t s,
-                      LaunchCounter& lc, const HsHook& hook) {
+                      LaunchCounter& lc, const HsHook& hook, const HsSplit* split) {
   const float alpha2 = alpha * alpha;   // f32 alpha**2 as in the numba signature (HornSchunck.py:52-55)
   int cur = 0;
   const Img* U[2] = {&ua, &ub};
@@ -620,11 +624,31 @@ int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb
         hs_sweep_simple_kernel<true><<<g, b, 0, s>>>(*U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2);
       else
         hs_sweep_simple_kernel<false><<<g, b, 0, s>>>(*U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2);
+      if (split && split->every > 0 && ((done + 1) % split->every == 0 || done + 1 == niter)) {
+        split->begin(cur ^ 1);
+        split->end();
+      }
       done += 1;
     } else {
       int T = left < fuse ? left : fuse;
       if (T == 7) T = 6;
-      launch_hs_fused(T, variant, precise, *U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2, s);
+      const bool block_end = split && split->every > 0 && ((done + T) % split->every == 0 || done + T == niter);
+      if (block_end) {
+        // boundary tiles first, then the exchange of the freshly written buffer starts (other stream) while the
+        // interior tiles run; a kernel that cannot split runs whole and the exchange follows it
+        const HsTileRows outer{split->mid_lo, split->mid_hi, false}, inner{split->mid_lo, split->mid_hi, true};
+        if (launch_hs_fused(T, variant, precise, *U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2, s, &outer)) {
+          split->begin(cur ^ 1);
+          launch_hs_fused(T, variant, precise, *U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2, s, &inner);
+          lc.n += 1;
+        } else {
+          launch_hs_fused(T, variant, precise, *U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2, s);
+          split->begin(cur ^ 1);
+        }
+        split->end();
+      } else {
+        launch_hs_fused(T, variant, precise, *U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2, s);
+      }
       done += T;
     }
     cur ^= 1;

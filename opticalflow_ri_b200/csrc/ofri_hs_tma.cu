@@ -49,13 +49,15 @@ struct TmCfg {
 struct TmTile { int x0, y0, b; };
 
 template <int T, int R, int NRG>
-__device__ __forceinline__ TmTile tm_decode(int tile, int tiles_x, int tiles_y) {
+__device__ __forceinline__ TmTile tm_decode(int tile, int tiles_x, int tiles_y, int4 rows) {
   using C = TmCfg<T, R, NRG>;
   const int per = tiles_x * tiles_y;
   TmTile t;
   t.b = tile / per;
   const int r = tile - t.b * per;
-  const int by = r / tiles_x, bx = r - by * tiles_x;
+  int by = r / tiles_x;
+  const int bx = r - by * tiles_x;
+  by += by < rows.x ? rows.y : rows.z;     // tile-row subset of a split launch (rows = {cut, off0, off1, -}); identity otherwise
   t.x0 = bx * C::TW - C::HX;
   t.y0 = by * C::TH - T;
   return t;
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(TmCfg<T, R, NRG>::NT, 1)
 hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CUtensorMap mV,
               const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
               const __grid_constant__ CUtensorMap mC, Img uo, Img vo, int W, int H, int tiles_x, int tiles_y,
-              int ntiles, float alpha2) {
+              int ntiles, float alpha2, int4 rows) {
   using C = TmCfg<T, R, NRG>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage = reinterpret_cast<float*>(smem_raw);
@@ -391,7 +393,7 @@ hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CU
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    const TmTile t0 = tm_decode<T, R, NRG>(tile, tiles_x, tiles_y);
+    const TmTile t0 = tm_decode<T, R, NRG>(tile, tiles_x, tiles_y, rows);
     mbar_expect_tx(bar, (unsigned)C::STAGE_BYTES);
     const unsigned dst = smem_u32(stage);
     tma_load_3d(dst + 0 * C::PLANE * 4, &mU, t0.x0, t0.y0, t0.b, bar);
@@ -403,10 +405,10 @@ hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CU
   __syncthreads();
   unsigned phase = 0;
   for (; tile < ntiles; tile += gridDim.x) {
-    const TmTile tl = tm_decode<T, R, NRG>(tile, tiles_x, tiles_y);
+    const TmTile tl = tm_decode<T, R, NRG>(tile, tiles_x, tiles_y, rows);
     const int nt = tile + gridDim.x;
     const bool has_next = nt < ntiles;
-    const TmTile nx = tm_decode<T, R, NRG>(has_next ? nt : tile, tiles_x, tiles_y);
+    const TmTile nx = tm_decode<T, R, NRG>(has_next ? nt : tile, tiles_x, tiles_y, rows);
     const bool edge = (tl.x0 < 0) || (tl.x0 + C::SW > W) || (tl.y0 < 0) || (tl.y0 + C::SH > H);   // CTA-uniform
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -420,7 +422,7 @@ hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CU
 
 template <int T, int R, int NRG, bool PRECISE>
 static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx, const Img& fy,
-                       const Img& ft, float alpha2, int num_sms, cudaStream_t s) {
+                       const Img& ft, float alpha2, int num_sms, cudaStream_t s, const HsTileRows* sub) {
   using C = TmCfg<T, R, NRG>;
   if (ui.W <= C::HX + 1 || ui.H <= T + 1) return false;   // the ghost frame mirrors HX columns / T rows of real cells
   CUtensorMap mU, mV, mA, mB, mC;
@@ -432,33 +434,50 @@ static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& v
     cudaGetLastError();
     return false;
   }
-  const int tiles_x = (ui.W + C::TW - 1) / C::TW, tiles_y = (ui.H + C::TH - 1) / C::TH;
+  const int tiles_x = (ui.W + C::TW - 1) / C::TW, tiles_y_all = (ui.H + C::TH - 1) / C::TH;
+  int tiles_y = tiles_y_all;
+  int4 rows = make_int4(tiles_y_all, 0, 0, 0);
+  if (sub) {   // split launch: the tile rows lying entirely inside output rows [row_lo, row_hi), or all the others
+    int m_lo = (sub->row_lo + C::TH - 1) / C::TH, m_hi = sub->row_hi / C::TH;
+    if (m_lo < 0) m_lo = 0;
+    if (m_hi > tiles_y_all) m_hi = tiles_y_all;
+    if (m_hi < m_lo) m_hi = m_lo;
+    if (sub->inside) {
+      tiles_y = m_hi - m_lo;
+      rows = make_int4(tiles_y, m_lo, 0, 0);
+    } else {
+      tiles_y = m_lo + (tiles_y_all - m_hi);
+      rows = make_int4(m_lo, 0, m_hi - m_lo, 0);
+    }
+    if (tiles_y == 0) return true;
+  }
   const long ntiles = (long)tiles_x * tiles_y * ui.batch;
   if (ntiles > 0x7fffffffL) return false;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
   kern<<<grid, C::NT, C::SMEM_BYTES, s>>>(mU, mV, mA, mB, mC, uo, vo, ui.W, ui.H, tiles_x, tiles_y, (int)ntiles,
-                                          alpha2);
+                                          alpha2, rows);
   return true;
 }
 
 template <int T>
 static bool launch_T(int variant, bool precise, const Img& ui, const Img& vi, const Img& uo, const Img& vo,
-                     const Img& fx, const Img& fy, const Img& ft, float alpha2, int num_sms, cudaStream_t s) {
+                     const Img& fx, const Img& fy, const Img& ft, float alpha2, int num_sms, cudaStream_t s,
+                     const HsTileRows* sub) {
   if (precise)   // doubles in registers: 4-row strips, 34 x 128 tile, 256 threads
-    return launch_cfg<T, 4, 8, true>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);
+    return launch_cfg<T, 4, 8, true>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);
   switch (variant) {
     default:
-    case 24: return launch_cfg<T, 8, 8, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);     // 66 x 128, 256 threads
-    case 25: return launch_cfg<T, 6, 8, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);     // 50 x 128, 256 threads
-    case 26: return launch_cfg<T, 4, 12, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);    // 50 x 128, 384 threads
-    case 27: return launch_cfg<T, 6, 10, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);    // 62 x 128, 320 threads
+    case 24: return launch_cfg<T, 8, 8, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);     // 66 x 128, 256 threads
+    case 25: return launch_cfg<T, 6, 8, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);     // 50 x 128, 256 threads
+    case 26: return launch_cfg<T, 4, 12, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);    // 50 x 128, 384 threads
+    case 27: return launch_cfg<T, 6, 10, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);    // 62 x 128, 320 threads
   }
 }
 
 // T in {4, 6, 8}.  Returns false if this kernel cannot run (other T, no driver entry point, map encoding failed): the
 // caller then uses the non-persistent kernels.
 bool launch_hs_tma(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo, const Img& vo,
-                   const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
+                   const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s, const HsTileRows* sub) {
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -467,9 +486,9 @@ bool launch_hs_tma(int T, int variant, bool precise, const Img& ui, const Img& v
     if (num_sms <= 0) num_sms = 148;
   }
   switch (T) {
-    case 4: return launch_T<4>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);
-    case 6: return launch_T<6>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);
-    case 8: return launch_T<8>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s);
+    case 4: return launch_T<4>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);
+    case 6: return launch_T<6>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);
+    case 8: return launch_T<8>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);
     default: return false;
   }
 }

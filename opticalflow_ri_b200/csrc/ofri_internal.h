@@ -61,6 +61,19 @@ struct LsBand { int own_lo; int own_hi; double npix; };
 typedef std::function<void(int k0, int n, int written)> LsHook;
 // Same for Horn-Schunck: after `done` sweeps in total, the current state is in buffer `cur` (0 = a, 1 = b).
 typedef std::function<void(int done, int cur)> HsHook;
+// Split launch of the TMA kernel: only the tile rows lying entirely inside output rows [row_lo, row_hi) (inside = true)
+// or all the other tile rows (inside = false).
+struct HsTileRows { int row_lo; int row_hi; bool inside; };
+// Row-band mode with overlap: the launch that completes a block of `every` sweeps (and the last launch) is issued in
+// two parts -- first the tiles that produce the rows the neighbours need (everything outside [mid_lo, mid_hi)), then
+// begin(cur) starts the ghost-row exchange of buffer `cur` on the communication stream, then the interior tiles run
+// under it, then end() makes the compute stream wait for the exchange.
+struct HsSplit {
+  int every = 0;
+  int mid_lo = 0, mid_hi = 0;
+  std::function<void(int cur)> begin;
+  std::function<void()> end;
+};
 
 
 // ---- stages (ofri_stages.cu) ---------------------------------------------------------------------------------
@@ -95,13 +108,14 @@ void launch_hs_derivs(const Img& im1, const Img& im2, const Img& fx, const Img& 
 // precise = reference arithmetic bit for bit (f64-accumulated stencil, IEEE division) instead of the f32/FMA fast path.
 int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb, const Img& fx, const Img& fy,
                       const Img& ft, float alpha, int niter, int fuse, int variant, bool precise, cudaStream_t s,
-                      LaunchCounter& lc, const HsHook& hook = HsHook());
+                      LaunchCounter& lc, const HsHook& hook = HsHook(), const HsSplit* split = nullptr);
 // packed-f32x2 register-resident fused sweeps (ofri_hs_pk.cu): T sweeps ui,vi -> uo,vo on prepared (a, b, c) planes
 void launch_hs_packed(int T, int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
                       const Img& fy, const Img& ft, cudaStream_t s);
 // persistent TMA-fed register-resident fused sweeps (ofri_hs_tma.cu); false = not applicable, use another kernel
 bool launch_hs_tma(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo, const Img& vo,
-                   const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s);
+                   const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s,
+                   const HsTileRows* sub = nullptr);
 // err[b] = (sqrt(sum (u-u0)^2) + sqrt(sum (v-v0)^2)) / (H*W); u0.p == nullptr means u0 = v0 = 0.  acc: [batch][2] f64 scratch
 void launch_hs_error(const Img& u, const Img& v, const Img& u0, const Img& v0, double* acc, float* err, int err_stride,
                      cudaStream_t s, LaunchCounter& lc);
