@@ -53,6 +53,8 @@ struct ofri_ctx {
   int hs_precise = 1;   // 0 = fast f32/FMA everywhere, 1 = reference arithmetic on the coarse pyramid levels, 2 = everywhere
   // row-band (domain-decomposed) mode
   ofri::Comm* comm = nullptr;
+  int hs_fuse_fast = 0;     // fuse factor of the fast-arithmetic Horn-Schunck launches only (0 = hs_fuse)
+  int auto_fuse = 1;        // deeper fusion for launches that cannot fill the GPU (see eff_hs_fuse)
   int band_exchange = 32;   // Horn-Schunck sweeps between two ghost-row exchanges (rounded up to a multiple of hs_fuse)
   int band_reach = 8;       // rows the warp may reach beyond a band's ghost frame (>= max |v| / 2 + 2)
   // timings of the last call
@@ -353,6 +355,19 @@ void plan_workspace(Bump& b, int batch, int H, int W, const ofri_params* p, Work
   ws->lsw_flag = (int*)b.take(sizeof(int) * 4);
 }
 
+// A launch that cannot fill the GPU (fewer tiles than SMs, e.g. one 512 x 512 pair) is bound by launch latency, not by
+// throughput: fuse 8 (Horn-Schunck) / 4 (Liu-Shen) sweeps per launch then.  Results do not depend on the fuse factor
+// (bit-identical, tested).  Not used in row-band mode, where the exchange interval is tied to the configured factor.
+int eff_hs_fuse(ofri_handle h, int H, int W, int batch, bool precise = false) {
+  const int fuse = (!precise && h->hs_fuse_fast > 0) ? h->hs_fuse_fast : h->hs_fuse;
+  if (!h->auto_fuse || fuse < 1 || fuse >= 8) return fuse;
+  return (long)((W + 119) / 120) * ((H + 57) / 58) * batch < 148 ? 8 : fuse;
+}
+int eff_ls_fuse(ofri_handle h, int H, int W, int batch) {
+  if (!h->auto_fuse || h->ls_fuse < 1 || h->ls_fuse >= 4) return h->ls_fuse;
+  return (long)((W + 119) / 120) * ((H + 29) / 30) * batch < 148 ? 4 : h->ls_fuse;
+}
+
 GaussTaps make_taps(const float* k, int n) {
   GaussTaps t;
   t.K = n;
@@ -387,7 +402,7 @@ int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws
       const bool precise = h->hs_precise >= 2 || (h->hs_precise == 1 && coarse_level);
       Timed t(h, precise ? "hs_iterate_precise" : "hs_iterate");
       res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], a.hs_niter,
-                              h->hs_fuse, h->hs_variant, precise, s, h->lc);
+                              eff_hs_fuse(h, Hl, Wl, U[cur].batch, precise), h->hs_variant, precise, s, h->lc);
     }
     cur = res ? (cur ^ 1) : cur;
     if (d_err) {
@@ -405,8 +420,8 @@ int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws
   }
   {
     Timed t(h, "ls_iterate");
-    launch_ls_solve(V[cur], U[cur], V[cur ^ 1], U[cur ^ 1], co, a.ls_h, a.ls_maxiter, a.ls_tol, h->ls_fuse,
-                    h->ls_variant, ws.ls_errs,
+    launch_ls_solve(V[cur], U[cur], V[cur ^ 1], U[cur ^ 1], co, a.ls_h, a.ls_maxiter, a.ls_tol,
+                    eff_ls_fuse(h, Hl, Wl, U[cur].batch), h->ls_variant, ws.ls_errs,
                     ws.ls_state, V[cur], U[cur], d_err, err_stride, nullptr, s, h->lc);
   }
   return cur;
@@ -888,7 +903,9 @@ int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs
         if (!c || c->nranks == 1) return;
         cudaStreamWaitEvent(s, h->ev_c1, 0);
       };
-      res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], niter, h->hs_fuse,
+      int fuse = h->hs_fuse;
+      if (!precise && h->hs_fuse_fast > 0 && E % h->hs_fuse_fast == 0) fuse = h->hs_fuse_fast;
+      res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], niter, fuse,
                               h->hs_variant, precise, s, h->lc, HsHook(), &split);
     }
     cur = res ? (cur ^ 1) : cur;
@@ -1207,6 +1224,8 @@ static int* option_slot(ofri_handle h, const char* key) {
   if (!strcmp(key, "ls_variant")) return &h->ls_variant;
   if (!strcmp(key, "chunk_pairs")) return &h->chunk_pairs;
   if (!strcmp(key, "timing")) return &h->timing;
+  if (!strcmp(key, "auto_fuse")) return &h->auto_fuse;
+  if (!strcmp(key, "hs_fuse_fast")) return &h->hs_fuse_fast;
   if (!strcmp(key, "band_exchange")) return &h->band_exchange;
   if (!strcmp(key, "band_reach")) return &h->band_reach;
   return nullptr;
@@ -1354,8 +1373,8 @@ int ofri_hs_compute(ofri_handle h, const float* im1, const float* im2, const flo
       return rc;
   }
   launch_hs_derivs(i1, i2, fx, fy, ft, h->stream, h->lc);
-  int res = launch_hs_iterate(U[0], V[0], U[1], V[1], fx, fy, ft, alpha, niter, h->hs_fuse, h->hs_variant,
-                              h->hs_precise >= 2, h->stream, h->lc);
+  int res = launch_hs_iterate(U[0], V[0], U[1], V[1], fx, fy, ft, alpha, niter, eff_hs_fuse(h, H, W, batch),
+                              h->hs_variant, h->hs_precise >= 2, h->stream, h->lc);
   Img nu, nv;
   launch_hs_error(U[res], V[res], zero0 ? nu : U0, zero0 ? nv : V0, acc, d_err, 1, h->stream, h->lc);
   if ((rc = download(h, u_out, U[res])) || (rc = download(h, v_out, V[res]))) return rc;
@@ -1392,7 +1411,7 @@ int ofri_ls_compute(ofri_handle h, const float* im1, const float* im2, const flo
     return rc;
   }
   launch_ls_coefficients(i1, i2, hpar, co, mx, h->stream, h->lc);
-  launch_ls_solve(V[0], U[0], V[1], U[1], co, hpar, maxiter, tol, h->ls_fuse, h->ls_variant, errs, state, V[0], U[0],
+  launch_ls_solve(V[0], U[0], V[1], U[1], co, hpar, maxiter, tol, eff_ls_fuse(h, H, W, batch), h->ls_variant, errs, state, V[0], U[0],
                   d_err, 1, d_it,
                   h->stream, h->lc);
   if ((rc = download(h, u_out, U[0])) || (rc = download(h, v_out, V[0]))) return rc;

@@ -29,6 +29,7 @@ def ofri():
 @pytest.fixture(scope="module")
 def h(ofri):
     hd = ofri.Handle(0)          # raises (no CPU fallback) if the CUDA library / GPU is missing
+    hd.set_option("auto_fuse", 0)   # the tests below pick fuse factors explicitly (see test_auto_fuse_is_invisible)
     yield hd
     hd.close()
 
@@ -373,6 +374,21 @@ def test_driver_baseline_configs_bundled(h, ofri, configs_bundled, bundled_pair,
     print("\n%s: max|dU| %.3g max|dV| %.3g |dEPE-RMSE| %.3g" % (cfg, du, dv, de))
     assert du <= TOL_FLOW and dv <= TOL_FLOW, (du, dv)
     assert de <= TOL_EPE, de
+
+
+def test_auto_fuse_is_invisible(h, ofri, configs_small):
+    """Launches that cannot fill the GPU fuse deeper (8 HS / 4 LS sweeps per launch): same bits."""
+    s = configs_small
+    mk = lambda: ofri.make_params(ofri.hs_algo([45, 21], 52), ofri.ls_algo(5), filter_sigma=3.4, filter_opt_sigma=0.48,
+                                  pyramid_levels=2, **HS_DEF)
+    U0, V0 = h.pyramidal_flow(s["crop0"], s["crop1"], mk())
+    try:
+        h.set_option("auto_fuse", 1)
+        U1, V1 = h.pyramidal_flow(s["crop0"], s["crop1"], mk())
+    finally:
+        h.set_option("auto_fuse", 0)
+    same(U1, U0)
+    same(V1, V0)
 
 
 def test_errors_reported(h, ofri, configs_small):

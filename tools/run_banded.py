@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--check-size", type=int, default=2048)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--hs-niter", type=int, default=600)
+    ap.add_argument("--ls-fuse", type=int, default=0)
+    ap.add_argument("--hs-fuse-fast", type=int, default=0)
     ap.add_argument("--exchange", type=int, default=0, help="HS sweeps between ghost-row exchanges (0 = default 32)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
@@ -51,6 +53,10 @@ def main():
     h.set_stream(stream.cuda_stream)
     if args.exchange:
         h.set_option("band_exchange", args.exchange)
+    if args.ls_fuse:
+        h.set_option("ls_fuse", args.ls_fuse)
+    if args.hs_fuse_fast:
+        h.set_option("hs_fuse_fast", args.hs_fuse_fast)
     if world > 1:
         uid = [ofri.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
