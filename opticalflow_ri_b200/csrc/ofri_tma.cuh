@@ -12,17 +12,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static EncodeTiledFn fn = [] {      // thread-safe one-time lookup (row bands may be driven by several host threads)
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
+    EncodeTiledFn f = nullptr;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
+      f = reinterpret_cast<EncodeTiledFn>(p);
     cudaGetLastError();
-  }
+    return f;
+  }();
   return fn;
 }
 
