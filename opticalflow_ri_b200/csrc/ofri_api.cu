@@ -57,6 +57,7 @@ struct ofri_ctx {
   int auto_fuse = 1;        // deeper fusion for launches that cannot fill the GPU (see eff_hs_fuse)
   int band_exchange = 32;   // Horn-Schunck sweeps between two ghost-row exchanges (rounded up to a multiple of hs_fuse)
   int band_reach = 8;       // rows the warp may reach beyond a band's ghost frame (>= max |v| / 2 + 2)
+  int spline_variant = 1;   // 1 = chunk-parallel windowed solves + fused row kernel, 0 = sequential line solves (A/B)
   // timings of the last call
   std::vector<StageTime> times;
   std::vector<std::pair<std::string, float>> times_ms;
@@ -493,10 +494,17 @@ int run_pyramid(ofri_handle h, const Img& im1, const Img& im2, const ofri_params
         // the tridiagonal solves have one thread per line (latency bound): run the two components side by side
         cudaEventRecord(h->ev_fork, s);
         cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0);
-        launch_spline(ua, un, mx, sy, sx, M1, T1, M2, s, h->lc);
-        launch_spline(va, vn, my, sy, sx, M1b, T1b, M2b, h->s_aux, h->lc);
+        bool ok = true;
+        if (h->spline_variant == 0) {
+          launch_spline_seq(ua, un, mx, sy, sx, M1, T1, M2, s, h->lc);
+          launch_spline_seq(va, vn, my, sy, sx, M1b, T1b, M2b, h->s_aux, h->lc);
+        } else {                      // T1 (H x w) doubles as the forward-elimination scratch (h x w)
+          ok = launch_spline(ua, un, mx, sy, sx, M1, viewd(ws.T1, prevH, prevW), s, h->lc) &&
+               launch_spline(va, vn, my, sy, sx, M1b, viewd(ws.T1b, prevH, prevW), h->s_aux, h->lc);
+        }
         cudaEventRecord(h->ev_join, h->s_aux);
         cudaStreamWaitEvent(s, h->ev_join, 0);
+        if (!ok) return fail(h, OFRI_ERR_CUDA, "spline up-sample launch failed");
       } else {
         launch_copy(un, ua, s, h->lc);
         launch_copy(vn, va, s, h->lc);
@@ -813,10 +821,11 @@ void plan_band_ws(Bump& b, const BandPlanInt& bp, int W, const ofri_params* p, B
     ws->gU = b.plane(1, c.Hl, c.Wl);
     ws->gV = b.plane(1, c.Hl, c.Wl);
     ws->M1 = b.planed(1, c.Hl, c.Wl);
-    ws->T1 = b.planed(1, rows, c.Wl);
+    const int trows = rows > c.Hl ? rows : c.Hl;   // T1: legacy T1 (rows x w) or forward-elimination scratch (strip x w)
+    ws->T1 = b.planed(1, trows, c.Wl);
     ws->M2 = b.planed(1, rows, c.Wl);
     ws->M1b = b.planed(1, c.Hl, c.Wl);
-    ws->T1b = b.planed(1, rows, c.Wl);
+    ws->T1b = b.planed(1, trows, c.Wl);
     ws->M2b = b.planed(1, rows, c.Wl);
   }
   if (has_ls) {
@@ -998,41 +1007,82 @@ int run_pyramid_banded(ofri_handle h, const float* d_im1, const float* d_im2, in
       const BandLevel& pl = bp.lv[l - 1];
       const int prow = pl.ext1 - pl.ext0;
       Img ua = view(Uacc, prow, pl.Wl), va = view(Vacc, prow, pl.Wl);
-      Img gU = view(ws.gU, pl.Hl, pl.Wl), gV = view(ws.gV, pl.Hl, pl.Wl);
       Img un = view(us, rows, Wl), vn = view(vs, rows, Wl);
+      SplineSys sy, sx;
+      int rc = get_spline_sys(h, pl.Hl, &sy);
+      if (rc) return rc;
+      rc = get_spline_sys(h, pl.Wl, &sx);
+      if (rc) return rc;
+      const int per_c = pl.own1 - pl.own0, per_f = bl.own1 - bl.own0;
+      const size_t own_cnt = (size_t)per_c * ua.pitch;
+      const float* su = ua.p + (size_t)(pl.own0 - pl.ext0) * ua.pitch;
+      const float* sv = va.p + (size_t)(pl.own0 - pl.ext0) * va.pitch;
+      // The column-direction solve needs, for this band's output rows, only a WINDOW of every column: the band's own
+      // coarse rows + `halo` rows of each neighbour (ofri_spline.cuh).  halo = the largest reach over all ranks, so
+      // that the (symmetric) exchange moves the same count everywhere.  Bands thinner than the halo fall back to the
+      // all-gather of the whole coarse plane.
+      int halo = 0;
+      for (int rr = 0; rr < n; ++rr) {
+        const int e0 = rr * per_f - bp.G < 0 ? 0 : rr * per_f - bp.G;
+        const int e1 = (rr + 1) * per_f + bp.G > bl.Hl ? bl.Hl : (rr + 1) * per_f + bp.G;
+        int lo, hi;
+        spline_rows_needed(e0, e1 - e0, pl.Hl, bl.Hl, sy, &lo, &hi);
+        if (rr * per_c - lo > halo) halo = rr * per_c - lo;
+        if (hi - (rr + 1) * per_c > halo) halo = hi - (rr + 1) * per_c;
+      }
+      const bool windowed = h->spline_variant != 0 && (n == 1 || halo <= per_c);
+      int S0 = 0, S1 = pl.Hl;                       // coarse rows held by the strip gU / gV
+      if (windowed && n > 1) {
+        S0 = pl.own0 - halo < 0 ? 0 : pl.own0 - halo;
+        S1 = pl.own1 + halo > pl.Hl ? pl.Hl : pl.own1 + halo;
+      }
+      Img gU = view(ws.gU, S1 - S0, pl.Wl), gV = view(ws.gV, S1 - S0, pl.Wl);
       {
         Timed t(h, "gather");
-        const size_t cnt = (size_t)(pl.own1 - pl.own0) * ua.pitch;
-        const float* su = ua.p + (size_t)(pl.own0 - pl.ext0) * ua.pitch;
-        const float* sv = va.p + (size_t)(pl.own0 - pl.ext0) * va.pitch;
-        if (c && n > 1) {
-          if (c->allgather(su, gU.p, cnt, s) || c->allgather(sv, gV.p, cnt, s))
+        if (c && n > 1 && windowed) {
+          float* ou = gU.p + (size_t)(pl.own0 - S0) * gU.pitch;
+          float* ov = gV.p + (size_t)(pl.own0 - S0) * gV.pitch;
+          cudaMemcpyAsync(ou, su, own_cnt * sizeof(float), cudaMemcpyDeviceToDevice, s);
+          cudaMemcpyAsync(ov, sv, own_cnt * sizeof(float), cudaMemcpyDeviceToDevice, s);
+          const size_t hc = (size_t)halo * gU.pitch;
+          const float* s_up[2] = {su, sv};
+          float* r_up[2] = {gU.p, gV.p};                                  // rows [own0 - halo, own0) (ranks > 0: S0 = own0 - halo)
+          const float* s_dn[2] = {su + own_cnt - hc, sv + own_cnt - hc};
+          float* r_dn[2] = {ou + own_cnt, ov + own_cnt};                  // rows [own1, own1 + halo)
+          if (c->exchange(2, s_up, r_up, s_dn, r_dn, hc, s))
+            return fail(h, OFRI_ERR_COMM, "halo exchange of the coarse flow failed: %s", c->error());
+        } else if (c && n > 1) {
+          if (c->allgather(su, gU.p, own_cnt, s) || c->allgather(sv, gV.p, own_cnt, s))
             return fail(h, OFRI_ERR_COMM, "all-gather of the coarse flow failed: %s", c->error());
         } else {
-          cudaMemcpyAsync(gU.p, su, cnt * sizeof(float), cudaMemcpyDeviceToDevice, s);
-          cudaMemcpyAsync(gV.p, sv, cnt * sizeof(float), cudaMemcpyDeviceToDevice, s);
+          cudaMemcpyAsync(gU.p, su, own_cnt * sizeof(float), cudaMemcpyDeviceToDevice, s);
+          cudaMemcpyAsync(gV.p, sv, own_cnt * sizeof(float), cudaMemcpyDeviceToDevice, s);
         }
       }
       {
         Timed t(h, "spline_upsample");
-        SplineSys sy, sx;
-        int rc = get_spline_sys(h, pl.Hl, &sy);
-        if (rc) return rc;
-        rc = get_spline_sys(h, pl.Wl, &sx);
-        if (rc) return rc;
         float mx = 1.0f, my = 1.0f;
         if (local_scaling) {
           mx = (float)Wl / (float)pl.Wl;
           my = (float)bl.Hl / (float)pl.Hl;
         }
-        ImgD M1 = viewd(ws.M1, pl.Hl, pl.Wl), T1 = viewd(ws.T1, rows, pl.Wl), M2 = viewd(ws.M2, rows, pl.Wl);
-        ImgD M1b = viewd(ws.M1b, pl.Hl, pl.Wl), T1b = viewd(ws.T1b, rows, pl.Wl), M2b = viewd(ws.M2b, rows, pl.Wl);
         cudaEventRecord(h->ev_fork, s);
         cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0);
-        launch_spline(gU, un, mx, sy, sx, M1, T1, M2, s, h->lc, bl.ext0, bl.Hl);
-        launch_spline(gV, vn, my, sy, sx, M1b, T1b, M2b, h->s_aux, h->lc, bl.ext0, bl.Hl);
+        bool ok = true;
+        if (h->spline_variant == 0) {
+          ImgD M1 = viewd(ws.M1, pl.Hl, pl.Wl), T1 = viewd(ws.T1, rows, pl.Wl), M2 = viewd(ws.M2, rows, pl.Wl);
+          ImgD M1b = viewd(ws.M1b, pl.Hl, pl.Wl), T1b = viewd(ws.T1b, rows, pl.Wl), M2b = viewd(ws.M2b, rows, pl.Wl);
+          launch_spline_seq(gU, un, mx, sy, sx, M1, T1, M2, s, h->lc, bl.ext0, bl.Hl);
+          launch_spline_seq(gV, vn, my, sy, sx, M1b, T1b, M2b, h->s_aux, h->lc, bl.ext0, bl.Hl);
+        } else {
+          ImgD M1 = viewd(ws.M1, S1 - S0, pl.Wl), D1 = viewd(ws.T1, S1 - S0, pl.Wl);
+          ImgD M1b = viewd(ws.M1b, S1 - S0, pl.Wl), D1b = viewd(ws.T1b, S1 - S0, pl.Wl);
+          ok = launch_spline(gU, un, mx, sy, sx, M1, D1, s, h->lc, S0, pl.Hl, bl.ext0, bl.Hl) &&
+               launch_spline(gV, vn, my, sy, sx, M1b, D1b, h->s_aux, h->lc, S0, pl.Hl, bl.ext0, bl.Hl);
+        }
         cudaEventRecord(h->ev_join, h->s_aux);
         cudaStreamWaitEvent(s, h->ev_join, 0);
+        if (!ok) return fail(h, OFRI_ERR_INVALID, "spline up-sample: the coarse strip does not cover the band");
       }
       {
         Timed t(h, "warp");
@@ -1228,6 +1278,7 @@ static int* option_slot(ofri_handle h, const char* key) {
   if (!strcmp(key, "hs_fuse_fast")) return &h->hs_fuse_fast;
   if (!strcmp(key, "band_exchange")) return &h->band_exchange;
   if (!strcmp(key, "band_reach")) return &h->band_reach;
+  if (!strcmp(key, "spline_variant")) return &h->spline_variant;
   return nullptr;
 }
 int ofri_set_option(ofri_handle h, const char* key, int value) {
@@ -1480,16 +1531,20 @@ int ofri_spline_upsample(ofri_handle h, const float* in, int batch, int in_h, in
   if (!in || !out || out_h < 1 || out_w < 1) return fail(h, OFRI_ERR_INVALID, "bad spline arguments");
   if (in_h < 4 || in_w < 4) return fail(h, OFRI_ERR_TOO_SMALL, "the cubic spline needs >= 4 samples per axis");
   size_t need = sizeof(float) * ((size_t)round_up(in_w, 4) * in_h + (size_t)round_up(out_w, 4) * out_h) * batch +
-                sizeof(double) * ((size_t)in_h * in_w + 2 * (size_t)out_h * in_w) * batch + 8192;
+                sizeof(double) * ((size_t)in_h * in_w + 2 * (size_t)(out_h > in_h ? out_h : in_h) * in_w) * batch + 8192;
   int rc = arena_reserve(h, need);
   if (rc) return rc;
   Bump b(h->arena, h->arena_cap, false);
   Img i = b.plane(batch, in_h, in_w), o = b.plane(batch, out_h, out_w);
-  ImgD M1 = b.planed(batch, in_h, in_w), T1 = b.planed(batch, out_h, in_w), M2 = b.planed(batch, out_h, in_w);
+  const int th = out_h > in_h ? out_h : in_h;
+  ImgD M1 = b.planed(batch, in_h, in_w), T1 = b.planed(batch, th, in_w), M2 = b.planed(batch, th, in_w);
   SplineSys sy, sx;
   if ((rc = get_spline_sys(h, in_h, &sy)) || (rc = get_spline_sys(h, in_w, &sx))) return rc;
   if ((rc = upload(h, i, in))) return rc;
-  launch_spline(i, o, mul, sy, sx, M1, T1, M2, h->stream, h->lc);
+  if (h->spline_variant == 0)
+    launch_spline_seq(i, o, mul, sy, sx, M1, viewd(T1, out_h, in_w), viewd(M2, out_h, in_w), h->stream, h->lc);
+  else if (!launch_spline(i, o, mul, sy, sx, M1, viewd(T1, in_h, in_w), h->stream, h->lc))
+    return fail(h, OFRI_ERR_CUDA, "spline up-sample launch failed");
   if ((rc = download(h, out, o))) return rc;
   return finish(h);
 }

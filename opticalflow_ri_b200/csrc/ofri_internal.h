@@ -5,6 +5,7 @@
 #include <functional>
 #include <string>
 #include "../../include/ofri.h"
+#include "ofri_spline.cuh"
 
 namespace ofri {
 
@@ -41,14 +42,7 @@ struct ResizeTaps {
   int in_size = 0, out_size = 0;
 };
 // Thomas-algorithm constants of the not-a-knot system for n samples (device pointers, m = n-2 entries)
-struct SplineSys {
-  const double* lo = nullptr;
-  const double* cp = nullptr;
-  const double* den = nullptr;
-  int n = 0;
-  int conv = 0;              // rows [conv, n-3) of the reduced system share (den_c, cp_c) and lo == 1
-  double den_c = 0.0, cp_c = 0.0, rcp_c = 0.0;   // rcp_c = RN(1 / den_c)
-};
+typedef SplineSysView SplineSys;
 
 struct LaunchCounter { int64_t n = 0; };
 
@@ -82,11 +76,22 @@ void launch_gauss(const Img& in, const Img& tmp, const Img& out, const GaussTaps
 // always the tap table of the WHOLE image)
 void launch_resize(const Img& in, const Img& tmp, const Img& out, const ResizeTaps& tx, const ResizeTaps& ty,
                    cudaStream_t s, LaunchCounter& lc, int in_row0 = 0, int out_row0 = 0);
-// up-sample `in` (h x w) to `out` (H x W) and multiply by mul; scratch: M1 (h x w), T1 (H x w), M2 (H x w) f64
-// band form: `out` (and T1, M2) hold rows [row0, row0 + out.H) of the Hg-row result; `in` is always the whole coarse plane
-void launch_spline(const Img& in, const Img& out, float mul, const SplineSys& sy, const SplineSys& sx,
-                   const ImgD& M1, const ImgD& T1, const ImgD& M2, cudaStream_t s, LaunchCounter& lc, int row0 = 0,
+// up-sample `in` (h x w) to `out` (H x W) and multiply by mul.
+// Strip form (row bands): `in` holds rows [in_row0, in_row0 + in.H) of the hg-row coarse plane, `out` rows
+// [row0, row0 + out.H) of the Hg-row result; in_row0 = row0 = 0, hg = in.H, Hg = out.H is the whole-image case.
+// f64 scratch: M1 and D1 at least in.H x in.W (same strip indexing as `in`).  Chunk-parallel windowed solves
+// (ofri_spline.cuh) + one fused kernel per output row (axis-0 evaluation, axis-1 solve and evaluation in shared
+// memory).  Returns false if `in` does not cover the rows the requested output rows need (spline_rows_needed).
+bool launch_spline(const Img& in, const Img& out, float mul, const SplineSys& sy, const SplineSys& sx, const ImgD& M1,
+                   const ImgD& D1, cudaStream_t s, LaunchCounter& lc, int in_row0 = 0, int hg = 0, int row0 = 0,
                    int Hg = 0);
+// coarse rows [*lo, *hi) a strip must hold for output rows [row0, row0 + rows) of Hg (coarse plane: hg rows, system sy)
+void spline_rows_needed(int row0, int rows, int hg, int Hg, const SplineSys& sy, int* lo, int* hi);
+// previous generation: one thread per line, sequential full-length solves (whole coarse plane only; kept as the A/B
+// reference of the tests).  Scratch: M1 (h x w), T1 (H x w), M2 (H x w) f64.
+void launch_spline_seq(const Img& in, const Img& out, float mul, const SplineSys& sy, const SplineSys& sx,
+                       const ImgD& M1, const ImgD& T1, const ImgD& M2, cudaStream_t s, LaunchCounter& lc, int row0 = 0,
+                       int Hg = 0);
 // band form: us / vs / out hold rows [row0, ..) and im1 / im2 rows [img_row0, ..) of an image of Hg rows
 void launch_warp_pair(const Img& im1, const Img& im2, const Img& us, const Img& vs, const Img& out1, const Img& out2,
                       cudaStream_t s, LaunchCounter& lc, int row0 = 0, int img_row0 = 0, int Hg = 0);

@@ -107,16 +107,26 @@ OFRI_HD void spline_locate(int k, int n, int N, double rN, int* i_out, double* s
 OFRI_HD void spline_locate(int k, int n, int N, int* i_out, double* s_out) {
   spline_locate(k, n, N, ddiv(1.0, (double)N), i_out, s_out);
 }
-OFRI_HD double spline_eval(double yi, double yj, double Mi, double Mj, double s) {
+// the part of the evaluation that depends on the position only (shared by all samples of one output row / column)
+struct SplinePos { double s, t, s3, t3; };
+OFRI_HD SplinePos spline_pos(double s) {
+  SplinePos p;
+  p.s = s;
+  p.t = dsub(1.0, s);
+  p.t3 = dmul(dmul(p.t, p.t), p.t);
+  p.s3 = dmul(dmul(s, s), s);
+  return p;
+}
+OFRI_HD double spline_eval_at(double yi, double yj, double Mi, double Mj, const SplinePos& p) {
   const double r6 = 0.16666666666666666;      // RN(1/6)
-  double t = dsub(1.0, s);
-  double t3 = dmul(dmul(t, t), t);
-  double s3 = dmul(dmul(s, s), s);
-  double a = ddiv_const(dmul(Mi, t3), 6.0, r6);
-  double b = ddiv_const(dmul(Mj, s3), 6.0, r6);
-  double c = dmul(dsub(yi, ddiv_const(Mi, 6.0, r6)), t);
-  double d = dmul(dsub(yj, ddiv_const(Mj, 6.0, r6)), s);
+  double a = ddiv_const(dmul(Mi, p.t3), 6.0, r6);
+  double b = ddiv_const(dmul(Mj, p.s3), 6.0, r6);
+  double c = dmul(dsub(yi, ddiv_const(Mi, 6.0, r6)), p.t);
+  double d = dmul(dsub(yj, ddiv_const(Mj, 6.0, r6)), p.s);
   return dadd(dadd(dadd(a, b), c), d);
+}
+OFRI_HD double spline_eval(double yi, double yj, double Mi, double Mj, double s) {
+  return spline_eval_at(yi, yj, Mi, Mj, spline_pos(s));
 }
 
 // ---- bilinear warp (GenericPyramidalOpticalFlow.py:70-116) --------------------------------------------------

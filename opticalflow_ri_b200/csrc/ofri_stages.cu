@@ -4,6 +4,7 @@
 // for coalesced access (threads along x) and exact reproduction of the reference arithmetic (ofri_pixel.cuh).
 #include "ofri_internal.h"
 #include "ofri_pixel.cuh"
+#include "ofri_spline.cuh"
 
 namespace ofri {
 
@@ -274,8 +275,8 @@ __global__ void spline_eval1_kernel(ImgD T1, ImgD M2, Img out, float mul, int ap
   if (apply_mul) r = fmul(r, mul);
   out.p[(long)b * out.stride + (long)k * out.pitch + l] = r;
 }
-void launch_spline(const Img& in, const Img& out, float mul, const SplineSys& sy, const SplineSys& sx, const ImgD& M1,
-                   const ImgD& T1, const ImgD& M2, cudaStream_t s, LaunchCounter& lc, int row0, int Hg) {
+void launch_spline_seq(const Img& in, const Img& out, float mul, const SplineSys& sy, const SplineSys& sx, const ImgD& M1,
+                       const ImgD& T1, const ImgD& M2, cudaStream_t s, LaunchCounter& lc, int row0, int Hg) {
   const int h = in.H, w = in.W, H = out.H;
   if (Hg <= 0) Hg = H;
   // axis 0: one thread per column
@@ -294,6 +295,207 @@ void launch_spline(const Img& in, const Img& out, float mul, const SplineSys& sy
                                                                           1.0 / (double)out.W);
   }
   lc.n += 4;
+}
+
+// ---- chunk-parallel / windowed generation (ofri_spline.cuh) ----------------------------------------------------------
+// Axis 0 (across rows; one thread per column and chunk, coalesced along x).  `in`, D and M are STRIPS: local row r is
+// row A + r of the hg-row coarse plane.  Pass 1 -> D (forward elimination, own rows of every chunk of [RA, RF]);
+// passes 2 + 3 -> M (back substitution; chunks that hold wanted rows only).  Two launches = the grid-wide barrier
+// between "every chunk has stored its dp" and "a chunk reads the dp of the chunks behind it".
+__global__ void spline_cols_fwd_kernel(Img in, ImgD D, int A, int hg, SplineSys sys, SplineWindow wy, int C) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= in.W) return;
+  const SplineChunk k = spline_chunk(wy, blockIdx.y, C, sys.conv, kSplineWarm);
+  const float* yp = in.p + (long)blockIdx.z * in.stride + x - (long)A * in.pitch;
+  double* dp = D.p + (long)blockIdx.z * D.stride + x - (long)A * D.pitch;
+  const long yq = in.pitch, dq = D.pitch;
+  spline_chunk_forward(k, hg - 2, sys, [&](int e) { return (double)__ldg(yp + (long)e * yq); },
+                       [&](int e) -> double& { return dp[(long)e * dq]; });
+}
+__global__ void spline_cols_bwd_kernel(ImgD D, ImgD M, int A, int hg, SplineSys sys, SplineWindow wy, int C) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= M.W) return;
+  const SplineChunk k = spline_chunk(wy, blockIdx.y, C, sys.conv, kSplineWarm);
+  if (k.ra > wy.RB) return;
+  const double* dp = D.p + (long)blockIdx.z * D.stride + x - (long)A * D.pitch;
+  double* mp = M.p + (long)blockIdx.z * M.stride + x - (long)A * M.pitch;
+  const long dq = D.pitch, mq = M.pitch;
+  auto Dr = [&](int e) { return dp[(long)e * dq]; };
+  const double next = spline_chunk_tail(k, wy, hg - 2, kSplineWarm, sys, Dr);
+  spline_chunk_back(k, hg, sys, next, Dr, [&](int e) -> double& { return mp[(long)e * mq]; });
+}
+
+// Axis 0 evaluation + axis 1 solve + axis 1 evaluation of RPB output rows (x segment `blockIdx.x`) in ONE block:
+//   phase 0  T[r][e] = axis-0 spline of column e at output row k (all threads, coalesced along e) -> shared
+//   phase 1  forward elimination, one thread per (row, chunk) of the segment's window
+//   phase 2  back substitution through the rows behind each chunk (read only)      } block barriers in between
+//   phase 3  back substitution of each chunk's own rows, in place                   }
+//   phase 4  out[k][l] for the segment's output columns (all threads, coalesced along l)
+// so the f64 intermediates (T1, M2 of the previous generation: 16 B per coarse column and output row each way) never
+// touch HBM.  Chunks are an odd number of doubles apart -> conflict-free shared-memory access in the solve phases.
+struct SplineRowsArgs {
+  int A, hg;            // coarse strip origin / coarse plane height
+  int row0, Hg;         // output strip origin / output plane height
+  double rHg, rW;       // RN(1 / Hg), RN(1 / out.W)
+  float mul;
+  int apply_mul;
+  int seg_len, nseg;    // knot intervals per x segment
+  int C, rpb;           // chunk size (odd), rows per block
+  int ne_max;           // doubles per row and array in shared memory
+  int small_ix;         // out.W * in.W < 2^31: 32-bit index arithmetic in spline_locate
+};
+__device__ __forceinline__ void spline_locate_dev(int k, int n, int N, double rN, int small, int* i_out, double* s_out) {
+  if (small) {
+    const unsigned num = (unsigned)k * (unsigned)n;
+    unsigned i = num / (unsigned)N;
+    double s = ddiv_const((double)(num - i * (unsigned)N), (double)N, rN);
+    if ((int)i >= n - 1) { i = n - 2; s = 1.0; }
+    *i_out = (int)i;
+    *s_out = s;
+  } else {
+    spline_locate(k, n, N, rN, i_out, s_out);
+  }
+}
+template <int NT>
+__global__ void __launch_bounds__(NT) spline_rows_kernel(Img in, ImgD M1, Img out, SplineSys sx, SplineRowsArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, b = blockIdx.z;
+  const int w = in.W, m = w - 2;
+  const int k0 = blockIdx.y * a.rpb;                                    // first local output row of this block
+  const int nrows = min(a.rpb, out.H - k0);
+  // segment -> wanted unknowns [xa, xb] -> window
+  const int xa = blockIdx.x * a.seg_len;
+  const bool last_seg = blockIdx.x == a.nseg - 1;
+  const int xb = last_seg ? w - 1 : xa + a.seg_len;
+  const SplineWindow wx = spline_window(xa, xb, w, sx.conv, kSplineWarm);
+  const int E0 = wx.FS, ne = wx.RF + 2 - wx.FS + 1;                     // elements E0 .. E0 + ne - 1 are staged
+  double* ysm = sm;
+  double* msm = sm + (size_t)a.rpb * a.ne_max;
+  const float* ip = in.p + (long)b * in.stride;
+  const double* m1 = M1.p + (long)b * M1.stride;
+  // ---- phase 0 ------------------------------------------------------------------------------------------------------
+  for (int r = 0; r < nrows; ++r) {
+    int i;
+    double sfr;
+    spline_locate(k0 + r + a.row0, a.hg, a.Hg, a.rHg, &i, &sfr);
+    const SplinePos pos = spline_pos(sfr);
+    const float* y0 = ip + (long)(i - a.A) * in.pitch;
+    const float* y1 = y0 + in.pitch;
+    const double* q0 = m1 + (long)(i - a.A) * M1.pitch;
+    const double* q1 = q0 + M1.pitch;
+    double* dst = ysm + (size_t)r * a.ne_max;
+    for (int e = tid; e < ne; e += NT)
+      dst[e] = spline_eval_at((double)__ldg(y0 + E0 + e), (double)__ldg(y1 + E0 + e), __ldg(q0 + E0 + e),
+                              __ldg(q1 + E0 + e), pos);
+  }
+  __syncthreads();
+  // ---- phases 1-3 ---------------------------------------------------------------------------------------------------
+  const int nch = spline_num_chunks(wx, a.C);
+  const int r = tid / nch, c = tid - r * nch;
+  const bool solver = r < nrows;
+  SplineChunk k;
+  double* yr = ysm + (size_t)r * a.ne_max - E0;
+  double* mr = msm + (size_t)r * a.ne_max - E0;
+  auto D = [&](int e) -> double& { return mr[e]; };
+  if (solver) {
+    k = spline_chunk(wx, c, a.C, sx.conv, kSplineWarm);
+    spline_chunk_forward(k, m, sx, [&](int e) { return yr[e]; }, D);
+  }
+  __syncthreads();
+  double next = 0.0;
+  const bool wanted = solver && k.ra <= wx.RB;
+  if (wanted) next = spline_chunk_tail(k, wx, m, kSplineWarm, sx, D);
+  __syncthreads();
+  if (wanted) spline_chunk_back(k, w, sx, next, D, D);
+  __syncthreads();
+  // ---- phase 4 ------------------------------------------------------------------------------------------------------
+  const long W = out.W;
+  const int l0 = (int)(((long)xa * W + w - 1) / w);
+  const int l1 = last_seg ? (int)W : (int)(((long)xb * W + w - 1) / w);
+  for (int rr = 0; rr < nrows; ++rr) {
+    const double* tp = ysm + (size_t)rr * a.ne_max - E0;
+    const double* mp = msm + (size_t)rr * a.ne_max - E0;
+    float* op = out.p + (long)b * out.stride + (long)(k0 + rr) * out.pitch;
+    for (int l = l0 + tid; l < l1; l += NT) {
+      int i;
+      double sfr;
+      spline_locate_dev(l, w, (int)W, a.rW, a.small_ix, &i, &sfr);
+      float v = (float)spline_eval(tp[i], tp[i + 1], mp[i], mp[i + 1], sfr);
+      if (a.apply_mul) v = fmul(v, a.mul);
+      op[l] = v;
+    }
+  }
+}
+
+void spline_rows_needed(int row0, int rows, int hg, int Hg, const SplineSys& sy, int* lo, int* hi) {
+  int ia, ib;
+  double sfr;
+  spline_locate(row0, hg, Hg, &ia, &sfr);
+  spline_locate(row0 + rows - 1, hg, Hg, &ib, &sfr);
+  const SplineWindow wy = spline_window(ia, ib + 1, hg, sy.conv, kSplineWarm);
+  *lo = wy.FS;
+  *hi = wy.RF + 3;
+}
+
+bool launch_spline(const Img& in, const Img& out, float mul, const SplineSys& sy, const SplineSys& sx, const ImgD& M1,
+                   const ImgD& D1, cudaStream_t s, LaunchCounter& lc, int in_row0, int hg, int row0, int Hg) {
+  if (hg <= 0) hg = in.H;
+  if (Hg <= 0) Hg = out.H;
+  const int w = in.W, A = in_row0;
+  // ---- axis 0: unknowns M1[ia .. ib + 1] of every column -----------------------------------------------------------
+  int ia, ib;
+  double sfr;
+  spline_locate(row0, hg, Hg, &ia, &sfr);
+  spline_locate(row0 + out.H - 1, hg, Hg, &ib, &sfr);
+  const SplineWindow wy = spline_window(ia, ib + 1, hg, sy.conv, kSplineWarm);
+  if (wy.FS < A || wy.RF + 2 > A + in.H - 1) return false;
+  if (M1.H < in.H || D1.H < in.H || M1.W < w || D1.W < w) return false;
+  {
+    const int range = wy.RF - wy.RA + 1;
+    long want = 300000L / ((long)w * in.batch);                 // ~2 threads per lane of the GPU
+    if (want < 1) want = 1;
+    if (want > range / 32) want = range / 32 > 0 ? range / 32 : 1;
+    int C = (int)((range + want - 1) / want);
+    if (C < 2) C = 2;
+    const int nch = spline_num_chunks(wy, C);
+    dim3 b(128), g((w + 127) / 128, nch, in.batch);
+    spline_cols_fwd_kernel<<<g, b, 0, s>>>(in, D1, A, hg, sy, wy, C);
+    spline_cols_bwd_kernel<<<g, b, 0, s>>>(D1, M1, A, hg, sy, wy, C);
+  }
+  // ---- axes 0 (evaluation) + 1, fused per output row ------------------------------------------------------------------
+  {
+    constexpr int NT = 256;
+    constexpr int MAXE = 13312;                                   // doubles per row and array: 2 x 104 KB
+    SplineRowsArgs a;
+    a.A = A; a.hg = hg; a.row0 = row0; a.Hg = Hg;
+    a.rHg = 1.0 / (double)Hg;
+    a.rW = 1.0 / (double)out.W;
+    a.mul = mul;
+    a.apply_mul = mul != 1.0f ? 1 : 0;
+    a.small_ix = (long)out.W * (long)w < 0x7fffffffL ? 1 : 0;
+    const int margin = 2 * kSplineWarm + 4;
+    a.nseg = w <= MAXE ? 1 : (w + (MAXE - margin) - 1) / (MAXE - margin);
+    a.seg_len = a.nseg == 1 ? w : (w + a.nseg - 1) / a.nseg;
+    const int ne = a.nseg == 1 ? w : a.seg_len + margin;
+    a.ne_max = ne | 1;                                            // odd row pitch
+    int rpb = (int)(65536 / ((long)a.ne_max * 16));
+    a.rpb = rpb < 1 ? 1 : (rpb > 8 ? 8 : rpb);
+    const int range = a.nseg == 1 ? w - 2 : a.seg_len + kSplineWarm + 1;
+    const int per_row = NT / a.rpb;                               // solver threads per row
+    int C = (range + per_row - 1) / per_row;
+    if (C < 9) C = 9;
+    a.C = C | 1;
+    const size_t smem = (size_t)2 * a.rpb * a.ne_max * sizeof(double);
+    if (cudaFuncSetAttribute(spline_rows_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    dim3 g(a.nseg, (out.H + a.rpb - 1) / a.rpb, in.batch);
+    spline_rows_kernel<NT><<<g, NT, smem, s>>>(in, M1, out, sx, a);
+  }
+  lc.n += 3;
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

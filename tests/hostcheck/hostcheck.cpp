@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../opticalflow_ri_b200/csrc/ofri_pixel.cuh"
 #include "../../opticalflow_ri_b200/csrc/ofri_tables.h"
+#include "../../opticalflow_ri_b200/csrc/ofri_spline.cuh"
 
 using namespace ofri;
 
@@ -35,7 +36,77 @@ static void solve_line(const T* y, long ye, double* M, long me, int n, const Hos
   M[0] = dsub(dmul(2.0, M[me]), M[2 * me]);
   M[(long)(n - 1) * me] = dsub(dmul(2.0, M[(long)(n - 2) * me]), M[(long)(n - 3) * me]);
 }
+// mirrors the chunk-parallel kernels (spline_cols_fwd/bwd_kernel, spline_rows_kernel): the unknowns M[a .. b] of one
+// line by windowed chunks of C rows (ofri_spline.cuh); D = forward-elimination scratch, same indexing as M
+static SplineSysView sys_view(const HostSplineSys& s, int n) {
+  SplineSysView v;
+  const int m = n - 2;
+  v.lo = s.lo.data(); v.cp = s.cp.data(); v.den = s.den.data();
+  v.n = n; v.conv = s.conv;
+  v.den_c = s.den[s.conv < m ? s.conv : m - 1];
+  v.cp_c = s.cp[s.conv < m ? s.conv : m - 1];
+  v.rcp_c = 1.0 / v.den_c;
+  return v;
+}
+template <typename T>
+static void solve_line_win(const T* y, long ye, double* D, double* M, long me, int n, int a, int b, int C, int Wm,
+                           const SplineSysView& sv) {
+  const int m = n - 2;
+  const SplineWindow w = spline_window(a, b, n, sv.conv, Wm);
+  const int nch = spline_num_chunks(w, C);
+  for (int c = 0; c < nch; ++c) {
+    SplineChunk k = spline_chunk(w, c, C, sv.conv, Wm);
+    spline_chunk_forward(k, m, sv, [&](int e) { return (double)y[(long)e * ye]; },
+                         [&](int e) -> double& { return D[(long)e * me]; });
+  }
+  for (int c = 0; c < nch; ++c) {
+    SplineChunk k = spline_chunk(w, c, C, sv.conv, Wm);
+    if (k.ra > w.RB) continue;
+    auto Dr = [&](int e) { return D[(long)e * me]; };
+    double next = spline_chunk_tail(k, w, m, Wm, sv, Dr);
+    spline_chunk_back(k, n, sv, next, Dr, [&](int e) -> double& { return M[(long)e * me]; });
+  }
+}
+
 extern "C" {
+
+// full-line sequential solve and windowed / chunked solve of the unknowns [a, b] (others left untouched), f64 in/out
+void hc_spline_line(const double* y, int n, double* M) {
+  HostSplineSys s = build_spline_sys(n);
+  solve_line<double>(y, 1, M, 1, n, s);
+}
+void hc_spline_line_win(const double* y, int n, int a, int b, int C, int Wm, double* M) {
+  HostSplineSys s = build_spline_sys(n);
+  std::vector<double> D(n, 0.0);
+  solve_line_win<double>(y, 1, D.data(), M, 1, n, a, b, C, Wm, sys_view(s, n));
+}
+// rows [row0, row0 + rows) of the up-sampled plane by the windowed algorithm (what a row band computes)
+void hc_spline_win(const float* in, int h, int w, int H, int W, float mul, int row0, int rows, int Cy, int Cx, int Wm,
+                   float* out) {
+  HostSplineSys sy = build_spline_sys(h), sx = build_spline_sys(w);
+  const SplineSysView vy = sys_view(sy, h), vx = sys_view(sx, w);
+  int ia, ib;
+  double sf;
+  spline_locate(row0, h, H, &ia, &sf);
+  spline_locate(row0 + rows - 1, h, H, &ib, &sf);
+  std::vector<double> M1((size_t)h * w, NAN), D1((size_t)h * w, NAN), T(w), D2(w), M2(w);
+  for (int x = 0; x < w; ++x) solve_line_win<float>(in + x, w, D1.data() + x, M1.data() + x, w, h, ia, ib + 1, Cy, Wm, vy);
+  for (int k = 0; k < rows; ++k) {
+    int i; double s;
+    spline_locate(k + row0, h, H, &i, &s);
+    const SplinePos pos = spline_pos(s);
+    for (int x = 0; x < w; ++x)
+      T[x] = spline_eval_at((double)in[(size_t)i * w + x], (double)in[(size_t)(i + 1) * w + x], M1[(size_t)i * w + x],
+                            M1[(size_t)(i + 1) * w + x], pos);
+    solve_line_win<double>(T.data(), 1, D2.data(), M2.data(), 1, w, 0, w - 1, Cx, Wm, vx);
+    for (int l = 0; l < W; ++l) {
+      spline_locate(l, w, W, &i, &s);
+      float r = (float)spline_eval(T[i], T[i + 1], M2[i], M2[i + 1], s);
+      if (mul != 1.0f) r = fmul(r, mul);
+      out[(size_t)k * W + l] = r;
+    }
+  }
+}
 
 void hc_gauss(const float* in, int H, int W, const float* taps, int K, float* out) {
   std::vector<float> tmp((size_t)H * W);

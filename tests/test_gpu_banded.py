@@ -52,6 +52,28 @@ def test_band_invariance_local(ofri, case, nb, shape):
     same(V, Vref, "V %s nb=%d" % (case, nb))
 
 
+@pytest.mark.parametrize("nb,shape", [(2, (640, 136)), (4, (1536, 72))])
+def test_band_spline_halo_path(ofri, nb, shape):
+    """Bands thick enough (coarse rows per band >= the 73-row spline halo) take the windowed column solve fed by a halo
+    exchange instead of the all-gather of the coarse flow; the result must still equal the single-band one bit for bit,
+    and the all-gather fall-back (spline_variant 0) as well."""
+    from opticalflow_ri_b200 import banded
+    H, W = shape
+    I0, I1 = O.synthetic_piv_pair(H, W, seed=5)
+    mk = lambda: CASES["ex3"](ofri)
+    h = ofri.Handle(0)
+    try:
+        Uref, Vref = h.pyramidal_flow(I0, I1, mk())
+    finally:
+        h.close()
+    U, V = banded.flow_banded_local(I0, I1, mk, nb)
+    same(U, Uref, "U halo nb=%d" % nb)
+    same(V, Vref, "V halo nb=%d" % nb)
+    U, V = banded.flow_banded_local(I0, I1, mk, nb, options={"spline_variant": 0})
+    same(U, Uref, "U all-gather nb=%d" % nb)
+    same(V, Vref, "V all-gather nb=%d" % nb)
+
+
 def test_band_plan_and_errors(ofri):
     h = ofri.Handle(0)
     try:

@@ -76,6 +76,38 @@ def test_spline_and_warp(hc, stages, tag, sc):
     assert np.array_equal(o1, stages["up_w1" + s + tag]) and np.array_equal(o2, stages["up_w2" + s + tag])
 
 
+def test_spline_windowed_line_is_bit_identical(hc):
+    """The chunk-parallel / windowed Thomas solve (ofri_spline.cuh: 48-row warm-up of both recurrences) reproduces the
+    sequential full-line solve bit for bit in float64 -- every chunk size, whole lines and interior windows."""
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(0)
+    for n in (4, 5, 7, 17, 64, 257, 1000):
+        y = np.cumsum(rng.normal(size=n)) * 10.0 ** float(rng.integers(-3, 3))
+        M = np.zeros(n)
+        hc.hc_spline_line(y.ctypes.data_as(dp), n, M.ctypes.data_as(dp))
+        for chunk in (2, 7, 33, 200):
+            for a, b in ((0, n - 1), (0, min(n - 1, 3)), (max(0, n - 3), n - 1), (n // 3, min(n - 1, n // 3 + n // 4))):
+                Mw = np.full(n, np.nan)
+                hc.hc_spline_line_win(y.ctypes.data_as(dp), n, a, b, chunk, 48, Mw.ctypes.data_as(dp))
+                assert np.array_equal(Mw[a:b + 1].view(np.uint64), M[a:b + 1].view(np.uint64)), (n, chunk, a, b)
+
+
+@pytest.mark.parametrize("shape", [(4, 4, 8, 8), (5, 7, 11, 13), (150, 200, 300, 400), (257, 130, 513, 259)])
+def test_spline_windowed_bands(hc, shape):
+    """Rows [row0, row0 + rows) of the up-sampled plane from the window of coarse rows a band holds == the same rows of
+    the whole-plane result (what the row-band mode relies on instead of an all-gather)."""
+    h, w, H, W = shape
+    rng = np.random.default_rng(1)
+    a = (rng.normal(size=(h, w)) * 3).astype(np.float32)
+    ref = np.empty((H, W), np.float32)
+    hc.hc_spline(p(a), h, w, H, W, C.c_float(2.0), p(ref))
+    for row0, rows in ((0, H), (0, min(H, 7)), (H // 3, H // 4 + 1), (max(H - 5, 0), min(5, H))):
+        for cy, cx in ((2, 9), (57, 33)):
+            out = np.empty((rows, W), np.float32)
+            hc.hc_spline_win(p(a), h, w, H, W, C.c_float(2.0), row0, rows, cy, cx, 48, p(out))
+            assert np.array_equal(out, ref[row0:row0 + rows]), (row0, rows, cy, cx)
+
+
 def test_warp_coords(hc, stages):
     i = f32(stages["warp_img"])
     o = np.empty_like(i)
