@@ -912,8 +912,12 @@ int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs
         if (!c || c->nranks == 1) return;
         cudaStreamWaitEvent(s, h->ev_c1, 0);
       };
+      // several ranks: a band's launches are short, so the fixed cost per launch (and per exchange / all-reduce) weighs
+      // more than on one GPU -- fuse 8 sweeps per fast-arithmetic launch unless configured otherwise
       int fuse = h->hs_fuse;
       if (!precise && h->hs_fuse_fast > 0 && E % h->hs_fuse_fast == 0) fuse = h->hs_fuse_fast;
+      else if (!precise && h->hs_fuse_fast == 0 && h->auto_fuse && c && c->nranks > 1 && fuse >= 1 && fuse < 8 && E % 8 == 0)
+        fuse = 8;
       res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], niter, fuse,
                               h->hs_variant, precise, s, h->lc, HsHook(), &split);
     }
@@ -944,7 +948,9 @@ int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs
     const int c0 = cur;
     // The ghost frame holds E valid rows after an exchange and every sweep spoils one more: refresh it only when the
     // next block would run out (the residual sums, in contrast, are needed by the very next launch's stopping rule).
-    const int Tl = h->ls_fuse > 4 ? 4 : (h->ls_fuse < 1 ? 1 : h->ls_fuse);
+    int ls_fuse = h->ls_fuse;
+    if (h->auto_fuse && c && c->nranks > 1 && ls_fuse >= 1 && ls_fuse < 4) ls_fuse = 4;   // half the launches / all-reduces
+    const int Tl = ls_fuse > 4 ? 4 : (ls_fuse < 1 ? 1 : ls_fuse);
     int spoiled = 0;
     LsHook hook = [&](int k0, int n, int written) {
       if (*comm_rc || !c || c->nranks == 1) return;
@@ -958,7 +964,7 @@ int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs
       if (written == 0 || written == 2) *comm_rc = band_exchange_uv(h, U[c0], V[c0], o0, o1, E);
       if (!*comm_rc && (written == 1 || written == 2)) *comm_rc = band_exchange_uv(h, U[c0 ^ 1], V[c0 ^ 1], o0, o1, E);
     };
-    launch_ls_solve(V[cur], U[cur], V[cur ^ 1], U[cur ^ 1], co, a.ls_h, a.ls_maxiter, a.ls_tol, h->ls_fuse, h->ls_variant,
+    launch_ls_solve(V[cur], U[cur], V[cur ^ 1], U[cur ^ 1], co, a.ls_h, a.ls_maxiter, a.ls_tol, ls_fuse, h->ls_variant,
                     ws.ls_errs, ws.ls_state, V[cur], U[cur], d_err, 1, nullptr, s, h->lc, &band, hook);
     if (!*comm_rc) *comm_rc = band_exchange_uv(h, U[cur], V[cur], o0, o1, E);    // ghosts of the selected final state
   }

@@ -125,6 +125,23 @@ OFRI_HD double spline_eval_at(double yi, double yj, double Mi, double Mj, const 
   double d = dmul(dsub(yj, ddiv_const(Mj, 6.0, r6)), p.s);
   return dadd(dadd(dadd(a, b), c), d);
 }
+// the same value with the position-independent quotients M/6 hoisted (one interval, several positions)
+struct SplineM6 { double i6, j6; };
+OFRI_HD SplineM6 spline_m6(double Mi, double Mj) {
+  const double r6 = 0.16666666666666666;
+  SplineM6 q;
+  q.i6 = ddiv_const(Mi, 6.0, r6);
+  q.j6 = ddiv_const(Mj, 6.0, r6);
+  return q;
+}
+OFRI_HD double spline_eval_m6(double yi, double yj, double Mi, double Mj, const SplineM6& q, const SplinePos& p) {
+  const double r6 = 0.16666666666666666;
+  double a = ddiv_const(dmul(Mi, p.t3), 6.0, r6);
+  double b = ddiv_const(dmul(Mj, p.s3), 6.0, r6);
+  double c = dmul(dsub(yi, q.i6), p.t);
+  double d = dmul(dsub(yj, q.j6), p.s);
+  return dadd(dadd(dadd(a, b), c), d);
+}
 OFRI_HD double spline_eval(double yi, double yj, double Mi, double Mj, double s) {
   return spline_eval_at(yi, yj, Mi, Mj, spline_pos(s));
 }

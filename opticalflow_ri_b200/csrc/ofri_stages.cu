@@ -379,14 +379,21 @@ __global__ void __launch_bounds__(NT) spline_rows_kernel(Img in, ImgD M1, Img ou
     double sfr;
     spline_locate(k0 + r + a.row0, a.hg, a.Hg, a.rHg, &i, &sfr);
     const SplinePos pos = spline_pos(sfr);
-    const float* y0 = ip + (long)(i - a.A) * in.pitch;
+    const float* y0 = ip + (long)(i - a.A) * in.pitch + E0;
     const float* y1 = y0 + in.pitch;
-    const double* q0 = m1 + (long)(i - a.A) * M1.pitch;
+    const double* q0 = m1 + (long)(i - a.A) * M1.pitch + E0;
     const double* q1 = q0 + M1.pitch;
     double* dst = ysm + (size_t)r * a.ne_max;
-    for (int e = tid; e < ne; e += NT)
-      dst[e] = spline_eval_at((double)__ldg(y0 + E0 + e), (double)__ldg(y1 + E0 + e), __ldg(q0 + E0 + e),
-                              __ldg(q1 + E0 + e), pos);
+    int e = tid;
+    for (; e + NT < ne; e += 2 * NT) {        // two independent samples per trip: their loads and chains interleave
+      const double ya = (double)__ldg(y0 + e), yb = (double)__ldg(y1 + e), ma = __ldg(q0 + e), mb = __ldg(q1 + e);
+      const double yc = (double)__ldg(y0 + e + NT), yd = (double)__ldg(y1 + e + NT), mc = __ldg(q0 + e + NT),
+                   md = __ldg(q1 + e + NT);
+      dst[e] = spline_eval_at(ya, yb, ma, mb, pos);
+      dst[e + NT] = spline_eval_at(yc, yd, mc, md, pos);
+    }
+    if (e < ne)
+      dst[e] = spline_eval_at((double)__ldg(y0 + e), (double)__ldg(y1 + e), __ldg(q0 + e), __ldg(q1 + e), pos);
   }
   __syncthreads();
   // ---- phases 1-3 ---------------------------------------------------------------------------------------------------
@@ -408,21 +415,27 @@ __global__ void __launch_bounds__(NT) spline_rows_kernel(Img in, ImgD M1, Img ou
   __syncthreads();
   if (wanted) spline_chunk_back(k, w, sx, next, D, D);
   __syncthreads();
-  // ---- phase 4 ------------------------------------------------------------------------------------------------------
+  // ---- phase 4: one thread per knot interval i; its outputs l in [ceil(i W / w), ceil((i+1) W / w)) (two at 2:1) share
+  // the interval's samples and the position-independent quotients M/6 ------------------------------------------------
   const long W = out.W;
-  const int l0 = (int)(((long)xa * W + w - 1) / w);
-  const int l1 = last_seg ? (int)W : (int)(((long)xb * W + w - 1) / w);
+  const int i_end = last_seg ? w - 1 : xb;                                 // intervals xa .. i_end - 1
   for (int rr = 0; rr < nrows; ++rr) {
     const double* tp = ysm + (size_t)rr * a.ne_max - E0;
     const double* mp = msm + (size_t)rr * a.ne_max - E0;
     float* op = out.p + (long)b * out.stride + (long)(k0 + rr) * out.pitch;
-    for (int l = l0 + tid; l < l1; l += NT) {
-      int i;
-      double sfr;
-      spline_locate_dev(l, w, (int)W, a.rW, a.small_ix, &i, &sfr);
-      float v = (float)spline_eval(tp[i], tp[i + 1], mp[i], mp[i + 1], sfr);
-      if (a.apply_mul) v = fmul(v, a.mul);
-      op[l] = v;
+    for (int i = xa + tid; i < i_end; i += NT) {
+      const double yi = tp[i], yj = tp[i + 1], Mi = mp[i], Mj = mp[i + 1];
+      const SplineM6 q = spline_m6(Mi, Mj);
+      const int la = (int)(((long)i * W + w - 1) / w);
+      const int lb = i == w - 2 ? (int)W : (int)(((long)(i + 1) * W + w - 1) / w);
+      for (int l = la; l < lb; ++l) {
+        int il;
+        double sfr;
+        spline_locate_dev(l, w, (int)W, a.rW, a.small_ix, &il, &sfr);        // il == i
+        float v = (float)spline_eval_m6(yi, yj, Mi, Mj, q, spline_pos(sfr));
+        if (a.apply_mul) v = fmul(v, a.mul);
+        op[l] = v;
+      }
     }
   }
 }
@@ -465,7 +478,7 @@ bool launch_spline(const Img& in, const Img& out, float mul, const SplineSys& sy
   // ---- axes 0 (evaluation) + 1, fused per output row ------------------------------------------------------------------
   {
     constexpr int NT = 256;
-    constexpr int MAXE = 13312;                                   // doubles per row and array: 2 x 104 KB
+    constexpr int MAXE = 4352;                                    // doubles per row and array: 2 x 34 KB -> 3 blocks / SM
     SplineRowsArgs a;
     a.A = A; a.hg = hg; a.row0 = row0; a.Hg = Hg;
     a.rHg = 1.0 / (double)Hg;
