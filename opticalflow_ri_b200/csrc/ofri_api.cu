@@ -57,6 +57,7 @@ struct ofri_ctx {
   int auto_fuse = 1;        // deeper fusion for launches that cannot fill the GPU (see eff_hs_fuse)
   int band_exchange = 32;   // Horn-Schunck sweeps between two ghost-row exchanges (rounded up to a multiple of hs_fuse)
   int band_reach = 8;       // rows the warp may reach beyond a band's ghost frame (>= max |v| / 2 + 2)
+  int band_reserve_sms = 8; // SMs an interior Horn-Schunck launch leaves free for the ghost-row exchange beside it (NCCL kernels)
   int spline_variant = 1;   // 1 = chunk-parallel windowed solves + fused row kernel, 0 = sequential line solves (A/B)
   // timings of the last call
   std::vector<StageTime> times;
@@ -900,6 +901,7 @@ int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs
       split.every = E;
       split.mid_lo = o0 + E;
       split.mid_hi = o1 - E;
+      split.reserve_sms = (c && c->nranks > 1 && c->uses_sms()) ? h->band_reserve_sms : 0;
       split.begin = [&](int which) {
         if (*comm_rc || !c || c->nranks == 1) return;
         const int b = which ? (c0 ^ 1) : c0;
@@ -1285,6 +1287,7 @@ static int* option_slot(ofri_handle h, const char* key) {
   if (!strcmp(key, "band_exchange")) return &h->band_exchange;
   if (!strcmp(key, "band_reach")) return &h->band_reach;
   if (!strcmp(key, "spline_variant")) return &h->spline_variant;
+  if (!strcmp(key, "band_reserve_sms")) return &h->band_reserve_sms;
   return nullptr;
 }
 int ofri_set_option(ofri_handle h, const char* key, int value) {

@@ -113,6 +113,7 @@ struct NcclComm : Comm {
     return check(a->AllGather(send, recv, count, kNcclFloat32, comm, s), "ncclAllGather");
   }
   const char* error() const override { return err.c_str(); }
+  bool uses_sms() const override { return true; }
 };
 }  // namespace
 

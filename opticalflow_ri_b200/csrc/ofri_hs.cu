@@ -636,7 +636,7 @@ int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb
       if (block_end) {
         // boundary tiles first, then the exchange of the freshly written buffer starts (other stream) while the
         // interior tiles run; a kernel that cannot split runs whole and the exchange follows it
-        const HsTileRows outer{split->mid_lo, split->mid_hi, false}, inner{split->mid_lo, split->mid_hi, true};
+        const HsTileRows outer{split->mid_lo, split->mid_hi, false, 0}, inner{split->mid_lo, split->mid_hi, true, split->reserve_sms};
         if (launch_hs_fused(T, variant, precise, *U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2, s, &outer)) {
           split->begin(cur ^ 1);
           launch_hs_fused(T, variant, precise, *U[cur], *V[cur], *U[cur ^ 1], *V[cur ^ 1], fx, fy, ft, alpha2, s, &inner);

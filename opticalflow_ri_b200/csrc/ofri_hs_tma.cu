@@ -453,7 +453,9 @@ static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& v
   }
   const long ntiles = (long)tiles_x * tiles_y * ui.batch;
   if (ntiles > 0x7fffffffL) return false;
-  const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+  int avail = num_sms - (sub ? sub->reserve_sms : 0);
+  if (avail < 1) avail = 1;
+  const int grid = (int)(ntiles < avail ? ntiles : avail);
   kern<<<grid, C::NT, C::SMEM_BYTES, s>>>(mU, mV, mA, mB, mC, uo, vo, ui.W, ui.H, tiles_x, tiles_y, (int)ntiles,
                                           alpha2, rows);
   return true;

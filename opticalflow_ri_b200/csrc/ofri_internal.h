@@ -57,7 +57,9 @@ typedef std::function<void(int k0, int n, int written)> LsHook;
 typedef std::function<void(int done, int cur)> HsHook;
 // Split launch of the TMA kernel: only the tile rows lying entirely inside output rows [row_lo, row_hi) (inside = true)
 // or all the other tile rows (inside = false).
-struct HsTileRows { int row_lo; int row_hi; bool inside; };
+// reserve_sms: leave that many SMs without a CTA of the (persistent, one CTA per SM, whole register file) kernel, so that
+// a communication kernel enqueued on another stream can start while this launch runs.
+struct HsTileRows { int row_lo; int row_hi; bool inside; int reserve_sms = 0; };
 // Row-band mode with overlap: the launch that completes a block of `every` sweeps (and the last launch) is issued in
 // two parts -- first the tiles that produce the rows the neighbours need (everything outside [mid_lo, mid_hi)), then
 // begin(cur) starts the ghost-row exchange of buffer `cur` on the communication stream, then the interior tiles run
@@ -65,6 +67,7 @@ struct HsTileRows { int row_lo; int row_hi; bool inside; };
 struct HsSplit {
   int every = 0;
   int mid_lo = 0, mid_hi = 0;
+  int reserve_sms = 0;            // SMs the interior launch leaves to the exchange running beside it
   std::function<void(int cur)> begin;
   std::function<void()> end;
 };
@@ -160,6 +163,7 @@ struct Comm {
   virtual int allreduce_max_u32(unsigned* p, size_t n, cudaStream_t s) = 0;
   virtual int allgather(const float* send, float* recv, size_t count, cudaStream_t s) = 0;   // recv: [nranks][count]
   virtual const char* error() const = 0;
+  virtual bool uses_sms() const { return false; }   // true: exchanges run as kernels (NCCL) and need free SMs to overlap
 };
 struct LocalGroup;
 int nccl_unique_id(void* out128, std::string* err);

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--hs-niter", type=int, default=600)
     ap.add_argument("--ls-fuse", type=int, default=0)
     ap.add_argument("--hs-fuse-fast", type=int, default=0)
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs an overlapped interior launch leaves to NCCL (-1 = default)")
     ap.add_argument("--exchange", type=int, default=0, help="HS sweeps between ghost-row exchanges (0 = default 32)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
@@ -57,6 +58,8 @@ def main():
         h.set_option("ls_fuse", args.ls_fuse)
     if args.hs_fuse_fast:
         h.set_option("hs_fuse_fast", args.hs_fuse_fast)
+    if args.reserve_sms >= 0:
+        h.set_option("band_reserve_sms", args.reserve_sms)
     if world > 1:
         uid = [ofri.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -106,7 +109,7 @@ def main():
     st = h.stage_timings()
     if rank == 0:
         px_it = 1.25 * N * N * (args.hs_niter + 60)
-        out.update({"size": N, "ms_per_pair": round(best, 1), "pairs_per_s": round(1e3 / best, 4),
+        out.update({"reserve_sms": h.get_option("band_reserve_sms"), "size": N, "ms_per_pair": round(best, 1), "pairs_per_s": round(1e3 / best, 4),
                     "gpix_iter_per_s": round(px_it / (best / 1e3) / 1e9, 1), "rows_owned": band.own1 - band.own0,
                     "rows_supplied": band.in1 - band.in0, "ghost": band.ghost, "exchange_every_sweeps": band.exchange,
                     "finite": bool(torch.isfinite(u).all().item()), "stages_rank0_ms": {k: round(x, 1) for k, x in st.items()}})
