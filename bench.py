@@ -123,7 +123,7 @@ def _cpu_one(seed_and_size):
     return time.perf_counter() - t
 
 
-def cpu_baseline(cores, sample_px=384):
+def cpu_baseline(cores, sample_px=768):
     """Oracle (kind 'port': numpy restatement of the reference, single-threaded per pair like the reference) on
     `cores` processes, each running ONE sample_px^2 pair with the full parameters; scaled to 1024^2 pairs by pixel count
     (the path is linear in pixels; stated in `sample`)."""
@@ -362,7 +362,8 @@ def main():
     ap.add_argument("--pairs-per-gpu", type=int, default=512)
     ap.add_argument("--e2e-pairs", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=384)
+    ap.add_argument("--cpu-sample", type=int, default=768,
+                    help="side of the sample pair the CPU arms time (768: ~12 s of single-core work per pair)")
     ap.add_argument("--cpu-cores", type=int, default=0, help="host processes of the reference arm (0 = all cores)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--hs-fuse", type=int, default=None)

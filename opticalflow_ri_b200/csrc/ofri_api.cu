@@ -357,16 +357,23 @@ void plan_workspace(Bump& b, int batch, int H, int W, const ofri_params* p, Work
   ws->lsw_flag = (int*)b.take(sizeof(int) * 4);
 }
 
-// A launch that cannot fill the GPU (fewer tiles than SMs, e.g. one 512 x 512 pair) is bound by launch latency, not by
-// throughput: fuse 8 (Horn-Schunck) / 4 (Liu-Shen) sweeps per launch then.  Results do not depend on the fuse factor
-// (bit-identical, tested).  Not used in row-band mode, where the exchange interval is tied to the configured factor.
+// Automatic fuse factors (auto_fuse = 1; results do not depend on the fuse factor: bit-identical, tested).
+//  * A launch that cannot fill the GPU (fewer tiles than SMs, e.g. one 512 x 512 pair) is bound by launch latency, not
+//    by throughput: fuse 8 (Horn-Schunck) / 4 (Liu-Shen) sweeps per launch.
+//  * Very large frames (>= 4096 in both directions): the image border wastes < 3 % of the (smaller) T = 8 tiles, and the
+//    fast Horn-Schunck kernel, HBM-bound at T = 4, becomes issue-bound at T = 8 and 12 % faster (16384^2: 200.6 ms
+//    instead of 225.7 for 600 sweeps); Liu-Shen gains 6 % from T = 4.  At 1024^2 the border waste cancels the gain.
+// Row-band mode ties the exchange interval to the configured factor and applies the same rules there.
+bool big_frame(int H, int W) { return H >= 4096 && W >= 4096; }
 int eff_hs_fuse(ofri_handle h, int H, int W, int batch, bool precise = false) {
   const int fuse = (!precise && h->hs_fuse_fast > 0) ? h->hs_fuse_fast : h->hs_fuse;
   if (!h->auto_fuse || fuse < 1 || fuse >= 8) return fuse;
+  if (!precise && h->hs_fuse_fast == 0 && big_frame(H, W)) return 8;
   return (long)((W + 119) / 120) * ((H + 57) / 58) * batch < 148 ? 8 : fuse;
 }
 int eff_ls_fuse(ofri_handle h, int H, int W, int batch) {
   if (!h->auto_fuse || h->ls_fuse < 1 || h->ls_fuse >= 4) return h->ls_fuse;
+  if (big_frame(H, W)) return 4;
   return (long)((W + 119) / 120) * ((H + 29) / 30) * batch < 148 ? 4 : h->ls_fuse;
 }
 
@@ -918,7 +925,8 @@ int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs
       // more than on one GPU -- fuse 8 sweeps per fast-arithmetic launch unless configured otherwise
       int fuse = h->hs_fuse;
       if (!precise && h->hs_fuse_fast > 0 && E % h->hs_fuse_fast == 0) fuse = h->hs_fuse_fast;
-      else if (!precise && h->hs_fuse_fast == 0 && h->auto_fuse && c && c->nranks > 1 && fuse >= 1 && fuse < 8 && E % 8 == 0)
+      else if (!precise && h->hs_fuse_fast == 0 && h->auto_fuse && fuse >= 1 && fuse < 8 && E % 8 == 0 &&
+               ((c && c->nranks > 1) || big_frame(bl.Hl, bl.Wl)))
         fuse = 8;
       res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], niter, fuse,
                               h->hs_variant, precise, s, h->lc, HsHook(), &split);
@@ -951,7 +959,8 @@ int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs
     // The ghost frame holds E valid rows after an exchange and every sweep spoils one more: refresh it only when the
     // next block would run out (the residual sums, in contrast, are needed by the very next launch's stopping rule).
     int ls_fuse = h->ls_fuse;
-    if (h->auto_fuse && c && c->nranks > 1 && ls_fuse >= 1 && ls_fuse < 4) ls_fuse = 4;   // half the launches / all-reduces
+    if (h->auto_fuse && ls_fuse >= 1 && ls_fuse < 4 && ((c && c->nranks > 1) || big_frame(bl.Hl, bl.Wl)))
+      ls_fuse = 4;                                                            // half the launches / all-reduces
     const int Tl = ls_fuse > 4 ? 4 : (ls_fuse < 1 ? 1 : ls_fuse);
     int spoiled = 0;
     LsHook hook = [&](int k0, int n, int written) {
