@@ -64,11 +64,14 @@ __device__ __forceinline__ void ls_row_update_regs(const float (&uu)[6], const f
                                                    const LsEdge& eg, float (&ou)[4], float (&ov)[4]) {
   const float (&c0)[4] = k.c[0], (&c1)[4] = k.c[1], (&c2)[4] = k.c[2], (&c3)[4] = k.c[3];
   const float (&c4)[4] = k.c[4], (&c5)[4] = k.c[5], (&c6)[4] = k.c[6], (&c7)[4] = k.c[7];
-  // zero-padded column sums for H8 (interior: identical to the clamped values)
-  float zsu[6], zsv[6], zmu[6], zmv[6];
+  // zero-padded column sums for H8 (interior: identical to the clamped values) and the vertical differences (clamped)
+  // that 2 Dr and 4 Mx are made of -- one each per column, shared by the pixels left and right of it
+  float zsu[6], zsv[6], zmu[6], zmv[6], vdu[6], vdv[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     float a = uu[c], d = ud[c], e = vu[c], f = vd[c];
+    vdu[c] = fsub(d, a);
+    vdv[c] = fsub(f, e);
     if (EDGE) {
       if (ztop) { a = 0.0f; e = 0.0f; }
       if (zbot) { d = 0.0f; f = 0.0f; }
@@ -88,11 +91,18 @@ __device__ __forceinline__ void ls_row_update_regs(const float (&uu)[6], const f
     }
     float h8u = ls_h8_cols(vlu, zsu[j + 1], vru, wu_, eu_);
     float h8v = ls_h8_cols(vlv, zsv[j + 1], vrv, wv_, ev_);
-    LsNb nu{uu[j + 1], ud[j + 1], um[j], um[j + 2], uu[j], uu[j + 2], ud[j], ud[j + 2]};
-    LsNb nv{vu[j + 1], vd[j + 1], vm[j], vm[j + 2], vu[j], vu[j + 2], vd[j], vd[j + 2]};
+    LsSt t;                                   // the same expressions as ls_update2 forms from the 8 neighbours
+    t.dr_u = vdu[j + 1];
+    t.dr_v = vdv[j + 1];
+    t.dc_u = fsub(um[j + 2], um[j]);
+    t.dc_v = fsub(vm[j + 2], vm[j]);
+    t.fr_u = fadd(uu[j + 1], ud[j + 1]);
+    t.fc_v = fadd(vm[j], vm[j + 2]);
+    t.mx_u = fsub(vdu[j + 2], vdu[j]);
+    t.mx_v = fsub(vdv[j + 2], vdv[j]);
     LsCoef c;
     c.IIx = c0[j]; c.IIy = c1[j]; c.II = c2[j]; c.Ixt = c3[j]; c.Iyt = c4[j]; c.B11 = c5[j]; c.B12 = c6[j]; c.B22 = c7[j];
-    ls_update2(nu, nv, h8u, h8v, c, hpar, &ou[j], &ov[j]);
+    ls_update3(t, h8u, h8v, c, hpar, &ou[j], &ov[j]);
   }
 }
 

@@ -12,7 +12,8 @@
 //   * Liu-Shen's boundary rules are not reflections ('nearest' for the difference stencils, zero padding for the
 //     8-neighbour sum), so border tiles run an EDGE instantiation that re-applies them every sweep;
 //   * the residual sums of every sweep (LS:79) are accumulated per thread over the tile's own output cells, reduced by
-//     warp shuffle into a shared per-sweep accumulator and added to errs[pair][k] with one f64 atomic per CTA and pair;
+//     f32 warp butterfly into the warp's own f64 slot in shared memory, added to errs[pair][k] with one f64 atomic per
+//     CTA, pair and sweep;
 //   * the stopping rule (LS:141) is evaluated per tile from the previous block's sums: tiles of stopped pairs are
 //     skipped (their TMA load is still consumed so the pipeline keeps its phase).
 // Algorithmic HBM traffic: 48 B per pixel per launch (read u, v + 8 planes; write u, v) for T sweeps.
@@ -36,7 +37,7 @@ struct LtCfg {
   static constexpr int XPLANE = XG * 2 * SW;
   static constexpr int STAGE_BYTES = 10 * PLANE * 4;
   static constexpr int X_BYTES = 2 * 2 * XPLANE * 4;
-  static constexpr int SMEM_BYTES = STAGE_BYTES + X_BYTES + 256;   // + mbarrier, stop flag, residual accumulators
+  static constexpr int SMEM_BYTES = STAGE_BYTES + X_BYTES + 1024;  // + mbarrier, stop flag, residual accumulators
   static_assert(TW > 0 && TH > 0 && T <= HX && NT <= 1024 && SH <= 256, "bad tile");
   static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit in shared memory");
   static_assert((PLANE * 4) % 128 == 0, "TMA destination alignment");
@@ -93,7 +94,7 @@ struct LtShared {
   unsigned long long bar;
   int stop;
   int pad;
-  double acc[4][2];      // residual sums of the current pair, per fused sweep
+  double acc[4][12][2];  // residual sums of the current pair, per fused sweep and WARP (own slot: no atomics)
 };
 
 template <int T, int R, int NRG>
@@ -124,7 +125,7 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     issue(lt_decode<T, R, NRG>(tile, tiles_x, tiles_y));
   }
-  if (tid < 8) sh->acc[tid >> 1][tid & 1] = 0.0;
+  if (tid < 4 * 12 * 2) (&sh->acc[0][0][0])[tid] = 0.0;
   __syncthreads();
   auto X = [&](int buf, int plane, int g, int which) -> float* {
     return xbuf + ((buf * 2 + plane) * C::XG + g) * 2 * SW + which * SW + sx;
@@ -134,9 +135,13 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
   auto flush = [&]() {    // all threads; ends with a barrier
     __syncthreads();
     if (acc_pair >= 0 && tid < 2 * T) {
-      const double v = sh->acc[tid >> 1][tid & 1];
+      double v = 0.0;
+#pragma unroll
+      for (int g = 0; g < NRG; ++g) {
+        v += sh->acc[tid >> 1][g][tid & 1];
+        sh->acc[tid >> 1][g][tid & 1] = 0.0;
+      }
       if (v != 0.0) atomicAdd(errs + ((long)acc_pair * maxiter + k0 + (tid >> 1)) * 2 + (tid & 1), v);
-      sh->acc[tid >> 1][tid & 1] = 0.0;
     }
     __syncthreads();
   };
@@ -254,16 +259,17 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
 #pragma unroll
           for (int q = 0; q < 4; ++q) { u[j][q] = ou[q]; v[j][q] = ov[q]; }
         }
-        // residual: f64 warp reduction, one shared atomic per warp and component
-        double su = (double)du2, sv = (double)dv2;
+        // residual: f32 butterfly over the warp (a balanced tree: relative error ~1e-7, below the f32 rounding of the
+        // reference's own BLAS norm), then f64 accumulation in the warp's own shared slot (no atomics)
+        float su = du2, sv = dv2;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          su += __shfl_xor_sync(0xffffffffu, su, o);
-          sv += __shfl_xor_sync(0xffffffffu, sv, o);
+          su = fadd(su, __shfl_xor_sync(0xffffffffu, su, o));
+          sv = fadd(sv, __shfl_xor_sync(0xffffffffu, sv, o));
         }
         if (lane == 0) {
-          atomicAdd(&sh->acc[s][0], su);
-          atomicAdd(&sh->acc[s][1], sv);
+          sh->acc[s][rg][0] += (double)su;
+          sh->acc[s][rg][1] += (double)sv;
         }
         if (!last) {
           const int nxt = cur ^ 1;

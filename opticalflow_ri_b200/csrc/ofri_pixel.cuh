@@ -324,29 +324,37 @@ struct LsNb { float n, s, w, e, nw, ne, sw, se; };
 OFRI_HD float ls_h8_cols(float vl, float vc, float vr, float w, float e) {   // vl = nw+sw, vc = n+s, vr = ne+se
   return fadd(fadd(fadd(vl, vc), vr), fadd(w, e));
 }
-OFRI_HD void ls_update2(const LsNb& u, const LsNb& v, float h8u, float h8v, const LsCoef& c, float hpar, float* un,
-                        float* vn) {
-  float dru = fsub(u.s, u.n), dcu = fsub(u.e, u.w), drv = fsub(v.s, v.n), dcv = fsub(v.e, v.w);   // 2 Dr, 2 Dc
-  float fru = fadd(u.n, u.s), fcv = fadd(v.w, v.e);
-  float mxu = fadd(fsub(fsub(u.nw, u.ne), u.sw), u.se);                                          // 4 Mx
-  float mxv = fadd(fsub(fsub(v.nw, v.ne), v.sw), v.se);
+// The stencil values of one pixel.  Written as differences / sums of COLUMN quantities (vertical difference s - n,
+// centre-row samples), so a kernel that sweeps along a row forms each column quantity once and shares it between the
+// three pixels it touches: 2 Dr = vd_c, 4 Mx = vd_e - vd_w with vd = s - n of the centre / east / west column.
+struct LsSt { float dr_u, dc_u, dr_v, dc_v, fr_u, fc_v, mx_u, mx_v; };
+OFRI_HD void ls_update3(const LsSt& t, float h8u, float h8v, const LsCoef& c, float hpar, float* un, float* vn) {
   float hx = fmul(0.5f, c.IIx), hy = fmul(0.5f, c.IIy), q = fmul(0.25f, c.II);
-  float bu = fmul(c.IIx, dru);
-  bu = fmaf(hx, dcv, bu);
-  bu = fmaf(hy, drv, bu);
-  bu = fmaf(c.II, fru, bu);
-  bu = fmaf(q, mxv, bu);
+  float bu = fmul(c.IIx, t.dr_u);
+  bu = fmaf(hx, t.dc_v, bu);
+  bu = fmaf(hy, t.dr_v, bu);
+  bu = fmaf(c.II, t.fr_u, bu);
+  bu = fmaf(q, t.mx_v, bu);
   bu = fmaf(hpar, h8u, bu);
   bu = fadd(bu, c.Ixt);
-  float bv = fmul(hy, dru);
-  bv = fmaf(hx, dcu, bv);
-  bv = fmaf(c.IIy, dcv, bv);
-  bv = fmaf(q, mxu, bv);
-  bv = fmaf(c.II, fcv, bv);
+  float bv = fmul(hy, t.dr_u);
+  bv = fmaf(hx, t.dc_u, bv);
+  bv = fmaf(c.IIy, t.dc_v, bv);
+  bv = fmaf(q, t.mx_u, bv);
+  bv = fmaf(c.II, t.fc_v, bv);
   bv = fmaf(hpar, h8v, bv);
   bv = fadd(bv, c.Iyt);
   *un = -fmaf(c.B11, bu, fmul(c.B12, bv));
   *vn = -fmaf(c.B12, bu, fmul(c.B22, bv));
+}
+OFRI_HD void ls_update2(const LsNb& u, const LsNb& v, float h8u, float h8v, const LsCoef& c, float hpar, float* un,
+                        float* vn) {
+  LsSt t;
+  t.dr_u = fsub(u.s, u.n); t.dc_u = fsub(u.e, u.w); t.dr_v = fsub(v.s, v.n); t.dc_v = fsub(v.e, v.w);   // 2 Dr, 2 Dc
+  t.fr_u = fadd(u.n, u.s); t.fc_v = fadd(v.w, v.e);
+  t.mx_u = fsub(fsub(u.se, u.ne), fsub(u.sw, u.nw));                                                 // 4 Mx
+  t.mx_v = fsub(fsub(v.se, v.ne), fsub(v.sw, v.nw));
+  ls_update3(t, h8u, h8v, c, hpar, un, vn);
 }
 // convenience for per-pixel callers: 3x3 clamped neighbourhoods + in-bounds mask (bit 3r+c)
 OFRI_HD void ls_update(const float uc[3][3], const float vc[3][3], unsigned inb, const LsCoef& c, float hpar,

@@ -80,6 +80,17 @@ void hc_spline_line_win(const double* y, int n, int a, int b, int C, int Wm, dou
   std::vector<double> D(n, 0.0);
   solve_line_win<double>(y, 1, D.data(), M, 1, n, a, b, C, Wm, sys_view(s, n));
 }
+// coarse rows [*lo, *hi) a band must hold to up-sample output rows [row0, row0 + rows) of H (launch_spline's rule)
+void hc_spline_rows_needed(int row0, int rows, int h, int H, int Wm, int* lo, int* hi) {
+  HostSplineSys sy = build_spline_sys(h);
+  int ia, ib;
+  double sf;
+  spline_locate(row0, h, H, &ia, &sf);
+  spline_locate(row0 + rows - 1, h, H, &ib, &sf);
+  const SplineWindow w = spline_window(ia, ib + 1, h, sy.conv, Wm);
+  *lo = w.FS;
+  *hi = w.RF + 3;
+}
 // rows [row0, row0 + rows) of the up-sampled plane by the windowed algorithm (what a row band computes)
 void hc_spline_win(const float* in, int h, int w, int H, int W, float mul, int row0, int rows, int Cy, int Cx, int Wm,
                    float* out) {
