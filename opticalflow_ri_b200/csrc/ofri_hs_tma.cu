@@ -476,7 +476,7 @@ static bool launch_T(int variant, bool precise, const Img& ui, const Img& vi, co
   }
 }
 
-// T in {4, 6, 8}.  Returns false if this kernel cannot run (other T, no driver entry point, map encoding failed): the
+// T in {4, 6, 8} (precise arithmetic: also 2, 3).  Returns false if this kernel cannot run (other T, no driver entry point, map encoding failed): the
 // caller then uses the non-persistent kernels.
 bool launch_hs_tma(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo, const Img& vo,
                    const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s, const HsTileRows* sub) {
@@ -488,6 +488,9 @@ bool launch_hs_tma(int T, int variant, bool precise, const Img& ui, const Img& v
     if (num_sms <= 0) num_sms = 148;
   }
   switch (T) {
+    // T = 2, 3: precise arithmetic only (fewer stale border cells per tile; the fast kernel would be HBM-bound there)
+    case 2: return precise ? launch_cfg<2, 4, 8, true>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub) : false;
+    case 3: return precise ? launch_cfg<3, 4, 8, true>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub) : false;
     case 4: return launch_T<4>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);
     case 6: return launch_T<6>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);
     case 8: return launch_T<8>(variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);

@@ -54,6 +54,9 @@ def run(tag):
 
 
 h.set_option("hs_precise", int(os.environ.get("HS_PRECISE", "1")))
+for _k in ("hs_fuse_fast", "hs_fuse_precise", "auto_fuse"):
+    if os.environ.get(_k.upper()):
+        h.set_option(_k, int(os.environ[_k.upper()]))
 which = os.environ.get("SWEEP", "hs,ls")
 if "one" in which:
     h.set_option("hs_fuse", int(os.environ.get("HS_FUSE", "4")))
