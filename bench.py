@@ -271,7 +271,7 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         px_fine, px_coarse = H * W, int(np.round(H * 0.5)) * int(np.round(W * 0.5))
         nl = -(-HS_NITER // max(T, 1))            # launches per level
-        chunk = min(P, 64)                        # pairs per launch (library chunking)
+        chunk = h.get_option("last_chunk_pairs") or min(P, 64)   # pairs per launch (the library's chunking)
         nchunks = -(-P // chunk)
 
         def entry(kernel, stage, bytes_px, px_levels, launches_per_level, sweeps):
@@ -300,13 +300,14 @@ def run_ours(args):
         if kernels:
             dom = max(kernels, key=lambda k: k["stage_ms"])
             roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
-                    "frac": dom["frac"], "traffic": ROOFLINE_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
+                    "frac": dom["frac"], "traffic": int(ROOFLINE_TRAFFIC_BYTES_PER_LAUNCH * chunk / 64.0), "peak_source": peak_src,
+                    "pairs_per_launch": chunk,
                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
                     "avg_launch_ms": dom["avg_launch_ms"], "share_of_step": dom["stage_ms"] / sum(stage_ms.values()),
                     "note": "achieved = algorithmic bytes of the kernel's launches in one step / their CUDA-event time "
                             "(stage timer on the launching stream); 28 B/px/launch = read U,V,a,b,c + write U,V, for T "
                             "fused sweeps; frac_in_unfused_bytes = the same sweeps/s expressed in the 28 B/px/sweep an "
-                            "unfused (T=1) sweep moves; traffic = dram read+write bytes per launch from the committed "
+                            "unfused (T=1) sweep moves; traffic = dram read+write bytes per launch (captured for a 64-pair launch: 1.850 GB vs 1.879 GB algorithmic, scaled to pairs_per_launch) from the committed "
                             "ncu capture (profiles/), null until captured for this launch shape",
                     "kernels": kernels}
     # ---- end-to-end through the host-pointer C-ABI call (pinned host buffers) -----------------------------------------

@@ -54,6 +54,7 @@ struct ofri_ctx {
   // row-band (domain-decomposed) mode
   ofri::Comm* comm = nullptr;
   int hs_fuse_fast = 0;     // fuse factor of the fast-arithmetic Horn-Schunck launches only (0 = hs_fuse)
+  int last_chunk_pairs = 0; // read-only: pairs per chunk the last batched call used
   int hs_fuse_precise = 0;  // fuse factor of the reference-arithmetic launches only (0 = hs_fuse); not used in row-band mode
   int auto_fuse = 1;        // deeper fusion for launches that cannot fill the GPU (see eff_hs_fuse)
   int band_exchange = 32;   // Horn-Schunck sweeps between two ghost-row exchanges (rounded up to a multiple of hs_fuse)
@@ -671,7 +672,12 @@ int ensure_stage(ofri_handle h, size_t bytes) {
   return OFRI_OK;
 }
 
+int pick_chunk_impl(ofri_handle h, int batch, int H, int W, const ofri_params* p, size_t extra_per_pair, int cap);
 int pick_chunk(ofri_handle h, int batch, int H, int W, const ofri_params* p, size_t extra_per_pair, int cap = 64) {
+  h->last_chunk_pairs = pick_chunk_impl(h, batch, H, W, p, extra_per_pair, cap);
+  return h->last_chunk_pairs;
+}
+int pick_chunk_impl(ofri_handle h, int batch, int H, int W, const ofri_params* p, size_t extra_per_pair, int cap) {
   if (h->chunk_pairs > 0) return h->chunk_pairs < batch ? h->chunk_pairs : batch;
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
@@ -680,42 +686,9 @@ int pick_chunk(ofri_handle h, int batch, int H, int W, const ofri_params* p, siz
   long n = (long)(budget / (per_pair ? per_pair : 1));
   if (n < 1) n = 1;
   if (n > cap) n = cap;        // enough to fill 148 SMs many times over; keeps the working set bounded
-  if (n >= batch) return batch;
-  // Wave fit: the persistent sweep kernels give every SM ceil(tiles / SMs) equal tiles, so a chunk whose tile counts sit
-  // just above a multiple of the SM count wastes most of a wave in every launch (64 pairs of 1024^2: 70.05 waves of
-  // the fast kernel -> 71).  Among the chunk sizes in (n/2, n] take the one with the least estimated sweep time for the
-  // whole batch (tiles x sweeps x relative tile cost of the three kernels, per level, incl. the remainder chunk).
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-  if (sms < 1) sms = 148;
-  const int L = p->pyramid_levels;
-  auto waves = [&](long tiles) { return (double)((tiles + sms - 1) / sms); };
-  auto chunk_cost = [&](int c) {
-    double t = 0.0, scale = 1.0 / std::pow(2.0, L - 1);
-    for (int l = 0; l < L; ++l, scale *= 2.0) {
-      const int Hl = l == L - 1 ? H : level_size(H, scale), Wl = l == L - 1 ? W : level_size(W, scale);
-      const long tx = (Wl + 119) / 120;
-      const ofri_algo* algos[2] = {&p->main_algo, &p->opt_algo};
-      for (const ofri_algo* a : algos) {
-        if (a->kind == OFRI_ALGO_HS) {
-          const bool precise = h->hs_precise >= 2 || (h->hs_precise == 1 && l < L - 1);
-          if (precise) t += waves(tx * ((Hl + 25) / 26) * c) * (a->hs_niter / 4.0) * 1.78;     // 34 x 128 tiles, T = 4
-          else t += waves(tx * ((Hl + 57) / 58) * c) * (a->hs_niter / 4.0) * 1.42;            // 66 x 128 tiles, T = 4
-        } else if (a->kind == OFRI_ALGO_LS) {
-          t += waves(tx * ((Hl + 29) / 30) * c) * (a->ls_maxiter / 2.0) * 1.48;               // 34 x 128 tiles, T = 2
-        }
-      }
-    }
-    return t;
-  };
-  int best = (int)n;
-  double best_cost = 0.0;
-  for (int c = (int)n; c > n / 2 && c >= 1; --c) {
-    const int full = batch / c, rem = batch % c;
-    const double cost = full * chunk_cost(c) + (rem ? chunk_cost(rem) : 0.0);
-    if (c == (int)n || cost < best_cost * 0.999) { best = c; best_cost = cost; }
-  }
-  return best;
+  // (a wave-fit choice of the chunk size -- tile counts just below a multiple of the SM count -- was measured: no
+  // difference, 459.0 / 459.5 vs 460.6 / 459.3 pairs/s, profiles/r1_chunk_wavefit_ab.txt)
+  return (int)(n < batch ? n : batch);
 }
 
 // generic helper for the stage-level host entry points: upload dense host planes into pitched device planes
@@ -1331,6 +1304,7 @@ static int* option_slot(ofri_handle h, const char* key) {
   if (!strcmp(key, "auto_fuse")) return &h->auto_fuse;
   if (!strcmp(key, "hs_fuse_fast")) return &h->hs_fuse_fast;
   if (!strcmp(key, "hs_fuse_precise")) return &h->hs_fuse_precise;
+  if (!strcmp(key, "last_chunk_pairs")) return &h->last_chunk_pairs;
   if (!strcmp(key, "band_exchange")) return &h->band_exchange;
   if (!strcmp(key, "band_reach")) return &h->band_reach;
   if (!strcmp(key, "spline_variant")) return &h->spline_variant;
