@@ -108,7 +108,8 @@ OFRI_API const char* ofri_last_error(ofri_handle h);                    /* h may
 /* run on a caller-owned stream (e.g. torch's current stream) instead of the handle's own; 0 restores */
 OFRI_API int ofri_set_stream(ofri_handle h, void* cuda_stream);
 OFRI_API int ofri_synchronize(ofri_handle h);
-/* tuning / A-B switches, e.g. ("hs_fuse", 4), ("ls_fuse", 2), ("chunk_pairs", 16); unknown key -> OFRI_ERR_INVALID */
+/* tuning / A-B switches, e.g. ("hs_fuse", 4), ("ls_fuse", 2), ("chunk_pairs", 16); the full table is in
+ * INTEGRATION.md section 5; unknown key -> OFRI_ERR_INVALID */
 OFRI_API int ofri_set_option(ofri_handle h, const char* key, int value);
 OFRI_API int ofri_get_option(ofri_handle h, const char* key, int* value);
 /* number of kernel launches issued by this handle since creation (for bench.py's gpu_launches) */
