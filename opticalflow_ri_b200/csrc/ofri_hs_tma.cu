@@ -33,6 +33,8 @@ struct TmCfg {
   static constexpr int SW = 128;
   static constexpr int SH = R * NRG + 2;
   static constexpr int NT = 32 * NRG;
+  static constexpr int CTAS = NT <= 128 ? 2 : 1;              // 4-warp CTAs: two per SM (255 registers x 128 threads each), so
+                                                              // one CTA's load / store phases run under the other's arithmetic
   static constexpr int TW = SW - 2 * HX;
   static constexpr int TH = SH - 2 * T;
   static constexpr int PLANE = SH * SW;                      // floats per staged plane
@@ -42,7 +44,7 @@ struct TmCfg {
   static constexpr int X_BYTES = 2 * 2 * XPLANE * 4;         // [buffer][U / V]
   static constexpr int SMEM_BYTES = STAGE_BYTES + X_BYTES + 64;
   static_assert(TW > 0 && TH > 0 && HX >= T && NT <= 1024 && SH <= 256, "bad tile");
-  static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit in shared memory");
+  static_assert(CTAS * (SMEM_BYTES + 1024) <= 227 * 1024, "tile does not fit in shared memory");
   static_assert((PLANE * 4) % 128 == 0, "TMA destination alignment");
 };
 
@@ -377,7 +379,7 @@ __device__ __forceinline__ void hs_tma_tile_precise(const TmTile& tl, int W, int
 }
 
 template <int T, int R, int NRG, bool PRECISE>
-__global__ void __launch_bounds__(TmCfg<T, R, NRG>::NT, 1)
+__global__ void __launch_bounds__(TmCfg<T, R, NRG>::NT, TmCfg<T, R, NRG>::CTAS)
 hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CUtensorMap mV,
               const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
               const __grid_constant__ CUtensorMap mC, Img uo, Img vo, int W, int H, int tiles_x, int tiles_y,
@@ -453,7 +455,7 @@ static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& v
   }
   const long ntiles = (long)tiles_x * tiles_y * ui.batch;
   if (ntiles > 0x7fffffffL) return false;
-  int avail = num_sms - (sub ? sub->reserve_sms : 0);
+  int avail = (num_sms - (sub ? sub->reserve_sms : 0)) * C::CTAS;
   if (avail < 1) avail = 1;
   const int grid = (int)(ntiles < avail ? ntiles : avail);
   kern<<<grid, C::NT, C::SMEM_BYTES, s>>>(mU, mV, mA, mB, mC, uo, vo, ui.W, ui.H, tiles_x, tiles_y, (int)ntiles,
@@ -473,6 +475,7 @@ static bool launch_T(int variant, bool precise, const Img& ui, const Img& vi, co
     case 25: return launch_cfg<T, 6, 8, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);     // 50 x 128, 256 threads
     case 26: return launch_cfg<T, 4, 12, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);    // 50 x 128, 384 threads
     case 27: return launch_cfg<T, 6, 10, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);    // 62 x 128, 320 threads
+    case 28: return launch_cfg<T, 8, 4, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);     // 34 x 128, 128 threads, 2 CTAs / SM
   }
 }
 

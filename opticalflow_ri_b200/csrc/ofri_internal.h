@@ -174,7 +174,7 @@ Comm* make_local_comm(LocalGroup* g, int rank, std::string* err);
 
 // persistent TMA-fed fused Liu-Shen block (ofri_ls_tma.cu): T sweeps ui, vi -> uo, vo; false = not applicable
 bool launch_ls_tma(int T, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const LsPlanes& co, float hpar,
-                   int k0, int maxiter, double tol, double* errs, const LsBand& band, cudaStream_t s);
+                   int k0, int maxiter, double tol, double* errs, const LsBand& band, cudaStream_t s, int variant = 8);
 
 const char* kernel_build_info();
 

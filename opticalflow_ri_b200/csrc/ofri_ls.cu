@@ -496,8 +496,8 @@ void launch_ls_solve(const Img& ua, const Img& va, const Img& ub, const Img& vb,
     for (int i = 0; i < nfull; ++i) {
       bool done = false;
       if (variant >= 8)      // persistent TMA-fed register-resident kernel (ofri_ls_tma.cu); launch i reads buffer (i & 1)
-        done = (i & 1) ? launch_ls_tma(T, ub, vb, ua, va, coef, hpar, i * T, maxiter, tol, errs, band, s)
-                       : launch_ls_tma(T, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, band, s);
+        done = (i & 1) ? launch_ls_tma(T, ub, vb, ua, va, coef, hpar, i * T, maxiter, tol, errs, band, s, variant)
+                       : launch_ls_tma(T, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, band, s, variant);
       if (!done) launch_ls_fused(T, variant >= 8 ? 4 : variant, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, band, s);
       lc.n += 1;
       // launch i wrote buffer b (odd launches write a); band mode: sum the block's residuals over all bands and refresh

@@ -30,16 +30,17 @@ struct LtCfg {
   static constexpr int SW = 128;
   static constexpr int SH = R * NRG + 2;
   static constexpr int NT = 32 * NRG;
+  static constexpr int CTAS = NT <= 128 ? 2 : 1;              // 4-warp CTAs: two per SM, phases of one under the other's arithmetic
   static constexpr int TW = SW - 2 * HX;
   static constexpr int TH = SH - 2 * T;
   static constexpr int PLANE = SH * SW;
-  static constexpr int XG = NRG + 2;
-  static constexpr int XPLANE = XG * 2 * SW;
+  static constexpr int XROWS = 2 * NRG + 2;                  // [tile row 0 | first, last row of every group | tile row SH-1]
+  static constexpr int XPLANE = XROWS * SW;
   static constexpr int STAGE_BYTES = 10 * PLANE * 4;
   static constexpr int X_BYTES = 2 * 2 * XPLANE * 4;
   static constexpr int SMEM_BYTES = STAGE_BYTES + X_BYTES + 1024;  // + mbarrier, stop flag, residual accumulators
   static_assert(TW > 0 && TH > 0 && T <= HX && NT <= 1024 && SH <= 256, "bad tile");
-  static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit in shared memory");
+  static_assert(CTAS * (SMEM_BYTES + 1024) <= 227 * 1024, "tile does not fit in shared memory");
   static_assert((PLANE * 4) % 128 == 0, "TMA destination alignment");
 };
 
@@ -98,7 +99,7 @@ struct LtShared {
 };
 
 template <int T, int R, int NRG>
-__global__ void __launch_bounds__(LtCfg<T, R, NRG>::NT, 1)
+__global__ void __launch_bounds__(LtCfg<T, R, NRG>::NT, LtCfg<T, R, NRG>::CTAS)
 ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H, int tiles_x, int tiles_y, int ntiles,
               float hpar, int k0, int maxiter, double tol, double* errs, LsBand band) {
   using C = LtCfg<T, R, NRG>;
@@ -128,7 +129,7 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
   if (tid < 4 * 12 * 2) (&sh->acc[0][0][0])[tid] = 0.0;
   __syncthreads();
   auto X = [&](int buf, int plane, int g, int which) -> float* {
-    return xbuf + ((buf * 2 + plane) * C::XG + g) * 2 * SW + which * SW + sx;
+    return xbuf + ((buf * 2 + plane) * C::XROWS + 2 * g + which - 1) * SW + sx;   // (g = 0: which = 1; g = NRG + 1: which = 0)
   };
   unsigned phase = 0;
   int acc_pair = -1;      // pair whose residual sums sit in sh->acc (CTA-uniform)
@@ -304,7 +305,8 @@ static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& v
   const int tiles_x = (ui.W + C::TW - 1) / C::TW, tiles_y = (ui.H + C::TH - 1) / C::TH;
   const long ntiles = (long)tiles_x * tiles_y * ui.batch;
   if (ntiles > 0x7fffffffL) return false;
-  const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+  const int slots = num_sms * C::CTAS;
+  const int grid = (int)(ntiles < slots ? ntiles : slots);
   kern<<<grid, C::NT, C::SMEM_BYTES, s>>>(maps, uo, vo, ui.W, ui.H, tiles_x, tiles_y, (int)ntiles, hpar, k0, maxiter, tol,
                                           errs, band);
   return true;
@@ -312,13 +314,20 @@ static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& v
 
 // One fused block of T sweeps (T in 2..4) ui, vi -> uo, vo.  false = not applicable (caller uses the other kernels).
 bool launch_ls_tma(int T, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const LsPlanes& co, float hpar,
-                   int k0, int maxiter, double tol, double* errs, const LsBand& band, cudaStream_t s) {
+                   int k0, int maxiter, double tol, double* errs, const LsBand& band, cudaStream_t s, int variant) {
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
+  }
+  if (variant == 9) {   // 18 x 128 tiles, 128 threads, two CTAs per SM
+    switch (T) {
+      case 2: return launch_cfg<2, 4, 4>(ui, vi, uo, vo, co, hpar, k0, maxiter, tol, errs, band, num_sms, s);
+      case 3: return launch_cfg<3, 4, 4>(ui, vi, uo, vo, co, hpar, k0, maxiter, tol, errs, band, num_sms, s);
+      default: return false;
+    }
   }
   switch (T) {
     case 2: return launch_cfg<2, 4, 8>(ui, vi, uo, vo, co, hpar, k0, maxiter, tol, errs, band, num_sms, s);

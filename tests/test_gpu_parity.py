@@ -206,7 +206,7 @@ def test_hs_fused_bit_identical_to_simple(h, shape):
             h.set_option("hs_fuse", 0)
             Ur, Vr = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
             for T in (1, 2, 3, 4, 5, 6, 8):
-                for variant in ((0, 2, 4, 8, 10, 16, 18, 24, 25, 26, 27) if precise == 0 else (0, 2, 24)):
+                for variant in ((0, 2, 4, 8, 10, 16, 18, 24, 25, 26, 27, 28) if precise == 0 else (0, 2, 24)):
                     h.set_option("hs_fuse", T)
                     h.set_option("hs_variant", variant)
                     U, V = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
@@ -295,7 +295,7 @@ def test_ls_fused_bit_identical_and_midblock_stop(h, shape):
             h.set_option("ls_fuse", 0)
             Ur, Vr, er, itr = h.ls_compute(g1, g2, U0, V0, 5, maxiter=maxiter, tol=tol)
             for T in (1, 2, 3, 4):
-                for lv in (0, 1, 2, 3, 4, 5, 8):
+                for lv in (0, 1, 2, 3, 4, 5, 8, 9):
                     h.set_option("ls_fuse", T)
                     h.set_option("ls_variant", lv)
                     U, V, e, it = h.ls_compute(g1, g2, U0, V0, 5, maxiter=maxiter, tol=tol)

@@ -74,8 +74,8 @@ if "hs" in which:
 if "ls" in which:
     h.set_option("hs_fuse", 4)
     h.set_option("hs_variant", int(os.environ.get("HS_VARIANT", "0")))
-    for T in (0, 1, 2, 3, 4):
-        for lv in ([0, 1, 2, 3, 4, 5, 8] if T > 0 else [0]):
+    for T in [int(x) for x in os.environ.get("LS_TS", "0,1,2,3,4").split(",")]:
+        for lv in ([int(x) for x in os.environ.get("LS_VARIANTS", "0,1,2,3,4,5,8").split(",")] if T > 0 else [0]):
             h.set_option("ls_fuse", T)
             h.set_option("ls_variant", lv)
             run({"hs_fuse": 4, "ls_fuse": T, "ls_variant": lv})
