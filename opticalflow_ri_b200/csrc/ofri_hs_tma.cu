@@ -436,6 +436,8 @@ static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& v
     cudaGetLastError();
     return false;
   }
+  if (C::CTAS > 1)   // two CTAs per SM only fit with the largest shared-memory carve-out
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   const int tiles_x = (ui.W + C::TW - 1) / C::TW, tiles_y_all = (ui.H + C::TH - 1) / C::TH;
   int tiles_y = tiles_y_all;
   int4 rows = make_int4(tiles_y_all, 0, 0, 0);

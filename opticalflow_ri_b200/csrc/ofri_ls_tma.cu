@@ -302,6 +302,8 @@ static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& v
     cudaGetLastError();
     return false;
   }
+  if (C::CTAS > 1)   // two CTAs per SM only fit with the largest shared-memory carve-out
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   const int tiles_x = (ui.W + C::TW - 1) / C::TW, tiles_y = (ui.H + C::TH - 1) / C::TH;
   const long ntiles = (long)tiles_x * tiles_y * ui.batch;
   if (ntiles > 0x7fffffffL) return false;
