@@ -1386,27 +1386,10 @@ int ofri_pyramidal_flow(ofri_handle h, const float* im1, const float* im2, int b
   rc = ensure_stage(h, 2 * slot_b);
   if (rc) return rc;
   cudaStream_t s = h->stream;
-  // Chunk schedule.  The H2D copy of the first chunk and the D2H copy of the last one have nothing to hide under, so
-  // with several chunks the first and the last are a quarter of the regular size (>= 4 pairs): compute starts after a
-  // quarter of the copy time and the tail copy is a quarter as long.  Pairs are independent: results do not change.
-  std::vector<std::pair<int, int>> sched;     // (first pair, pairs)
-  {
-    const int small = chunk / 4;
-    if (small >= 4 && batch >= 2 * chunk) {
-      sched.emplace_back(0, small);
-      int b0 = small;
-      while (batch - b0 > chunk + small) { sched.emplace_back(b0, chunk); b0 += chunk; }
-      const int rest = batch - b0;            // small < rest <= chunk + small
-      if (rest > small) { sched.emplace_back(b0, rest - small); b0 += rest - small; }
-      sched.emplace_back(b0, batch - b0);
-    } else {
-      for (int b0 = 0; b0 < batch; b0 += chunk) sched.emplace_back(b0, batch - b0 < chunk ? batch - b0 : chunk);
-    }
-  }
-  const int nchunks = (int)sched.size();
+  const int nchunks = (batch + chunk - 1) / chunk;   // (quarter-size first / last chunks were measured: no gain, profiles/)
   for (int c = 0; c < nchunks; ++c) {
-    const int b0 = sched[c].first;
-    const int nb = sched[c].second;
+    const int b0 = c * chunk;
+    const int nb = batch - b0 < chunk ? batch - b0 : chunk;
     const int slot = c & 1;
     char* base = h->stage + slot * slot_b;
     float* d_i1 = (float*)base;
