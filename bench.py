@@ -287,14 +287,17 @@ def run_ours(args):
                     "gpix_sweeps_per_s": sum(px_levels) * P * sweeps / (ms / 1e3) / 1e9,
                     "frac_in_unfused_bytes": sum(px_levels) * P * sweeps * bytes_px / (ms / 1e3) / 1e9 / peak}
 
-        precise_mode = h.get_option("hs_precise")
-        fast_levels = [px_fine] if precise_mode == 1 else ([px_coarse, px_fine] if precise_mode == 0 else [])
-        prec_levels = [px_coarse] if precise_mode == 1 else ([] if precise_mode == 0 else [px_coarse, px_fine])
+        # Which Horn-Schunck kernels ran is read off the stage timers: "hs_iterate" = fast kernel on the finest level,
+        # "hs_iterate_coarse" = fast kernel on the coarser level (hs_precise = 0, or 1 with the Liu-Shen refinement after
+        # it: this workload), "hs_iterate_precise" = reference-arithmetic kernel.
         kernels = [k for k in (
             entry("hs_tma_kernel<T=%d,R=8,NRG=8,fast> (persistent TMA-fed fused Horn-Schunck sweeps, finest level)" % T,
-                  "hs_iterate", 28.0, fast_levels, nl, HS_NITER),
-            entry("hs_tma_kernel<T=%d,R=4,NRG=8,precise> (same, reference arithmetic, coarse level)" % T,
-                  "hs_iterate_precise", 28.0, prec_levels, nl, HS_NITER),
+                  "hs_iterate", 28.0, [px_fine], nl, HS_NITER),
+            entry("hs_tma_kernel<T=%d,R=8,NRG=8,fast> (same kernel, coarse level 512x512: 15 %% of the tile area lies "
+                  "beyond the image border)" % T, "hs_iterate_coarse", 28.0, [px_coarse], nl, HS_NITER),
+            entry("hs_tma_kernel<T=%d,R=4,NRG=8,precise> (same, reference arithmetic)" % T,
+                  "hs_iterate_precise", 28.0, [px_coarse] if stage_ms.get("hs_iterate") else [px_coarse, px_fine], nl,
+                  HS_NITER),
             entry("ls_tma_kernel<T=%d,R=4,NRG=8> (persistent TMA-fed fused Liu-Shen sweeps, both levels)" % Tl,
                   "ls_iterate", 48.0, [px_coarse, px_fine], -(-LS_ITERS // Tl), LS_ITERS)) if k]
         if kernels:

@@ -50,7 +50,7 @@ struct ofri_ctx {
   LaunchCounter lc;
   // options
   int hs_fuse = 4, hs_variant = 24, ls_fuse = 2, ls_variant = 8, chunk_pairs = 0, timing = 0;
-  int hs_precise = 1;   // 0 = fast f32/FMA everywhere, 1 = reference arithmetic on the coarse pyramid levels, 2 = everywhere
+  int hs_precise = 1;   // 0 = fast f32/FMA everywhere, 1 = reference arithmetic where a coarse level's HS result reaches the warp unrefined (hs_needs_precise), 2 = everywhere
   // row-band (domain-decomposed) mode
   ofri::Comm* comm = nullptr;
   int hs_fuse_fast = 0;     // fuse factor of the fast-arithmetic Horn-Schunck launches only (0 = hs_fuse)
@@ -387,10 +387,24 @@ GaussTaps make_taps(const float* k, int n) {
   return t;
 }
 
+// hs_precise = 1: which Horn-Schunck solves run in the reference's exact arithmetic.  A rounding difference of ~1e-6 px in
+// a COARSE level's flow can flip the float32 rounding of a warp coordinate of the next level (GPOF:200-201: one ulp is
+// 3e-5 .. 6e-5 px at x ~ 500 .. 1000), which a weakly regularised fine-level solve follows 1:1 -- so a coarse
+// Horn-Schunck result that reaches the warp as it is must be exact.  When the Liu-Shen refinement runs after it on the
+// same level (the reference's optionalOFlowAlgoAdapter), its 60 sweeps contract the difference before the warp sees it:
+// measured final deviation of the all-fast path <= 1.2e-5 px for alpha = 0.5 .. 45 on the bundled pair and on synthetic
+// 1024^2 pairs, against up to 2e-2 px without the refinement (tools/precise_vs_fast.py, profiles/r1_precise_vs_fast.jsonl).
+bool hs_needs_precise(const ofri_params* p, bool coarse_level, bool is_main) {
+  if (!coarse_level) return false;
+  if (is_main && p->opt_algo.kind == OFRI_ALGO_LS) return false;   // refined by Liu-Shen before the warp
+  return true;
+}
+
 // one adapter compute() on level planes.  U/V state lives in ws.U[cur] / ws.V[cur]; returns the new cur.
 // uv_zero: the initial guess is identically zero (lets HS skip the copy of U0 for its error norm).
 int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws, const Img& im1, const Img& im2,
-                int Hl, int Wl, int cur, bool uv_zero, bool coarse_level, float* d_err, int err_stride) {
+                int Hl, int Wl, int cur, bool uv_zero, bool coarse_level, float* d_err, int err_stride,
+                bool finest = true) {
   cudaStream_t s = h->stream;
   Img U[2] = {view(ws.U[0], Hl, Wl), view(ws.U[1], Hl, Wl)};
   Img V[2] = {view(ws.V[0], Hl, Wl), view(ws.V[1], Hl, Wl)};
@@ -411,8 +425,10 @@ int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws
     {
       // rounding differences made on a coarse level are amplified by the warp + solve of the finer levels (up to
       // x50 for weakly regularised problems), so the coarse levels default to the reference's exact arithmetic
+      // (coarse_level = "a coarse level whose Horn-Schunck result reaches the warp unrefined": see hs_needs_precise)
       const bool precise = h->hs_precise >= 2 || (h->hs_precise == 1 && coarse_level);
-      Timed t(h, precise ? "hs_iterate_precise" : "hs_iterate");
+      // stage timers: the fast kernel on the finest level / on the coarser levels / the reference-arithmetic kernel
+      Timed t(h, precise ? "hs_iterate_precise" : (finest ? "hs_iterate" : "hs_iterate_coarse"));
       res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], a.hs_niter,
                               eff_hs_fuse(h, Hl, Wl, U[cur].batch, precise), h->hs_variant, precise, s, h->lc);
     }
@@ -615,10 +631,12 @@ int run_pyramid(ofri_handle h, const Img& im1, const Img& im2, const ofri_params
         }
       }
       float* e_main = d_err ? d_err + 2 * call_index : nullptr;
-      cur = run_adapter(h, p->main_algo, call_index, ws, work1, work2, Hl, Wl, cur, uv_zero, !last, e_main, err_stride);
+      cur = run_adapter(h, p->main_algo, call_index, ws, work1, work2, Hl, Wl, cur, uv_zero, hs_needs_precise(p, !last, true),
+                        e_main, err_stride, last);
       if (has_opt) {
         float* e_opt = d_err ? d_err + 2 * call_index + 1 : nullptr;
-        cur = run_adapter(h, p->opt_algo, call_index, ws, o1, o2, Hl, Wl, cur, false, !last, e_opt, err_stride);
+        cur = run_adapter(h, p->opt_algo, call_index, ws, o1, o2, Hl, Wl, cur, false, hs_needs_precise(p, !last, false), e_opt,
+                          err_stride, last);
       }
       Ucur = view(ws.U[cur], Hl, Wl);
       Vcur = view(ws.V[cur], Hl, Wl);
@@ -885,7 +903,7 @@ __global__ void band_reach_kernel(Img vs, float limit, int* flag) {
 
 int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs& ws, const Img& im1, const Img& im2,
                        const BandLevel& bl, int E, int cur, bool uv_zero, bool coarse_level, float* d_err,
-                       int* comm_rc) {
+                       int* comm_rc, bool finest = true) {
   cudaStream_t s = h->stream;
   ofri::Comm* c = h->comm;
   const int rows = bl.ext1 - bl.ext0, Wl = bl.Wl;
@@ -909,7 +927,7 @@ int run_adapter_banded(ofri_handle h, const ofri_algo& a, int call_index, BandWs
     int res;
     {
       const bool precise = h->hs_precise >= 2 || (h->hs_precise == 1 && coarse_level);
-      Timed t(h, precise ? "hs_iterate_precise" : "hs_iterate");
+      Timed t(h, precise ? "hs_iterate_precise" : (finest ? "hs_iterate" : "hs_iterate_coarse"));
       const int niter = a.hs_niter;
       const int c0 = cur;
       // every E sweeps: the tiles producing the rows the neighbours need run first, the exchange of the buffer just
@@ -1149,11 +1167,13 @@ int run_pyramid_banded(ofri_handle h, const float* d_im1, const float* d_im2, in
       launch_gauss(n2, gt, o2, taps_opt, s, h->lc);
     }
     float* e_main = d_err ? d_err + 2 * l : nullptr;
-    cur = run_adapter_banded(h, p->main_algo, l, ws, work1, work2, bl, bp.E, cur, true, !last, e_main, &comm_rc);
+    cur = run_adapter_banded(h, p->main_algo, l, ws, work1, work2, bl, bp.E, cur, true, hs_needs_precise(p, !last, true), e_main,
+                             &comm_rc, last);
     if (comm_rc) return comm_rc;
     if (has_opt) {
       float* e_opt = d_err ? d_err + 2 * l + 1 : nullptr;
-      cur = run_adapter_banded(h, p->opt_algo, l, ws, o1, o2, bl, bp.E, cur, false, !last, e_opt, &comm_rc);
+      cur = run_adapter_banded(h, p->opt_algo, l, ws, o1, o2, bl, bp.E, cur, false, hs_needs_precise(p, !last, false), e_opt,
+                               &comm_rc, last);
       if (comm_rc) return comm_rc;
     }
     Ucur = view(ws.U[cur], rows, Wl);

@@ -394,6 +394,40 @@ def test_driver_baseline_configs_bundled(h, ofri, configs_bundled, bundled_pair,
     assert de <= TOL_EPE, de
 
 
+@pytest.mark.parametrize("alpha", [1.0, 5.0, 21.0])
+def test_hs_precise_rule_liu_shen_contracts_coarse_rounding(h, ofri, bundled_pair, alpha):
+    """hs_precise = 1 (default) runs a coarse level's Horn-Schunck solve in the fast arithmetic when the Liu-Shen
+    refinement follows on the same level, and in the reference arithmetic when its result reaches the warp as it is.
+    Against the reference arithmetic on every level (hs_precise = 2): <= 2e-5 px either way on the bundled pair (a
+    fifth of the 1e-4 px bar), whereas the fast arithmetic everywhere WITHOUT the refinement is off by more than the bar
+    for weak regularisation -- which is why the rule exists."""
+    I0, I1 = bundled_pair
+    mk_ls = lambda: ofri.make_params(ofri.hs_algo([alpha, alpha], 200), ofri.ls_algo(5), filter_sigma=3.4,
+                                     filter_opt_sigma=0.48, pyramid_levels=2, **HS_DEF)
+    mk_hs = lambda: ofri.make_params(ofri.hs_algo([alpha, alpha], 200), filter_sigma=3.4, pyramid_levels=2, **HS_DEF)
+    try:
+        res = {}
+        for mode in (2, 1, 0):
+            h.set_option("hs_precise", mode)
+            h.set_option("timing", 1)
+            res["ls", mode] = h.pyramidal_flow(I0, I1, mk_ls())
+            stages_ls = dict(h.stage_timings())
+            res["hs", mode] = h.pyramidal_flow(I0, I1, mk_hs())
+            stages_hs = dict(h.stage_timings())
+            if mode == 1:      # which kernels ran: no precise sweeps with the refinement, precise coarse level without
+                assert stages_ls.get("hs_iterate_precise", 0.0) == 0.0 and stages_ls.get("hs_iterate", 0.0) > 0.0
+                assert stages_hs.get("hs_iterate_precise", 0.0) > 0.0
+        dev = lambda k, m: max(float(np.max(np.abs(res[k, m][i] - res[k, 2][i]))) for i in (0, 1))
+        print("\nalpha %g: HS+LS default %.3g, HS default %.3g, HS all-fast %.3g px" % (alpha, dev("ls", 1), dev("hs", 1),
+                                                                                      dev("hs", 0)))
+        assert dev("ls", 1) <= 2e-5 and dev("hs", 1) <= 2e-5
+        if alpha <= 1.0:
+            assert dev("hs", 0) > TOL_FLOW
+    finally:
+        h.set_option("hs_precise", 1)
+        h.set_option("timing", 0)
+
+
 def test_auto_fuse_is_invisible(h, ofri, configs_small):
     """Launches that cannot fill the GPU fuse deeper (8 HS / 4 LS sweeps per launch): same bits."""
     s = configs_small

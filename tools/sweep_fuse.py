@@ -42,13 +42,13 @@ def run(tag):
     h.synchronize()
     st = h.stage_timings()
     tot = e0.elapsed_time(e1)
-    hs = st.get("hs_iterate", 0.0) + st.get("hs_iterate_precise", 0.0)
+    hs = st.get("hs_iterate", 0.0) + st.get("hs_iterate_coarse", 0.0) + st.get("hs_iterate_precise", 0.0)
     ls = st.get("ls_iterate", 0.0)
     out = dict(tag, total_ms=round(tot, 2), pairs_per_s=round(P / (tot / 1e3), 1),
                hs_ms=round(hs, 2), hs_gpix_it_s=round(px * 600 / (hs / 1e3) / 1e9, 1) if hs else None,
                hs_GBs_per_T1=round(28 * px * 600 / (hs / 1e3) / 1e9, 1) if hs else None,
                ls_ms=round(ls, 2), ls_gpix_it_s=round(px * 60 / (ls / 1e3) / 1e9, 1) if ls else None,
-               other_ms=round(sum(x for k, x in st.items() if k not in ("hs_iterate", "hs_iterate_precise", "ls_iterate")), 2),
+               other_ms=round(sum(x for k, x in st.items() if k not in ("hs_iterate", "hs_iterate_coarse", "hs_iterate_precise", "ls_iterate")), 2),
                stages={k: round(x, 2) for k, x in st.items()})
     print(json.dumps(out), flush=True)
 
