@@ -890,7 +890,6 @@ int band_exchange_uv(ofri_handle h, const Img& U, const Img& V, int o0, int o1, 
   float* rd[2] = {dn ? U.p + (long)o1 * pitch : U.p, dn ? V.p + (long)o1 * pitch : V.p};
   if (c->exchange(2, su, ru, sd, rd, (size_t)E * pitch, stream))
     return fail(h, OFRI_ERR_COMM, "ghost-row exchange failed: %s", c->error());
-  h->lc.n += 0;
   return OFRI_OK;
 }
 
