@@ -396,7 +396,10 @@ GaussTaps make_taps(const float* k, int n) {
 // 1024^2 pairs, against up to 2e-2 px without the refinement (tools/precise_vs_fast.py, profiles/r1_precise_vs_fast.jsonl).
 bool hs_needs_precise(const ofri_params* p, bool coarse_level, bool is_main) {
   if (!coarse_level) return false;
-  if (is_main && p->opt_algo.kind == OFRI_ALGO_LS) return false;   // refined by Liu-Shen before the warp
+  // refined by Liu-Shen before the warp -- with the reference's own stopping parameters (60 sweeps, 1e-8: LS:141), the
+  // only ones the contraction was measured for; a shortened refinement keeps the exact arithmetic
+  if (is_main && p->opt_algo.kind == OFRI_ALGO_LS && p->opt_algo.ls_maxiter >= 60 && p->opt_algo.ls_tol <= 1e-8)
+    return false;
   return true;
 }
 
