@@ -193,16 +193,24 @@ __device__ __forceinline__ void hs_tma_tile(const TmTile& tl, int W, int H, cons
     }
   }
   // ---- interior cells -> HBM ------------------------------------------------------------------------------------------------
-  float* gU = uo.p + (long)tl.b * uo.stride;
-  float* gV = vo.p + (long)tl.b * vo.stride;
+  // strip rows j with T <= r0 + j < SH - T inside the image; one 64-bit base address per plane and tile, then + pitch
+  // per row (the per-row 64-bit index arithmetic it replaces was 0.7 of a sweep's instructions per tile)
   const bool in_cols = (sx >= HX) && (sx < SW - HX) && (gx < W);
+  const int j_lo = T - r0 > 0 ? T - r0 : 0;
+  int j_hi = SH - T - r0;
+  if (H - gy0 < j_hi) j_hi = H - gy0;
+  float* pU = uo.p + ((long)tl.b * uo.stride + (long)gy0 * uo.pitch + gx);
+  float* pV = vo.p + ((long)tl.b * vo.stride + (long)gy0 * vo.pitch + gx);
+  const long qU = uo.pitch, qV = vo.pitch;
+  if (in_cols) {
 #pragma unroll
-  for (int j = 0; j < R; ++j) {
-    const int sy = r0 + j, gy = gy0 + j;
-    if (in_cols && (sy >= T) && (sy < SH - T) && (gy < H)) {
-      const long go = (long)gy * uo.pitch + gx;
-      *reinterpret_cast<float4*>(gU + go) = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
-      *reinterpret_cast<float4*>(gV + go) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+    for (int j = 0; j < R; ++j) {
+      if (j >= j_lo && j < j_hi) {
+        *reinterpret_cast<float4*>(pU) = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
+        *reinterpret_cast<float4*>(pV) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+      }
+      pU += qU;
+      pV += qV;
     }
   }
   __syncthreads();   // the exchange buffers are free for the next tile
@@ -334,9 +342,13 @@ __device__ __forceinline__ void hs_tma_tile_precise(const TmTile& tl, int W, int
     tma_load_3d(dst + 3 * C::PLANE * 4, mB, nx.x0, nx.y0, nx.b, bar);
     tma_load_3d(dst + 4 * C::PLANE * 4, mC, nx.x0, nx.y0, nx.b, bar);
   }
-  float* gU = uo.p + (long)tl.b * uo.stride;
-  float* gV = vo.p + (long)tl.b * vo.stride;
   const bool in_cols = (sx >= HX) && (sx < SW - HX) && (gx < W);
+  const int j_lo = T - r0 > 0 ? T - r0 : 0;          // strip rows stored: T <= r0 + j < SH - T, inside the image
+  int j_hi = SH - T - r0;
+  if (H - gy0 < j_hi) j_hi = H - gy0;
+  float* const pU0 = uo.p + ((long)tl.b * uo.stride + (long)gy0 * uo.pitch + gx);
+  float* const pV0 = vo.p + ((long)tl.b * vo.stride + (long)gy0 * vo.pitch + gx);
+  const long qU = uo.pitch, qV = vo.pitch;
 #pragma unroll 1
   for (int s = 0; s < T; ++s) {
     const int cur = s & 1;
@@ -357,13 +369,9 @@ __device__ __forceinline__ void hs_tma_tile_precise(const TmTile& tl, int W, int
       for (int q = 0; q < 4; ++q) { u[j][q] = (double)ou[q]; v[j][q] = (double)ov[q]; }
       if (j == 0) { eu0 = make_float4(ou[0], ou[1], ou[2], ou[3]); ev0 = make_float4(ov[0], ov[1], ov[2], ov[3]); }
       if (j == R - 1) { eu1 = make_float4(ou[0], ou[1], ou[2], ou[3]); ev1 = make_float4(ov[0], ov[1], ov[2], ov[3]); }
-      if (last) {                                  // interior cells -> HBM straight from the float32 results
-        const int sy = r0 + j, gy = gy0 + j;
-        if (in_cols && (sy >= T) && (sy < SH - T) && (gy < H)) {
-          const long go = (long)gy * uo.pitch + gx;
-          *reinterpret_cast<float4*>(gU + go) = make_float4(ou[0], ou[1], ou[2], ou[3]);
-          *reinterpret_cast<float4*>(gV + go) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-        }
+      if (last && in_cols && j >= j_lo && j < j_hi) {   // interior cells -> HBM straight from the float32 results
+        *reinterpret_cast<float4*>(pU0 + j * qU) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+        *reinterpret_cast<float4*>(pV0 + j * qV) = make_float4(ov[0], ov[1], ov[2], ov[3]);
       }
     }
     if (!last) {

@@ -212,8 +212,9 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
     eg.bot_j = edge ? (H - 1) - gy0 : -1000;
     const bool in_cols = (sx >= HX) && (sx < SW - HX);
     const int own_lo_ = band.own_lo, own_hi_ = band.own_hi;
-    float* gU = uo.p + (long)tl.b * uo.stride;
-    float* gV = vo.p + (long)tl.b * vo.stride;
+    float* const pU0 = uo.p + ((long)tl.b * uo.stride + (long)gy0 * uo.pitch + gx);   // + j * pitch per strip row
+    float* const pV0 = vo.p + ((long)tl.b * vo.stride + (long)gy0 * vo.pitch + gx);
+    const long qU = uo.pitch, qV = vo.pitch;
 
     auto sweep_all = [&](auto edge_tag) {
       constexpr bool EDGE = decltype(edge_tag)::value;
@@ -253,9 +254,8 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
             }
           }
           if (last && own && gx < W) {
-            const long go = (long)gy * uo.pitch + gx;
-            *reinterpret_cast<float4*>(gU + go) = make_float4(ou[0], ou[1], ou[2], ou[3]);
-            *reinterpret_cast<float4*>(gV + go) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            *reinterpret_cast<float4*>(pU0 + j * qU) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+            *reinterpret_cast<float4*>(pV0 + j * qV) = make_float4(ov[0], ov[1], ov[2], ov[3]);
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) { u[j][q] = ou[q]; v[j][q] = ov[q]; }
