@@ -1,6 +1,7 @@
 """Row-band domain decomposition (BASELINE configs[4]) on ONE GPU: N virtual bands driven by N host threads
 over the library's local communicator must reproduce the single-band result BIT FOR BIT on every owned row -- ghost
-frames, ghost-row exchanges, global-coordinate resample / warp, all-reduced maxima and residuals, all-gathered spline."""
+frames, ghost-row exchanges, global-coordinate resample / warp, all-reduced maxima and residuals, and the spline up-sample
+from a halo of the coarse flow (windowed column solve; all-gather for bands thinner than the halo)."""
 import numpy as np
 import pytest
 
