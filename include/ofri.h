@@ -116,6 +116,10 @@ OFRI_API int ofri_get_option(ofri_handle h, const char* key, int* value);
 OFRI_API int64_t ofri_launch_count(ofri_handle h);
 /* device-time breakdown of the last host-level call: names[i] -> ms[i]; returns the number of entries */
 OFRI_API int ofri_stage_timings(ofri_handle h, const char** names, float* ms, int max_entries);
+/* profiling hook (no reference counterpart): SM cycles thread 0 of every CTA of the persistent sweep kernels spent per
+ * phase since the last read; family 0 = Horn-Schunck kernel, 1 = Liu-Shen kernel; out8[8].  All zero unless the
+ * library was built with -DOFRI_PHASE_TIMING (tools/phase_timing.py builds that variant as libofri_phase.so). */
+OFRI_API int ofri_debug_phase_read(ofri_handle h, int family, unsigned long long* out8);
 
 /* ---- whole path: replaces genericPyramidalOpticalFlow(...) (GenericPyramidalOpticalFlow.py:238-416) and
  *      GenericPyramidalOpticalFlowWrapper.calculateFlow (GenericPyramidalOpticalFlowWrapper.py:41-64) --------

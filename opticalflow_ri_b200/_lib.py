@@ -5,7 +5,8 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libofri.so")
+# OFRI_LIB: load another build of the same library (tools/phase_timing.py: libofri_phase.so); still CUDA-only
+LIB_PATH = os.environ.get("OFRI_LIB") or os.path.join(HERE, "libofri.so")
 HEADER = os.path.join(HERE, "..", "include", "ofri.h")
 
 OFRI_MAX_GAUSS_TAPS = 129
@@ -58,6 +59,7 @@ _SIGNATURES = {
     "ofri_get_option": (C.c_int, [_H, C.c_char_p, C.POINTER(C.c_int)]),
     "ofri_launch_count": (C.c_int64, [_H]),
     "ofri_stage_timings": (C.c_int, [_H, C.POINTER(C.c_char_p), _fp, C.c_int]),
+    "ofri_debug_phase_read": (C.c_int, [_H, C.c_int, C.POINTER(C.c_ulonglong)]),
     "ofri_pyramidal_flow": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Params),
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "ofri_pyramidal_flow_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Params),

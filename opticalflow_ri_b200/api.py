@@ -157,6 +157,13 @@ class Handle:
         n = self._L.ofri_stage_timings(self._h, names, ms, 64)
         return {names[i].decode(): float(ms[i]) for i in range(n)}
 
+    def phase_cycles(self, family):
+        """ofri_debug_phase_read: per-phase SM cycles of the persistent kernels (0 = HS, 1 = LS) since the last read;
+        all zero unless the loaded library is the -DOFRI_PHASE_TIMING build."""
+        out = (C.c_ulonglong * 8)()
+        self._check(self._L.ofri_debug_phase_read(self._h, int(family), out))
+        return [int(x) for x in out]
+
     # -- whole path ---------------------------------------------------------------------------------------------
     def pyramidal_flow(self, im1, im2, params, want_errors=False):
         a, single = _batched(im1)

@@ -30,16 +30,21 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, phase_timing=False):
+    """phase_timing: the profiling variant libofri_phase.so (-DOFRI_PHASE_TIMING: per-phase clock64() accumulators in the
+    persistent sweep kernels; tools/phase_timing.py) -- never loaded by the product path."""
+    lib = os.path.join(HERE, "libofri_phase.so") if phase_timing else LIB
+    if not force and not phase_timing and not needs_build():
         return LIB
     nvcc = _nvcc()
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build", "phase") if phase_timing else os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        o = os.path.join(bdir, s.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + (["-DOFRI_PHASE_TIMING"] if phase_timing else []) + \
+            (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for s, p in procs:
@@ -48,10 +53,10 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % s)
-    cmd = [nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
+    cmd = [nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-ldl"]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, phase_timing="--phase" in sys.argv))

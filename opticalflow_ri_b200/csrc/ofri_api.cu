@@ -634,11 +634,14 @@ int run_pyramid(ofri_handle h, const Img& im1, const Img& im2, const ofri_params
         }
       }
       float* e_main = d_err ? d_err + 2 * call_index : nullptr;
-      cur = run_adapter(h, p->main_algo, call_index, ws, work1, work2, Hl, Wl, cur, uv_zero, hs_needs_precise(p, !last, true),
+      // "coarse" for the arithmetic rule = a later warp consumes this result: every level but the last, and on the last
+      // level every k but the last (the k-loop re-warps by the accumulated flow, GPOF:392-404)
+      const bool feeds_warp = !last || (k + 1 < KL && p->warping);
+      cur = run_adapter(h, p->main_algo, call_index, ws, work1, work2, Hl, Wl, cur, uv_zero, hs_needs_precise(p, feeds_warp, true),
                         e_main, err_stride, last);
       if (has_opt) {
         float* e_opt = d_err ? d_err + 2 * call_index + 1 : nullptr;
-        cur = run_adapter(h, p->opt_algo, call_index, ws, o1, o2, Hl, Wl, cur, false, hs_needs_precise(p, !last, false), e_opt,
+        cur = run_adapter(h, p->opt_algo, call_index, ws, o1, o2, Hl, Wl, cur, false, hs_needs_precise(p, feeds_warp, false), e_opt,
                           err_stride, last);
       }
       Ucur = view(ws.U[cur], Hl, Wl);
@@ -761,8 +764,9 @@ int finish(ofri_handle h) {
 //   * ghost rows of (U, V) are refreshed from the neighbours' owned rows every E sweeps (Comm::exchange);
 //   * Liu-Shen's image maxima (LS:96-97) and per-sweep residual sums (LS:79, 141) and Horn-Schunck's error sums
 //     (HS:100) are all-reduced, so every rank takes the same decisions and reports the same scalars;
-//   * the spline up-sample solves along whole columns: the owned coarse rows are all-gathered and every rank solves the
-//     (small) coarse system redundantly, then evaluates only its own band;
+//   * the spline up-sample solves along whole columns: a rank exchanges a halo of the coarse flow with its neighbours
+//     and solves only the WINDOW of every column its band needs (windowed Thomas solve, ofri_spline.cuh: bit-identical
+//     to the full solve); bands thinner than the halo fall back to an all-gather + redundant full solve;
 //   * Pillow's resample and the warp use GLOBAL row coordinates (tap tables of the whole image; float32 rounding of
 //     y +- v/2 depends on the magnitude of y).
 // Owned rows are therefore bit-identical to the single-GPU result (tested with N virtual bands on one GPU).
@@ -1349,6 +1353,15 @@ int ofri_get_option(ofri_handle h, const char* key, int* value) {
 }
 int64_t ofri_launch_count(ofri_handle h) { return h ? h->lc.n : 0; }
 
+int ofri_debug_phase_read(ofri_handle h, int family, unsigned long long* out8) {
+  OFRI_ENTER(h);
+  if (!out8 || family < 0 || family > 1) return fail(h, OFRI_ERR_INVALID, "bad arguments");
+  OFRI_CUDA(h, cudaDeviceSynchronize());
+  if (family == 0) ofri::hs_tma_phase_read(out8);
+  else ofri::ls_tma_phase_read(out8);
+  return OFRI_OK;
+}
+
 int ofri_stage_timings(ofri_handle h, const char** names, float* ms, int max_entries) {
   if (!h) return 0;
   int n = 0;
@@ -1431,8 +1444,8 @@ int ofri_pyramidal_flow(ofri_handle h, const float* im1, const float* im2, int b
     plan_workspace(bump, nb, H, W, p, &ws);
     rc = run_pyramid(h, dense(d_i1, nb, H, W), dense(d_i2, nb, H, W), p, dense(d_u, nb, H, W), dense(d_v, nb, H, W),
                      err_out ? d_e : nullptr, ws);
-    if (rc) return rc;
-    if ((rc = check_lsw_flag(h, p, ws))) return rc;
+    if (!rc) rc = check_lsw_flag(h, p, ws);
+    if (rc) return drain_streams(h, rc);
     OFRI_CUDA(h, cudaEventRecord(h->ev_comp[slot], s));
     OFRI_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
     OFRI_CUDA(h, cudaMemcpyAsync(u_out + b0 * plane, d_u, plane_b * nb, cudaMemcpyDeviceToHost, h->s_out));

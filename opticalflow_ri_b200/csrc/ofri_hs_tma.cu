@@ -151,6 +151,7 @@ __device__ __forceinline__ void hs_tma_tile(const TmTile& tl, int W, int H, cons
   *reinterpret_cast<float4*>(X(0, 0, rg + 1, 1)) = make_float4(u[R - 1][0], u[R - 1][1], u[R - 1][2], u[R - 1][3]);
   *reinterpret_cast<float4*>(X(0, 1, rg + 1, 1)) = make_float4(v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3]);
   __syncthreads();   // every thread has drained the staging buffer; exchange buffer 0 is complete
+  OFRI_PH(2);
   // ---- prefetch the CTA's next tile under this tile's arithmetic ---------------------------------------------------------
   if (issue_next && threadIdx.x == 0) {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads above -> async-proxy writes below
@@ -192,6 +193,7 @@ __device__ __forceinline__ void hs_tma_tile(const TmTile& tl, int W, int H, cons
       __syncthreads();
     }
   }
+  OFRI_PH(3);
   // ---- interior cells -> HBM ------------------------------------------------------------------------------------------------
   // strip rows j with T <= r0 + j < SH - T inside the image; one 64-bit base address per plane and tile, then + pitch
   // per row (the per-row 64-bit index arithmetic it replaces was 0.7 of a sweep's instructions per tile)
@@ -214,6 +216,7 @@ __device__ __forceinline__ void hs_tma_tile(const TmTile& tl, int W, int H, cons
     }
   }
   __syncthreads();   // the exchange buffers are free for the next tile
+  OFRI_PH(4);
 }
 
 
@@ -332,6 +335,7 @@ __device__ __forceinline__ void hs_tma_tile_precise(const TmTile& tl, int W, int
   *reinterpret_cast<float4*>(X(0, 0, rg + 1, 1)) = eu1;
   *reinterpret_cast<float4*>(X(0, 1, rg + 1, 1)) = ev1;
   __syncthreads();
+  OFRI_PH(2);
   if (issue_next && threadIdx.x == 0) {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     mbar_expect_tx(bar, (unsigned)C::STAGE_BYTES);
@@ -383,7 +387,9 @@ __device__ __forceinline__ void hs_tma_tile_precise(const TmTile& tl, int W, int
       __syncthreads();
     }
   }
+  OFRI_PH(3);
   __syncthreads();
+  OFRI_PH(4);
 }
 
 template <int T, int R, int NRG, bool PRECISE>
@@ -413,6 +419,7 @@ hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CU
     tma_load_3d(dst + 4 * C::PLANE * 4, &mC, t0.x0, t0.y0, t0.b, bar);
   }
   __syncthreads();
+  OFRI_PH_INIT;
   unsigned phase = 0;
   for (; tile < ntiles; tile += gridDim.x) {
     const TmTile tl = tm_decode<T, R, NRG>(tile, tiles_x, tiles_y, rows);
@@ -420,14 +427,18 @@ hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CU
     const bool has_next = nt < ntiles;
     const TmTile nx = tm_decode<T, R, NRG>(has_next ? nt : tile, tiles_x, tiles_y, rows);
     const bool edge = (tl.x0 < 0) || (tl.x0 + C::SW > W) || (tl.y0 < 0) || (tl.y0 + C::SH > H);   // CTA-uniform
+    OFRI_PH(5);
     mbar_wait(bar, phase);
     phase ^= 1;
+    OFRI_PH(0);
     if (edge) hs_tma_ghosts<T, R, NRG>(tl, W, H, stage);
+    OFRI_PH(1);
     if constexpr (PRECISE)
       hs_tma_tile_precise<T, R, NRG>(tl, W, H, uo, vo, stage, xbuf, has_next, nx, &mU, &mV, &mA, &mB, &mC, bar, alpha2);
     else
       hs_tma_tile<T, R, NRG>(tl, W, H, uo, vo, stage, xbuf, has_next, nx, &mU, &mV, &mA, &mB, &mC, bar);
   }
+  OFRI_PH_FLUSH;
 }
 
 template <int T, int R, int NRG, bool PRECISE>
@@ -510,5 +521,9 @@ bool launch_hs_tma(int T, int variant, bool precise, const Img& ui, const Img& v
     default: return false;
   }
 }
+
+// phase-timing table of this translation unit (all zero unless built with -DOFRI_PHASE_TIMING): cycles of thread 0 of
+// every CTA in [0] mbarrier wait, [1] ghost fix-up, [2] staging -> registers, [3] sweeps, [4] stores, [5] tile decode
+void hs_tma_phase_read(unsigned long long* out) { OFRI_PH_READ(out); }
 
 }  // namespace ofri

@@ -176,6 +176,10 @@ Comm* make_local_comm(LocalGroup* g, int rank, std::string* err);
 bool launch_ls_tma(int T, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const LsPlanes& co, float hpar,
                    int k0, int maxiter, double tol, double* errs, const LsBand& band, cudaStream_t s, int variant = 8);
 
+// cycles per phase of the persistent kernels since the last read (all zero unless built with -DOFRI_PHASE_TIMING)
+void hs_tma_phase_read(unsigned long long* out8);
+void ls_tma_phase_read(unsigned long long* out8);
+
 const char* kernel_build_info();
 
 }  // namespace ofri

@@ -131,6 +131,7 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
   auto X = [&](int buf, int plane, int g, int which) -> float* {
     return xbuf + ((buf * 2 + plane) * C::XROWS + 2 * g + which - 1) * SW + sx;   // (g = 0: which = 1; g = NRG + 1: which = 0)
   };
+  OFRI_PH_INIT;
   unsigned phase = 0;
   int acc_pair = -1;      // pair whose residual sums sit in sh->acc (CTA-uniform)
   auto flush = [&]() {    // all threads; ends with a barrier
@@ -156,8 +157,10 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
     }
     if (tid == 0)
       sh->stop = (k0 > 0 && ls_stopped_before(errs + (long)tl.b * maxiter * 2, k0, tol, band.npix, T)) ? 1 : 0;
+    OFRI_PH(5);
     mbar_wait(bar, phase);
     phase ^= 1;
+    OFRI_PH(0);
     // ---- staging buffer -> registers ---------------------------------------------------------------------------------
     const int gx = tl.x0 + sx, gy0 = tl.y0 + r0;
     float u[R][4], v[R][4];
@@ -196,6 +199,7 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
     *reinterpret_cast<float4*>(X(0, 0, rg + 1, 1)) = make_float4(u[R - 1][0], u[R - 1][1], u[R - 1][2], u[R - 1][3]);
     *reinterpret_cast<float4*>(X(0, 1, rg + 1, 1)) = make_float4(v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3]);
     __syncthreads();   // staging buffer drained, exchange buffer 0 complete, stop flag visible
+    OFRI_PH(2);
     if (has_next && tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       issue(lt_decode<T, R, NRG>(nt, tiles_x, tiles_y));
@@ -284,9 +288,12 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
     };
     if (edge) sweep_all(std::true_type{});
     else sweep_all(std::false_type{});
+    OFRI_PH(3);
     __syncthreads();   // exchange buffers free for the next tile
+    OFRI_PH(4);
   }
   flush();
+  OFRI_PH_FLUSH;
 }
 
 template <int T, int R, int NRG>
@@ -338,5 +345,9 @@ bool launch_ls_tma(int T, const Img& ui, const Img& vi, const Img& uo, const Img
     default: return false;
   }
 }
+
+// phase-timing table (see ofri_hs_tma.cu): [0] mbarrier wait, [2] staging -> registers, [3] sweeps + stores, [4] final
+// barrier, [5] per-tile bookkeeping (decode, residual flush, stop flag)
+void ls_tma_phase_read(unsigned long long* out) { OFRI_PH_READ(out); }
 
 }  // namespace ofri

@@ -62,4 +62,26 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map
       : "memory");
 }
 
+
+// ---- optional phase timing of the persistent kernels (tools/phase_timing.py; built with -DOFRI_PHASE_TIMING into a
+// separate libofri_phase.so, never into the product library): thread 0 of every CTA accumulates clock64() deltas per
+// phase in shared memory and adds them to the translation unit's table (g_phase_acc) at exit.
+#define OFRI_NPHASE 8
+#if defined(OFRI_PHASE_TIMING)
+__shared__ long long ph_acc_[OFRI_NPHASE];
+__shared__ long long ph_last_;
+static __device__ unsigned long long g_phase_acc[OFRI_NPHASE];
+#define OFRI_PH_INIT do { if (threadIdx.x == 0) { for (int i_ = 0; i_ < OFRI_NPHASE; ++i_) ph_acc_[i_] = 0; ph_last_ = clock64(); } } while (0)
+#define OFRI_PH(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); ph_acc_[i] += t_ - ph_last_; ph_last_ = t_; } } while (0)
+#define OFRI_PH_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < OFRI_NPHASE; ++i_) \
+  atomicAdd(&g_phase_acc[i_], (unsigned long long)ph_acc_[i_]); } while (0)
+#define OFRI_PH_READ(out) do { cudaMemcpyFromSymbol(out, g_phase_acc, sizeof(unsigned long long) * OFRI_NPHASE); \
+  unsigned long long z_[OFRI_NPHASE] = {0}; cudaMemcpyToSymbol(g_phase_acc, z_, sizeof(z_)); } while (0)
+#else
+#define OFRI_PH_INIT do { } while (0)
+#define OFRI_PH(i) do { } while (0)
+#define OFRI_PH_FLUSH do { } while (0)
+#define OFRI_PH_READ(out) do { for (int i_ = 0; i_ < OFRI_NPHASE; ++i_) (out)[i_] = 0; } while (0)
+#endif
+
 }  // namespace ofri

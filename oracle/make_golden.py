@@ -249,7 +249,7 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
-if __name__ == "__main__" and "--lswarp" not in sys.argv:
+if __name__ == "__main__" and "--lswarp" not in sys.argv and "--big" not in sys.argv and "--extra" not in sys.argv:
     main()
 
 
@@ -300,3 +300,61 @@ def main_lswarp():
 
 if __name__ == "__main__" and "--lswarp" in sys.argv:
     main_lswarp()
+
+
+def main_big(which):
+    """`python oracle/make_golden.py --big 1024|2048`: the reference's flow for one seeded synthetic PIV pair at the frame
+    sizes BASELINE names (config 4: 1024 x 1024; the row-band path: 2048 x 2048), full EX3 parameters
+    (examples/LiuSE_PyHSchunck_Fs3_4_PyrLvls2.py:133-139: FILTER 3.4, HS alphas [21, 45] x 600 sweeps, 2 levels,
+    FILTER_OPT 0.48, Liu-Shen h = 5).  Inputs are stored as uint8 (what the generator renders), outputs as float32.
+    ~1 min / ~4 min of single-core time; written to tests/golden/big_<size>.npz."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from opticalflow_ri_b200.synthetic import synthetic_piv_pair          # host-side generator, not the compute path
+    GPOF, HS, LS, GF, GKBE, WRAP = import_reference()
+    n = int(which)
+    seed = {1024: 0, 2048: 1}.get(n, n)
+    a, b = synthetic_piv_pair(n, n, seed)
+    import time
+    t0 = time.time()
+    with quiet():
+        U, V = GPOF.genericPyramidalOpticalFlow(a.copy(), b.copy(), 3.4, HS.HSOpticalFlowAlgoAdapter([21, 45], 600), 2, 1,
+                                                0.48, LS.LiuShenOpticalFlowAlgoAdapter(5))
+    dt = time.time() - t0
+    out = os.path.join(OUT, "big_%d.npz" % n)
+    np.savez_compressed(out, im0=a.astype(np.uint8), im1=b.astype(np.uint8), U=np.float32(U), V=np.float32(V),
+                        seed=np.int64(seed), ref_seconds=np.float64(dt))
+    print(out, os.path.getsize(out), "reference took %.1f s" % dt)
+
+
+def main_extra():
+    """`python oracle/make_golden.py --extra`: additional small whole-driver cases (tests/golden/configs_extra.npz):
+    Horn-Schunck only, kLevels = 2 with a weak regularisation (alpha = 1): the k-loop re-warps the level images by the
+    UNREFINED Horn-Schunck result of the previous k (GPOF:392-404), the case where a float32 coordinate flip in the
+    warp is followed 1:1 by the next solve."""
+    GPOF, HS, LS, GF, GKBE, WRAP = import_reference()
+    a8, b8 = load_bundled()
+    I0, I1 = a8.astype(np.float32), b8.astype(np.float32)
+    c0 = np.ascontiguousarray(I0[150:350, 100:332])
+    c1 = np.ascontiguousarray(I1[150:350, 100:332])
+    g = {"crop0": c0, "crop1": c1}
+
+    def run(im0, im1, FILTER, main, L=1, k=1, FILTER_OPT=None, opt=None, **kw):
+        with quiet():
+            U, V = GPOF.genericPyramidalOpticalFlow(im0, im1, FILTER, main, L, k, FILTER_OPT, opt, **kw)
+        return np.asarray(U, dtype=np.float32), np.asarray(V, dtype=np.float32)
+
+    U, V = run(c0, c1, 3.4, HS.HSOpticalFlowAlgoAdapter([1.0, 1.0, 1.0, 1.0], 100), 2, 2)
+    g["k2a1_U"], g["k2a1_V"] = U, V
+    U, V = run(c0, c1, 3.4, HS.HSOpticalFlowAlgoAdapter([1.0, 1.0], 100), 1, 2)
+    g["l1k2a1_U"], g["l1k2a1_V"] = U, V
+    U, V = run(c0, c1, 2.0, HS.HSOpticalFlowAlgoAdapter([0.5, 0.5, 2.0, 2.0, 2.0, 2.0], 60), 3, 2)
+    g["l3k2_U"], g["l3k2_V"] = U, V
+    out = os.path.join(OUT, "configs_extra.npz")
+    np.savez_compressed(out, **g)
+    print(out, os.path.getsize(out))
+
+
+if __name__ == "__main__" and "--big" in sys.argv:
+    main_big(sys.argv[sys.argv.index("--big") + 1])
+if __name__ == "__main__" and "--extra" in sys.argv:
+    main_extra()
