@@ -51,10 +51,13 @@ typedef enum {
   OFRI_ERR_TOO_SMALL = -7,     /* a pyramid level has < 4 samples on an axis (scipy raises in the spline) */
   OFRI_ERR_UNSUPPORTED = -8,   /* combination outside the native path (e.g. row-band mode with kLevels > 1) */
   OFRI_ERR_COMM = -9,          /* NCCL / multi-GPU error */
-  OFRI_ERR_INDEX = -10         /* biLinear=False warp: a scatter target left the frame (IndexError at GPOF:207) */
+  OFRI_ERR_INDEX = -10,        /* biLinear=False warp: a scatter target left the frame (IndexError at GPOF:207) */
+  OFRI_ERR_CALLBACK = -11      /* an external adapter's compute() callback reported failure (ofri_pyramidal_flow_external) */
 } ofri_status;
 
-typedef enum { OFRI_ALGO_NONE = -1, OFRI_ALGO_HS = 0, OFRI_ALGO_LS = 1 } ofri_algo_kind;
+/* OFRI_ALGO_EXTERNAL: a foreign adapter (any object with the reference's duck-typed compute(), GPOF:256-290) driven
+ * through a callback -- only valid with ofri_pyramidal_flow_external */
+typedef enum { OFRI_ALGO_NONE = -1, OFRI_ALGO_HS = 0, OFRI_ALGO_LS = 1, OFRI_ALGO_EXTERNAL = 2 } ofri_algo_kind;
 
 /* One optical-flow algorithm adapter (the reference's plugin protocol: compute(im1, im2, U, V) -> (U, V, error),
  * GenericPyramidalOpticalFlow.py:256-290).
@@ -127,6 +130,25 @@ OFRI_API int ofri_debug_phase_read(ofri_handle h, int family, unsigned long long
  * err_out: optional [batch][levels*k_levels][2] = (main error, optional error) per compute call, or NULL. */
 OFRI_API int ofri_pyramidal_flow(ofri_handle h, const float* im1, const float* im2, int batch, int H, int W,
                         const ofri_params* p, float* u_out, float* v_out, float* err_out);
+/* page-locked host memory for callers without a CUDA binding of their own (opticalflow_ri_b200/pipeline.py: the frame
+ * ring of the file -> GPU -> file pipeline): buffers from here make the host-pointer call above fully asynchronous */
+OFRI_API int ofri_host_alloc(ofri_handle h, size_t bytes, void** out);
+OFRI_API int ofri_host_free(ofri_handle h, void* p);
+
+/* The same driver with FOREIGN adapters (the reference's plugin protocol, GenericPyramidalOpticalFlow.py:256-290, call
+ * sites :406 and :410; e.g. examples/LiuSE_denseLK_Fs2_0_PyrLvls2.py:68-74: a dense Lucas-Kanade main adapter refined by
+ * Liu-Shen): an adapter whose kind is OFRI_ALGO_EXTERNAL is computed by `fn` -- the host-side compute(im1, im2, U, V) of
+ * that adapter -- everything else (level stages, the other adapter if it is HS / LS, accumulation) stays on the device.
+ * Per external compute(): one D2H of the level's (filtered, warped) frames and of the current U, V into dense host
+ * buffers, the callback, one H2D of the U, V it wrote; nothing else crosses the bus until u_out / v_out at the end.
+ * fn(user, which, call_index, im1, im2, U, V, H, W, err): which = 0 main / 1 optional; call_index = level * k_levels + k;
+ * im1 / im2 read-only H x W; U / V in: current flow increment, out: the adapter's result; *err = its error estimate;
+ * return 0, or non-zero to abort the call with OFRI_ERR_CALLBACK.  One pair per call (foreign adapters are not batched). */
+typedef int (*ofri_adapter_fn)(void* user, int which, int call_index, const float* im1, const float* im2, float* U,
+                               float* V, int H, int W, float* err);
+OFRI_API int ofri_pyramidal_flow_external(ofri_handle h, const float* im1, const float* im2, int H, int W,
+                                          const ofri_params* p, ofri_adapter_fn fn, void* user, float* u_out, float* v_out,
+                                          float* err_out);
 /* same with DEVICE pointers (dense, pitch == W), enqueued on the handle's stream, no synchronisation */
 OFRI_API int ofri_pyramidal_flow_dev(ofri_handle h, const float* d_im1, const float* d_im2, int batch, int H, int W,
                             const ofri_params* p, float* d_u_out, float* d_v_out, float* d_err_out);
@@ -195,6 +217,9 @@ OFRI_API int ofri_nccl_unique_id(void* out128);
 OFRI_API int ofri_comm_init_nccl(ofri_handle h, int rank, int nranks, const void* uid128);
 OFRI_API int ofri_local_group_create(int nranks, void** group);
 OFRI_API int ofri_local_group_destroy(void* group);
+/* a rank of the group failed (or will not reach its collectives): wake the ranks blocked in a collective and make
+ * every later collective of the group return OFRI_ERR_COMM instead of waiting forever */
+OFRI_API int ofri_local_group_abort(void* group);
 OFRI_API int ofri_comm_init_local(ofri_handle h, void* group, int rank);   /* call from the thread that drives `rank` */
 OFRI_API int ofri_comm_destroy(ofri_handle h);
 OFRI_API int ofri_band_plan(ofri_handle h, int H, int W, const ofri_params* p, int rank, int nranks, ofri_band* out);

@@ -11,11 +11,11 @@ HEADER = os.path.join(HERE, "..", "include", "ofri.h")
 
 OFRI_MAX_GAUSS_TAPS = 129
 OFRI_MAX_ALPHAS = 64
-ALGO_NONE, ALGO_HS, ALGO_LS = -1, 0, 1
+ALGO_NONE, ALGO_HS, ALGO_LS, ALGO_EXTERNAL = -1, 0, 1, 2
 
 OK = 0
 ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_ALPHAS, ERR_FILTER_OPT, ERR_TOO_SMALL, ERR_UNSUPPORTED, ERR_COMM, \
-    ERR_INDEX = -1, -2, -3, -4, -5, -6, -7, -8, -9, -10
+    ERR_INDEX, ERR_CALLBACK = -1, -2, -3, -4, -5, -6, -7, -8, -9, -10, -11
 
 
 class OfriError(RuntimeError):
@@ -47,6 +47,9 @@ class Band(C.Structure):
 
 _fp = C.POINTER(C.c_float)
 _H = C.c_void_p
+# ofri_adapter_fn: int fn(void* user, int which, int call_index, const float* im1, const float* im2, float* U, float* V,
+#                         int H, int W, float* err)
+ADAPTER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp)
 _SIGNATURES = {
     "ofri_abi_version": (C.c_int, []),
     "ofri_device_count": (C.c_int, []),
@@ -62,6 +65,10 @@ _SIGNATURES = {
     "ofri_debug_phase_read": (C.c_int, [_H, C.c_int, C.POINTER(C.c_ulonglong)]),
     "ofri_pyramidal_flow": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Params),
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ofri_host_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "ofri_host_free": (C.c_int, [_H, C.c_void_p]),
+    "ofri_pyramidal_flow_external": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Params), ADAPTER_FN,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ofri_pyramidal_flow_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Params),
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "ofri_hs_compute": (C.c_int, [_H, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp, _fp]),
@@ -82,6 +89,7 @@ _SIGNATURES = {
     "ofri_comm_init_nccl": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
     "ofri_local_group_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "ofri_local_group_destroy": (C.c_int, [C.c_void_p]),
+    "ofri_local_group_abort": (C.c_int, [C.c_void_p]),
     "ofri_comm_init_local": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "ofri_comm_destroy": (C.c_int, [_H]),
     "ofri_band_plan": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(Params), C.c_int, C.c_int, C.POINTER(Band)]),

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import ALGO_HS, ALGO_LS, ALGO_NONE, Algo, Band, OfriError, Params
+from ._lib import ALGO_EXTERNAL, ALGO_HS, ALGO_LS, ALGO_NONE, Algo, Band, OfriError, Params
 
 _EXC = {_lib.ERR_INVALID: ValueError, _lib.ERR_ALPHAS: IndexError, _lib.ERR_FILTER_OPT: TypeError,
         _lib.ERR_TOO_SMALL: ValueError, _lib.ERR_UNSUPPORTED: NotImplementedError, _lib.ERR_OOM: MemoryError,
@@ -29,6 +29,15 @@ def _batched(a):
     return a, False
 
 
+def _same_shape(first, **others):
+    """Every companion array of a call must have the (batch, H, W) of the first one: the C entry points take raw
+    pointers + one set of sizes, so a mismatch would read past a buffer (the reference raises a broadcast error)."""
+    for name, a in others.items():
+        if a is not None and a.shape != first.shape:
+            raise ValueError("operands could not be broadcast together: %s has shape %r, expected %r"
+                             % (name, a.shape, first.shape))
+
+
 def hs_algo(alphas_in_order, niter):
     a = Algo()
     a.kind = ALGO_HS
@@ -47,6 +56,13 @@ def ls_algo(h, maxiter=60, tol=1e-8):
     a.ls_h = float(np.float32(h))
     a.ls_maxiter = int(maxiter)
     a.ls_tol = float(tol)
+    return a
+
+
+def external_algo():
+    """A foreign adapter (the reference's duck-typed compute() protocol) driven through Handle.pyramidal_flow_external."""
+    a = Algo()
+    a.kind = ALGO_EXTERNAL
     return a
 
 
@@ -182,6 +198,64 @@ class Handle:
             err = err[0] if want_errors else None
         return (U, V, err) if want_errors else (U, V)
 
+    def pinned_empty(self, shape, dtype=np.float32):
+        """A numpy array in page-locked host memory (ofri_host_alloc); freed when the array is garbage collected.  The
+        host-pointer calls are fully asynchronous on such buffers (no bounce through the library's own pinned ring)."""
+        shape = tuple(int(x) for x in np.atleast_1d(shape))
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dt.itemsize
+        p = C.c_void_p()
+        self._check(self._L.ofri_host_alloc(self._h, C.c_size_t(max(nbytes, 1)), C.byref(p)))
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        L, h, addr = self._L, self, p.value
+        import weakref
+        weakref.finalize(buf, lambda: h._h and L.ofri_host_free(h._h, C.c_void_p(addr)))
+        return arr
+
+    def pyramidal_flow_external(self, im1, im2, params, compute_main=None, compute_optional=None, want_errors=False):
+        """One pair with FOREIGN adapters (ofri_pyramidal_flow_external): compute_main / compute_optional are Python
+        callables compute(im1, im2, U, V) -> (U, V, error) for the adapters whose kind in `params` is ALGO_EXTERNAL.
+        The level stages and any HS / Liu-Shen adapter stay on the GPU; per external compute() only the level's frames
+        and the current (U, V) come down and the adapter's (U, V) goes back up."""
+        a = _f32(im1)
+        b = _f32(im2)
+        if a.ndim != 2 or a.shape != b.shape:
+            raise ValueError("foreign adapters take one (H, W) pair")
+        H, W = a.shape
+        U = np.empty((H, W), np.float32)
+        V = np.empty((H, W), np.float32)
+        ncall = max(params.pyramid_levels * params.k_levels, 1)
+        err = np.zeros((ncall, 2), np.float32)
+        raised = []
+
+        def cb(user, which, call_index, p1, p2, pu, pv, h, w, perr):
+            try:
+                fn = compute_optional if which else compute_main
+                shp = (h, w)
+                i1 = np.ctypeslib.as_array(p1, shape=shp)
+                i2 = np.ctypeslib.as_array(p2, shape=shp)
+                u = np.ctypeslib.as_array(pu, shape=shp)
+                v = np.ctypeslib.as_array(pv, shape=shp)
+                res = fn(i1.copy(), i2.copy(), u.copy(), v.copy())      # the adapter may keep or modify what it gets
+                u[...] = np.asarray(res[0], dtype=np.float32)
+                v[...] = np.asarray(res[1], dtype=np.float32)
+                try:
+                    perr[0] = float(res[2])
+                except Exception:
+                    perr[0] = 0.0
+                return 0
+            except BaseException as e:          # noqa: BLE001 -- re-raised below, outside the C frame
+                raised.append(e)
+                return 1
+
+        rc = self._L.ofri_pyramidal_flow_external(self._h, a.ctypes.data, b.ctypes.data, H, W, C.byref(params),
+                                                  _lib.ADAPTER_FN(cb), None, U.ctypes.data, V.ctypes.data, err.ctypes.data)
+        if raised:
+            raise raised[0]
+        self._check(rc)
+        return (U, V, err) if want_errors else (U, V)
+
     def pyramidal_flow_ptr(self, im1_ptr, im2_ptr, batch, H, W, params, u_ptr, v_ptr, err_ptr=None, device=False):
         """Raw-pointer form: HOST pointers (device=False; e.g. pinned torch tensors) or DEVICE pointers."""
         fn = self._L.ofri_pyramidal_flow_dev if device else self._L.ofri_pyramidal_flow
@@ -216,6 +290,7 @@ class Handle:
         B, H, W = a.shape
         u0 = _batched(U0)[0] if U0 is not None else None
         v0 = _batched(V0)[0] if V0 is not None else None
+        _same_shape(a, im2=b, U0=u0, V0=v0)
         U = np.empty((B, H, W), np.float32)
         V = np.empty((B, H, W), np.float32)
         err = np.empty(B, np.float32)
@@ -230,6 +305,7 @@ class Handle:
         B, H, W = a.shape
         u0 = _batched(U0)[0] if U0 is not None else None
         v0 = _batched(V0)[0] if V0 is not None else None
+        _same_shape(a, im2=b, U0=u0, V0=v0)
         U = np.empty((B, H, W), np.float32)
         V = np.empty((B, H, W), np.float32)
         err = np.empty(B, np.float32)
@@ -271,6 +347,7 @@ class Handle:
         a, single = _batched(img)
         y, _ = _batched(cy)
         x, _ = _batched(cx)
+        _same_shape(a, cy=y, cx=x)
         B, H, W = a.shape
         out = np.empty_like(a)
         self._check(self._L.ofri_warp_bilinear(self._h, _ptr(a), _ptr(y), _ptr(x), B, H, W, _ptr(out)))
@@ -281,6 +358,7 @@ class Handle:
         b, _ = _batched(im2)
         u, _ = _batched(us)
         v, _ = _batched(vs)
+        _same_shape(a, im2=b, us=u, vs=v)
         B, H, W = a.shape
         o1 = np.empty_like(a)
         o2 = np.empty_like(a)
@@ -292,6 +370,7 @@ class Handle:
         a, single = _batched(im1)
         u, _ = _batched(us)
         v, _ = _batched(vs)
+        _same_shape(a, us=u, vs=v)
         B, H, W = a.shape
         mask_size = 3
         sg, tr = 0.6 * mask_size, 4.0 / 0.6 * mask_size
@@ -303,6 +382,7 @@ class Handle:
     def hs_derivatives(self, im1, im2):
         a, single = _batched(im1)
         b, _ = _batched(im2)
+        _same_shape(a, im2=b)
         B, H, W = a.shape
         fx, fy, ft = np.empty_like(a), np.empty_like(a), np.empty_like(a)
         self._check(self._L.ofri_hs_derivatives(self._h, _ptr(a), _ptr(b), B, H, W, _ptr(fx), _ptr(fy), _ptr(ft)))
@@ -314,6 +394,7 @@ class Handle:
         dx, _ = _batched(fx)
         dy, _ = _batched(fy)
         dt, _ = _batched(ft)
+        _same_shape(u, V0=v, fx=dx, fy=dy, ft=dt)
         B, H, W = u.shape
         U, V = np.empty_like(u), np.empty_like(u)
         self._check(self._L.ofri_hs_iterate(self._h, _ptr(u), _ptr(v), _ptr(dx), _ptr(dy), _ptr(dt), B, H, W,
@@ -323,6 +404,7 @@ class Handle:
     def ls_coefficients(self, im1, im2, h):
         a, single = _batched(im1)
         b, _ = _batched(im2)
+        _same_shape(a, im2=b)
         B, H, W = a.shape
         coef = np.empty((8, B, H, W), np.float32)
         self._check(self._L.ofri_ls_coefficients(self._h, _ptr(a), _ptr(b), B, H, W, float(np.float32(h)), _ptr(coef)))
@@ -360,6 +442,11 @@ class LocalGroup:
         if rc != 0:
             raise OfriError(rc, self._L.ofri_last_error(None).decode())
         self.nranks = int(nranks)
+
+    def abort(self):
+        """A rank failed: wake the ranks blocked in a collective; their calls return an error instead of hanging."""
+        if self.ptr:
+            self._L.ofri_local_group_abort(self.ptr)
 
     def close(self):
         if self.ptr:

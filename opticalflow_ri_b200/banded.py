@@ -56,6 +56,7 @@ def flow_banded_local(im1, im2, params_factory, nbands, devices=None, options=No
             h.close()
         except BaseException as e:      # noqa: BLE001 -- reported to the caller below
             errors[r] = e
+            group.abort()               # the other bands may be blocked in a collective waiting for this one
 
     threads = [threading.Thread(target=worker, args=(r,)) for r in range(nbands)]
     for t in threads:
@@ -63,7 +64,7 @@ def flow_banded_local(im1, im2, params_factory, nbands, devices=None, options=No
     for t in threads:
         t.join()
     group.close()
-    for e in errors:
-        if e is not None:
-            raise e
+    first = [e for e in errors if e is not None and "aborted" not in str(e)] or [e for e in errors if e is not None]
+    if first:
+        raise first[0]                  # the original failure, not the peers' "group aborted"
     return U, V

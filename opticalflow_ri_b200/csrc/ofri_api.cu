@@ -6,8 +6,10 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <condition_variable>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -45,11 +47,21 @@ struct ofri_ctx {
   // staging buffers of the host-pointer entry points (double buffered)
   char* stage = nullptr;
   size_t stage_cap = 0;
+  // pinned bounce ring of the host-pointer path for PAGEABLE caller buffers (same slot layout as `stage`)
+  char* hstage = nullptr;
+  size_t hstage_cap = 0;
+  const ofri_params* ext_params = nullptr;
+  int ext_rc = 0;                     // error code of a failed external compute() (run_adapter returns -1)
+  ofri_adapter_fn ext_fn = nullptr;   // set for the duration of ofri_pyramidal_flow_external
+  void* ext_user = nullptr;
+  std::vector<float> ext_buf;         // dense host copies handed to the callback: im1, im2, U, V
+  int last_host_path = 0;        // read-only: 1 = direct copies (pinned caller buffers / one chunk), 2 = pinned bounce ring
+  int last_hs_fuse_fine = 0, last_hs_fuse_coarse = 0, last_ls_fuse = 0;   // read-only: fuse factors the last call used
   std::map<std::pair<int, int>, DevResizeTaps> taps;
   std::map<int, DevSplineSys> splines;
   LaunchCounter lc;
   // options
-  int hs_fuse = 4, hs_variant = 24, ls_fuse = 2, ls_variant = 8, chunk_pairs = 0, timing = 0;
+  int hs_fuse = 4, hs_variant = 24, ls_fuse = 4, ls_variant = 8, chunk_pairs = 0, timing = 0;
   int hs_precise = 1;   // 0 = fast f32/FMA everywhere, 1 = reference arithmetic where a coarse level's HS result reaches the warp unrefined (hs_needs_precise), 2 = everywhere
   // row-band (domain-decomposed) mode
   ofri::Comm* comm = nullptr;
@@ -60,6 +72,7 @@ struct ofri_ctx {
   int band_exchange = 32;   // Horn-Schunck sweeps between two ghost-row exchanges (rounded up to a multiple of hs_fuse)
   int band_reach = 8;       // rows the warp may reach beyond a band's ghost frame (>= max |v| / 2 + 2)
   int band_reserve_sms = 8; // SMs an interior Horn-Schunck launch leaves free for the ghost-row exchange beside it (NCCL kernels)
+  int host_bounce = 1;      // host-pointer path: 1 = pageable caller buffers go through the pinned bounce ring, 0 = always direct copies
   int spline_variant = 1;   // 1 = chunk-parallel windowed solves + fused row kernel, 0 = sequential line solves (A/B)
   // timings of the last call
   std::vector<StageTime> times;
@@ -269,8 +282,10 @@ int check_params(ofri_handle h, const ofri_params* p, int H, int W) {
   const ofri_algo* algos[2] = {&p->main_algo, &p->opt_algo};
   for (int a = 0; a < 2; ++a) {
     const ofri_algo* g = algos[a];
-    if (a == 0 && g->kind != OFRI_ALGO_HS && g->kind != OFRI_ALGO_LS)
-      return fail(h, OFRI_ERR_INVALID, "main adapter must be HS or LS");
+    const bool ext_ok = g->kind == OFRI_ALGO_EXTERNAL && h && h->ext_fn;
+    if (a == 0 && g->kind != OFRI_ALGO_HS && g->kind != OFRI_ALGO_LS && !ext_ok)
+      return fail(h, OFRI_ERR_INVALID, "main adapter must be HS or LS (external adapters: ofri_pyramidal_flow_external)");
+    if (ext_ok) continue;
     if (g->kind == OFRI_ALGO_HS) {
       if (g->n_alphas < 0 || g->n_alphas > OFRI_MAX_ALPHAS) return fail(h, OFRI_ERR_INVALID, "bad n_alphas");
       if (g->n_alphas < p->pyramid_levels * p->k_levels)
@@ -367,12 +382,31 @@ void plan_workspace(Bump& b, int batch, int H, int W, const ofri_params* p, Work
 //    instead of 225.7 for 600 sweeps); Liu-Shen gains 6 % from T = 4.  At 1024^2 the border waste cancels the gain.
 // Row-band mode ties the exchange interval to the configured factor and applies the same rules there.
 bool big_frame(int H, int W) { return H >= 4096 && W >= 4096; }
-int eff_hs_fuse(ofri_handle h, int H, int W, int batch, bool precise = false) {
+// Tile-time model of the fast Horn-Schunck TMA kernel (phase profile profiles/r2_phase_*.jsonl):
+// a 66 x 128 tile costs ~2.2 us of fixed work (staging -> registers, stores, ghost columns) + 0.72 us per fused sweep and
+// yields (66 - 2T) x (128 - 2 HX) cells per sweep; the image border wastes a different share of the last tile row /
+// column for every T.  Cost of one sweep over an H x W level, in model us per pair:
+double hs_tile_cost(int H, int W, int T) {
+  const int HX = T <= 4 ? 4 : 8, TW = 128 - 2 * HX, TH = 66 - 2 * T;
+  return (double)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * (2.2 + 0.72 * T) / T;
+}
+int eff_hs_fuse(ofri_handle h, int H, int W, int batch, bool precise = false, int niter = 0) {
   const int fuse = precise ? (h->hs_fuse_precise > 0 ? h->hs_fuse_precise : h->hs_fuse)
                            : (h->hs_fuse_fast > 0 ? h->hs_fuse_fast : h->hs_fuse);
   if (!h->auto_fuse || fuse < 1 || fuse >= 8) return fuse;
   if (!precise && h->hs_fuse_fast == 0 && big_frame(H, W)) return 8;
-  return (long)((W + 119) / 120) * ((H + 57) / 58) * batch < 148 ? 8 : fuse;
+  if ((long)((W + 119) / 120) * ((H + 57) / 58) * batch < 148) return 8;
+  if (!precise && h->hs_fuse_fast == 0 && fuse == 4 && niter > 0) {
+    // per-level choice among the fuse factors the TMA kernel has (4, 6, 8): e.g. 512 x 512 (the coarse level of the
+    // 1024 x 1024 workload) loses 15 % of its T = 4 tile area to the border but only 9 % at T = 6 (measured: 18.0 ->
+    // 16.3 ms per 64 pairs); only factors that divide the sweep count (no tail launches on the slower fall-back kernel)
+    int best = fuse;
+    double cbest = hs_tile_cost(H, W, fuse) * 0.97;      // change only for a modelled gain of more than 3 %
+    for (int T : {6, 8})
+      if (niter % T == 0 && hs_tile_cost(H, W, T) < cbest) { best = T; cbest = hs_tile_cost(H, W, T); }
+    return best;
+  }
+  return fuse;
 }
 int eff_ls_fuse(ofri_handle h, int H, int W, int batch) {
   if (!h->auto_fuse || h->ls_fuse < 1 || h->ls_fuse >= 4) return h->ls_fuse;
@@ -411,6 +445,32 @@ int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws
   cudaStream_t s = h->stream;
   Img U[2] = {view(ws.U[0], Hl, Wl), view(ws.U[1], Hl, Wl)};
   Img V[2] = {view(ws.V[0], Hl, Wl), view(ws.V[1], Hl, Wl)};
+  if (a.kind == OFRI_ALGO_EXTERNAL) {
+    // a foreign adapter's compute() on the host: frames + current U, V down, result up; everything else stays put
+    Timed t(h, "external_adapter");
+    const size_t n = (size_t)Hl * Wl;
+    h->ext_buf.resize(4 * n);
+    float* hb = h->ext_buf.data();
+    const Img* src[4] = {&im1, &im2, &U[cur], &V[cur]};
+    for (int i = 0; i < 4; ++i)
+      if (cudaMemcpy2DAsync(hb + i * n, sizeof(float) * Wl, src[i]->p, sizeof(float) * src[i]->pitch, sizeof(float) * Wl, Hl,
+                            cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        return h->ext_rc = fail(h, OFRI_ERR_CUDA, "D2H for the external adapter failed: %s", cudaGetErrorString(cudaGetLastError())), -1;
+    if (cudaStreamSynchronize(s) != cudaSuccess)
+      return h->ext_rc = fail(h, OFRI_ERR_CUDA, "execution failed before the external adapter: %s", cudaGetErrorString(cudaGetLastError())), -1;
+    float err = 0.0f;
+    const int which = (&a == &h->ext_params->opt_algo) ? 1 : 0;
+    if (h->ext_fn(h->ext_user, which, call_index, hb, hb + n, hb + 2 * n, hb + 3 * n, Hl, Wl, &err) != 0)
+      return h->ext_rc = fail(h, OFRI_ERR_CALLBACK, "the external adapter's compute() failed (call %d)", call_index), -1;
+    cudaMemcpy2DAsync(U[cur].p, sizeof(float) * U[cur].pitch, hb + 2 * n, sizeof(float) * Wl, sizeof(float) * Wl, Hl,
+                      cudaMemcpyHostToDevice, s);
+    cudaMemcpy2DAsync(V[cur].p, sizeof(float) * V[cur].pitch, hb + 3 * n, sizeof(float) * Wl, sizeof(float) * Wl, Hl,
+                      cudaMemcpyHostToDevice, s);
+    if (d_err) cudaMemcpyAsync(d_err, &err, sizeof(float), cudaMemcpyHostToDevice, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess)      // the host buffers are reused by the next compute()
+      return h->ext_rc = fail(h, OFRI_ERR_CUDA, "H2D after the external adapter failed: %s", cudaGetErrorString(cudaGetLastError())), -1;
+    return cur;
+  }
   if (a.kind == OFRI_ALGO_HS) {
     Img fx = view(ws.fx, Hl, Wl), fy = view(ws.fy, Hl, Wl), ft = view(ws.ft, Hl, Wl);
     {
@@ -432,8 +492,10 @@ int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws
       const bool precise = h->hs_precise >= 2 || (h->hs_precise == 1 && coarse_level);
       // stage timers: the fast kernel on the finest level / on the coarser levels / the reference-arithmetic kernel
       Timed t(h, precise ? "hs_iterate_precise" : (finest ? "hs_iterate" : "hs_iterate_coarse"));
-      res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], a.hs_niter,
-                              eff_hs_fuse(h, Hl, Wl, U[cur].batch, precise), h->hs_variant, precise, s, h->lc);
+      const int fuse = eff_hs_fuse(h, Hl, Wl, U[cur].batch, precise, a.hs_niter);
+      (finest ? h->last_hs_fuse_fine : h->last_hs_fuse_coarse) = fuse;
+      res = launch_hs_iterate(U[cur], V[cur], U[cur ^ 1], V[cur ^ 1], fx, fy, ft, a.alphas[call_index], a.hs_niter, fuse,
+                              h->hs_variant, precise, s, h->lc);
     }
     cur = res ? (cur ^ 1) : cur;
     if (d_err) {
@@ -451,8 +513,9 @@ int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws
   }
   {
     Timed t(h, "ls_iterate");
+    h->last_ls_fuse = eff_ls_fuse(h, Hl, Wl, U[cur].batch);
     launch_ls_solve(V[cur], U[cur], V[cur ^ 1], U[cur ^ 1], co, a.ls_h, a.ls_maxiter, a.ls_tol,
-                    eff_ls_fuse(h, Hl, Wl, U[cur].batch), h->ls_variant, ws.ls_errs,
+                    h->last_ls_fuse, h->ls_variant, ws.ls_errs,
                     ws.ls_state, V[cur], U[cur], d_err, err_stride, nullptr, s, h->lc);
   }
   return cur;
@@ -639,10 +702,12 @@ int run_pyramid(ofri_handle h, const Img& im1, const Img& im2, const ofri_params
       const bool feeds_warp = !last || (k + 1 < KL && p->warping);
       cur = run_adapter(h, p->main_algo, call_index, ws, work1, work2, Hl, Wl, cur, uv_zero, hs_needs_precise(p, feeds_warp, true),
                         e_main, err_stride, last);
+      if (cur < 0) return h->ext_rc;
       if (has_opt) {
         float* e_opt = d_err ? d_err + 2 * call_index + 1 : nullptr;
         cur = run_adapter(h, p->opt_algo, call_index, ws, o1, o2, Hl, Wl, cur, false, hs_needs_precise(p, feeds_warp, false), e_opt,
                           err_stride, last);
+        if (cur < 0) return h->ext_rc;
       }
       Ucur = view(ws.U[cur], Hl, Wl);
       Vcur = view(ws.V[cur], Hl, Wl);
@@ -694,6 +759,40 @@ int ensure_stage(ofri_handle h, size_t bytes) {
   }
   h->stage_cap = bytes;
   return OFRI_OK;
+}
+
+int ensure_hstage(ofri_handle h, size_t bytes) {
+  if (bytes <= h->hstage_cap) return OFRI_OK;
+  OFRI_CUDA(h, cudaDeviceSynchronize());
+  if (h->hstage) cudaFreeHost(h->hstage);
+  h->hstage = nullptr;
+  h->hstage_cap = 0;
+  cudaError_t e = cudaHostAlloc((void**)&h->hstage, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, OFRI_ERR_OOM, "cudaHostAlloc of %zu pinned staging bytes failed", bytes);
+  }
+  h->hstage_cap = bytes;
+  return OFRI_OK;
+}
+// true iff p points into page-locked (or device-accessible) host memory: async copies from / to it really are async
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// error exit of the chunked host-pointer path: earlier chunks' copies may still be in flight into the caller's buffers
+// (and into staging slots the next call would reuse) -- wait for them before reporting the error
+int drain_streams(ofri_handle h, int rc) {
+  cudaStreamSynchronize(h->s_in);
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->s_out);
+  cudaGetLastError();
+  return rc;
 }
 
 int pick_chunk_impl(ofri_handle h, int batch, int H, int W, const ofri_params* p, size_t extra_per_pair, int cap);
@@ -1255,9 +1354,9 @@ int ofri_create(int device, ofri_handle* out) {
     return fail(nullptr, OFRI_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   for (int i = 0; i < 2; ++i) {
-    cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming | cudaEventBlockingSync);
     cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming | cudaEventBlockingSync);
   }
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
@@ -1276,6 +1375,7 @@ int ofri_destroy(ofri_handle h) {
   for (auto& kv : h->splines) { cudaFree(kv.second.lo); cudaFree(kv.second.cp); cudaFree(kv.second.den); }
   if (h->arena) cudaFree(h->arena);
   if (h->stage) cudaFree(h->stage);
+  if (h->hstage) cudaFreeHost(h->hstage);
   delete h->comm;
   for (int i = 0; i < 2; ++i) {
     cudaEventDestroy(h->ev_h2d[i]);
@@ -1331,6 +1431,11 @@ static int* option_slot(ofri_handle h, const char* key) {
   if (!strcmp(key, "hs_fuse_fast")) return &h->hs_fuse_fast;
   if (!strcmp(key, "hs_fuse_precise")) return &h->hs_fuse_precise;
   if (!strcmp(key, "last_chunk_pairs")) return &h->last_chunk_pairs;
+  if (!strcmp(key, "last_host_path")) return &h->last_host_path;
+  if (!strcmp(key, "last_hs_fuse_fine")) return &h->last_hs_fuse_fine;
+  if (!strcmp(key, "last_hs_fuse_coarse")) return &h->last_hs_fuse_coarse;
+  if (!strcmp(key, "last_ls_fuse")) return &h->last_ls_fuse;
+  if (!strcmp(key, "host_bounce")) return &h->host_bounce;
   if (!strcmp(key, "band_exchange")) return &h->band_exchange;
   if (!strcmp(key, "band_reach")) return &h->band_reach;
   if (!strcmp(key, "spline_variant")) return &h->spline_variant;
@@ -1413,51 +1518,199 @@ int ofri_pyramidal_flow(ofri_handle h, const float* im1, const float* im2, int b
   const size_t err_b = sizeof(float) * err_stride;
   // per pair staging: 2 inputs + 2 outputs + errors, double buffered
   const size_t slot_per_pair = 4 * plane_b + ((err_b + 255) & ~(size_t)255);
+  // Pageable caller buffers (what every numpy caller of the drop-in API passes): cudaMemcpyAsync on them is synchronous
+  // and staged by the driver, so chunk c's copies would serialise with the enqueueing of chunk c+1.  They go through a
+  // pinned bounce ring instead: one host thread fills the ring's input slots from the caller's frames, this thread
+  // issues asynchronous copies ring <-> device around the compute, a second host thread empties the output slots into
+  // the caller's arrays -- both memcpy streams overlap the GPU work.  Pinned caller buffers (and calls of one chunk,
+  // where nothing can overlap) keep the direct copies.
+  const bool pinned = is_pinned(im1) && is_pinned(im2) && is_pinned(u_out) && is_pinned(v_out) &&
+                      (!err_out || is_pinned(err_out));
   // smaller chunks than the device-pointer path: the first H2D and the last D2H of a call are not overlapped
-  const int chunk = pick_chunk(h, batch, H, W, p, 2 * slot_per_pair, 32);
+  int chunk = pick_chunk(h, batch, H, W, p, 2 * slot_per_pair, pinned ? 32 : 16);
+  const bool bounce = !pinned && h->host_bounce && batch > chunk;
+  if (!pinned && !bounce) chunk = pick_chunk(h, batch, H, W, p, 2 * slot_per_pair, 32);
+  h->last_host_path = bounce ? 2 : 1;
   rc = arena_reserve(h, workspace_bytes(chunk, H, W, p));
   if (rc) return rc;
   const size_t slot_b = ((slot_per_pair * chunk) + 255) & ~(size_t)255;
   rc = ensure_stage(h, 2 * slot_b);
   if (rc) return rc;
+  if (bounce && (rc = ensure_hstage(h, 2 * slot_b))) return rc;
   cudaStream_t s = h->stream;
   const int nchunks = (batch + chunk - 1) / chunk;   // (quarter-size first / last chunks were measured: no gain, profiles/)
+
+  // ---- helper threads of the bounce path -----------------------------------------------------------------------------
+  struct Pipe {
+    std::mutex m;
+    std::condition_variable cv;
+    int loaded = 0, issued = 0, unloaded = 0;   // chunks whose input is in the ring / whose copies are enqueued / whose output reached the caller
+    bool abort = false;
+  } pipe;
+  auto wait_for = [&](int Pipe::*field, int value) {   // false = aborted
+    std::unique_lock<std::mutex> lk(pipe.m);
+    pipe.cv.wait(lk, [&] { return pipe.abort || pipe.*field >= value; });
+    return !pipe.abort;
+  };
+  auto bump = [&](int Pipe::*field) {
+    { std::lock_guard<std::mutex> lk(pipe.m); pipe.*field += 1; }
+    pipe.cv.notify_all();
+  };
+  auto slot_ptrs = [&](char* base, float** i1, float** i2, float** u, float** v, float** e) {
+    *i1 = (float*)base;
+    *i2 = *i1 + plane * chunk;
+    *u = *i2 + plane * chunk;
+    *v = *u + plane * chunk;
+    *e = *v + plane * chunk;
+  };
+  std::thread loader, unloader;
+  const int dev = h->device;
+  if (bounce) {
+    loader = std::thread([&] {
+      cudaSetDevice(dev);
+      for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * chunk, nb = batch - b0 < chunk ? batch - b0 : chunk, slot = c & 1;
+        if (c >= 2) {                        // the H2D of chunk c-2 must have drained this input slot
+          if (!wait_for(&Pipe::issued, c - 1)) return;
+          cudaEventSynchronize(h->ev_h2d[slot]);
+        }
+        float *i1, *i2, *u, *v, *e;
+        slot_ptrs(h->hstage + slot * slot_b, &i1, &i2, &u, &v, &e);
+        memcpy(i1, im1 + b0 * plane, plane_b * nb);
+        memcpy(i2, im2 + b0 * plane, plane_b * nb);
+        bump(&Pipe::loaded);
+      }
+    });
+    unloader = std::thread([&] {
+      cudaSetDevice(dev);
+      for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * chunk, nb = batch - b0 < chunk ? batch - b0 : chunk, slot = c & 1;
+        if (!wait_for(&Pipe::issued, c + 1)) return;
+        // ev_d2h[slot] was recorded for chunk c and is not re-recorded before chunk c+2, which waits for `unloaded`
+        cudaEventSynchronize(h->ev_d2h[slot]);
+        float *i1, *i2, *u, *v, *e;
+        slot_ptrs(h->hstage + slot * slot_b, &i1, &i2, &u, &v, &e);
+        memcpy(u_out + b0 * plane, u, plane_b * nb);
+        memcpy(v_out + b0 * plane, v, plane_b * nb);
+        if (err_out) memcpy(err_out + (size_t)b0 * err_stride, e, err_b * nb);
+        bump(&Pipe::unloaded);
+      }
+    });
+  }
+  auto stop_threads = [&](bool aborting) {
+    if (!bounce) return;
+    if (aborting) {
+      { std::lock_guard<std::mutex> lk(pipe.m); pipe.abort = true; }
+      pipe.cv.notify_all();
+    }
+    if (loader.joinable()) loader.join();
+    if (unloader.joinable()) unloader.join();
+  };
+  auto bail = [&](int code) {
+    drain_streams(h, code);
+    stop_threads(true);
+    return code;
+  };
+#define OFRI_CUDA_BAIL(call)                                                                                 \
+  do {                                                                                                       \
+    cudaError_t e_ = (call);                                                                                 \
+    if (e_ != cudaSuccess)                                                                                   \
+      return bail(fail(h, e_ == cudaErrorMemoryAllocation ? OFRI_ERR_OOM : OFRI_ERR_CUDA, "%s failed: %s", #call, \
+                       cudaGetErrorString(e_)));                                                             \
+  } while (0)
+
   for (int c = 0; c < nchunks; ++c) {
     const int b0 = c * chunk;
     const int nb = batch - b0 < chunk ? batch - b0 : chunk;
     const int slot = c & 1;
-    char* base = h->stage + slot * slot_b;
-    float* d_i1 = (float*)base;
-    float* d_i2 = d_i1 + plane * chunk;
-    float* d_u = d_i2 + plane * chunk;
-    float* d_v = d_u + plane * chunk;
-    float* d_e = d_v + plane * chunk;
+    float *d_i1, *d_i2, *d_u, *d_v, *d_e;
+    slot_ptrs(h->stage + slot * slot_b, &d_i1, &d_i2, &d_u, &d_v, &d_e);
+    float *h_i1 = nullptr, *h_i2 = nullptr, *h_u = nullptr, *h_v = nullptr, *h_e = nullptr;
+    if (bounce) {
+      slot_ptrs(h->hstage + slot * slot_b, &h_i1, &h_i2, &h_u, &h_v, &h_e);
+      if (!wait_for(&Pipe::loaded, c + 1)) return bail(fail(h, OFRI_ERR_CUDA, "host staging aborted"));
+    }
     // H2D on the copy-in stream once the previous user of this slot (compute of chunk c-2) is done
-    if (c >= 2) OFRI_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_comp[slot], 0));
-    OFRI_CUDA(h, cudaMemcpyAsync(d_i1, im1 + b0 * plane, plane_b * nb, cudaMemcpyHostToDevice, h->s_in));
-    OFRI_CUDA(h, cudaMemcpyAsync(d_i2, im2 + b0 * plane, plane_b * nb, cudaMemcpyHostToDevice, h->s_in));
-    OFRI_CUDA(h, cudaEventRecord(h->ev_h2d[slot], h->s_in));
-    OFRI_CUDA(h, cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
-    if (c >= 2) OFRI_CUDA(h, cudaStreamWaitEvent(s, h->ev_d2h[slot], 0));   // output slot drained
-    Bump bump(h->arena, h->arena_cap, false);
+    if (c >= 2) OFRI_CUDA_BAIL(cudaStreamWaitEvent(h->s_in, h->ev_comp[slot], 0));
+    OFRI_CUDA_BAIL(cudaMemcpyAsync(d_i1, bounce ? h_i1 : im1 + b0 * plane, plane_b * nb, cudaMemcpyHostToDevice, h->s_in));
+    OFRI_CUDA_BAIL(cudaMemcpyAsync(d_i2, bounce ? h_i2 : im2 + b0 * plane, plane_b * nb, cudaMemcpyHostToDevice, h->s_in));
+    OFRI_CUDA_BAIL(cudaEventRecord(h->ev_h2d[slot], h->s_in));
+    OFRI_CUDA_BAIL(cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
+    if (c >= 2) OFRI_CUDA_BAIL(cudaStreamWaitEvent(s, h->ev_d2h[slot], 0));   // output slot drained
+    Bump bump_alloc(h->arena, h->arena_cap, false);
     Workspace ws;
-    plan_workspace(bump, nb, H, W, p, &ws);
+    plan_workspace(bump_alloc, nb, H, W, p, &ws);
     rc = run_pyramid(h, dense(d_i1, nb, H, W), dense(d_i2, nb, H, W), p, dense(d_u, nb, H, W), dense(d_v, nb, H, W),
                      err_out ? d_e : nullptr, ws);
     if (!rc) rc = check_lsw_flag(h, p, ws);
-    if (rc) return drain_streams(h, rc);
-    OFRI_CUDA(h, cudaEventRecord(h->ev_comp[slot], s));
-    OFRI_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
-    OFRI_CUDA(h, cudaMemcpyAsync(u_out + b0 * plane, d_u, plane_b * nb, cudaMemcpyDeviceToHost, h->s_out));
-    OFRI_CUDA(h, cudaMemcpyAsync(v_out + b0 * plane, d_v, plane_b * nb, cudaMemcpyDeviceToHost, h->s_out));
+    if (rc) return bail(rc);
+    OFRI_CUDA_BAIL(cudaEventRecord(h->ev_comp[slot], s));
+    OFRI_CUDA_BAIL(cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
+    // the ring's output slot is free once the unloader has copied chunk c-2 out of it
+    if (bounce && c >= 2 && !wait_for(&Pipe::unloaded, c - 1)) return bail(fail(h, OFRI_ERR_CUDA, "host staging aborted"));
+    OFRI_CUDA_BAIL(cudaMemcpyAsync(bounce ? h_u : u_out + b0 * plane, d_u, plane_b * nb, cudaMemcpyDeviceToHost, h->s_out));
+    OFRI_CUDA_BAIL(cudaMemcpyAsync(bounce ? h_v : v_out + b0 * plane, d_v, plane_b * nb, cudaMemcpyDeviceToHost, h->s_out));
     if (err_out)
-      OFRI_CUDA(h, cudaMemcpyAsync(err_out + (size_t)b0 * err_stride, d_e, err_b * nb, cudaMemcpyDeviceToHost,
-                                   h->s_out));
-    OFRI_CUDA(h, cudaEventRecord(h->ev_d2h[slot], h->s_out));
+      OFRI_CUDA_BAIL(cudaMemcpyAsync(bounce ? h_e : err_out + (size_t)b0 * err_stride, d_e, err_b * nb,
+                                     cudaMemcpyDeviceToHost, h->s_out));
+    OFRI_CUDA_BAIL(cudaEventRecord(h->ev_d2h[slot], h->s_out));
+    if (bounce) bump(&Pipe::issued);
   }
+#undef OFRI_CUDA_BAIL
+  stop_threads(false);                       // the unloader returns after the last chunk reached the caller's arrays
   OFRI_CUDA(h, cudaStreamSynchronize(h->s_out));
   rc = finish(h);
   return rc;
+}
+
+int ofri_host_alloc(ofri_handle h, size_t bytes, void** out) {
+  OFRI_ENTER(h);
+  if (!out || bytes == 0) return fail(h, OFRI_ERR_INVALID, "bad host allocation request");
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, OFRI_ERR_OOM, "cudaHostAlloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+  }
+  return OFRI_OK;
+}
+int ofri_host_free(ofri_handle h, void* p) {
+  OFRI_ENTER(h);
+  if (p) OFRI_CUDA(h, cudaFreeHost(p));
+  return OFRI_OK;
+}
+
+int ofri_pyramidal_flow_external(ofri_handle h, const float* im1, const float* im2, int H, int W, const ofri_params* p,
+                                 ofri_adapter_fn fn, void* user, float* u_out, float* v_out, float* err_out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, 1, H, W);
+  if (!im1 || !im2 || !u_out || !v_out || !fn) return fail(h, OFRI_ERR_INVALID, "NULL image / output / callback pointer");
+  h->ext_fn = fn;
+  h->ext_user = user;
+  h->ext_params = p;
+  struct Reset { ofri_handle h; ~Reset() { h->ext_fn = nullptr; h->ext_user = nullptr; h->ext_params = nullptr; } } reset{h};
+  int rc = check_params(h, p, H, W);
+  if (rc) return rc;
+  rc = arena_reserve(h, workspace_bytes(1, H, W, p) + 4 * (sizeof(float) * (size_t)round_up(W, 4) * H + 256) + 4096);
+  if (rc) return rc;
+  const int err_stride = p->pyramid_levels * p->k_levels * 2;
+  Bump bump(h->arena, h->arena_cap, false);
+  Workspace ws;
+  plan_workspace(bump, 1, H, W, p, &ws);
+  Img i1 = bump.plane(1, H, W), i2 = bump.plane(1, H, W), uo = bump.plane(1, H, W), vo = bump.plane(1, H, W);
+  float* d_err = err_out ? (float*)bump.take(sizeof(float) * err_stride) : nullptr;
+  if (d_err) cudaMemsetAsync(d_err, 0, sizeof(float) * err_stride, h->stream);
+  if ((rc = upload(h, i1, im1)) || (rc = upload(h, i2, im2))) return rc;
+  rc = run_pyramid(h, i1, i2, p, uo, vo, d_err, ws);
+  if (!rc) rc = check_lsw_flag(h, p, ws);
+  if (rc) {
+    cudaStreamSynchronize(h->stream);
+    cudaGetLastError();
+    return rc;
+  }
+  if ((rc = download(h, u_out, uo)) || (rc = download(h, v_out, vo))) return rc;
+  if (err_out) OFRI_CUDA(h, cudaMemcpyAsync(err_out, d_err, sizeof(float) * err_stride, cudaMemcpyDeviceToHost, h->stream));
+  return finish(h);
 }
 
 // ---- adapters stand-alone ------------------------------------------------------------------------------------------------
@@ -1758,6 +2011,10 @@ int ofri_local_group_create(int nranks, void** group) {
 }
 int ofri_local_group_destroy(void* group) {
   ofri::free_local_group((ofri::LocalGroup*)group);
+  return OFRI_OK;
+}
+int ofri_local_group_abort(void* group) {
+  ofri::abort_local_group((ofri::LocalGroup*)group);
   return OFRI_OK;
 }
 int ofri_comm_init_local(ofri_handle h, void* group, int rank) {

@@ -162,16 +162,24 @@ struct LocalGroup {
     std::vector<unsigned> hu;
   };
   std::vector<Slot> slots;
-  void barrier() {
+  bool aborted = false;    // set when a rank failed: wakes every waiter, all later collectives of the group fail
+  // false = the group was aborted (a peer failed before or during this collective)
+  bool barrier() {
     std::unique_lock<std::mutex> l(m);
+    if (aborted) return false;
     long g = gen;
     if (++count == n) {
       count = 0;
       ++gen;
       cv.notify_all();
     } else {
-      cv.wait(l, [&] { return gen != g; });
+      cv.wait(l, [&] { return gen != g || aborted; });
     }
+    return !aborted;
+  }
+  void abort() {
+    { std::lock_guard<std::mutex> l(m); aborted = true; }
+    cv.notify_all();
   }
 };
 LocalGroup* make_local_group(int n) {
@@ -180,6 +188,9 @@ LocalGroup* make_local_group(int n) {
   g->n = n;
   g->slots.resize(n);
   return g;
+}
+void abort_local_group(LocalGroup* g) {
+  if (g) g->abort();
 }
 void free_local_group(LocalGroup* g) {
   if (!g) return;
@@ -210,7 +221,7 @@ struct LocalComm : Comm {
       me.p[8 + i] = send_up ? send_up[i] : nullptr;
     }
     int rc = cuda(cudaEventRecord(me.ready, s), "cudaEventRecord");
-    g->barrier();
+    if (!g->barrier()) { err = "local group aborted: another rank failed"; return -1; }
     const size_t bytes = count * sizeof(float);
     if (!rc && rank > 0) {
       LocalGroup::Slot& nb = g->slots[rank - 1];
@@ -225,10 +236,10 @@ struct LocalComm : Comm {
         rc |= cuda(cudaMemcpyAsync(recv_dn[i], nb.p[8 + i], bytes, cudaMemcpyDefault, s), "cudaMemcpyAsync");
     }
     if (!rc) rc |= cuda(cudaEventRecord(me.done, s), "cudaEventRecord");
-    g->barrier();
+    if (!g->barrier()) { err = "local group aborted: another rank failed"; return -1; }
     if (!rc && rank > 0) rc |= cuda(cudaStreamWaitEvent(s, g->slots[rank - 1].done, 0), "cudaStreamWaitEvent");
     if (!rc && rank < nranks - 1) rc |= cuda(cudaStreamWaitEvent(s, g->slots[rank + 1].done, 0), "cudaStreamWaitEvent");
-    g->barrier();
+    if (!g->barrier()) { err = "local group aborted: another rank failed"; return -1; }
     return rc;
   }
   template <typename TT, typename Op>
@@ -237,11 +248,11 @@ struct LocalComm : Comm {
     (me.*field).resize(n);
     int rc = cuda(cudaMemcpyAsync((me.*field).data(), p, n * sizeof(TT), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync");
     rc |= cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
-    g->barrier();
+    if (!g->barrier()) { err = "local group aborted: another rank failed"; return -1; }
     std::vector<TT> res((g->slots[0].*field).begin(), (g->slots[0].*field).begin() + n);
     for (int r = 1; r < nranks; ++r)
       for (size_t i = 0; i < n; ++i) res[i] = op(res[i], (g->slots[r].*field)[i]);     // rank order: deterministic
-    g->barrier();
+    if (!g->barrier()) { err = "local group aborted: another rank failed"; return -1; }
     rc |= cuda(cudaMemcpyAsync(p, res.data(), n * sizeof(TT), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync");
     rc |= cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
     return rc;
@@ -256,16 +267,16 @@ struct LocalComm : Comm {
     LocalGroup::Slot& me = g->slots[rank];
     me.p[0] = send;
     int rc = cuda(cudaEventRecord(me.ready, s), "cudaEventRecord");
-    g->barrier();
+    if (!g->barrier()) { err = "local group aborted: another rank failed"; return -1; }
     for (int r = 0; r < nranks && !rc; ++r) {
       rc |= cuda(cudaStreamWaitEvent(s, g->slots[r].ready, 0), "cudaStreamWaitEvent");
       rc |= cuda(cudaMemcpyAsync(recv + (size_t)r * count, g->slots[r].p[0], count * sizeof(float), cudaMemcpyDefault, s),
                  "cudaMemcpyAsync");
     }
     if (!rc) rc |= cuda(cudaEventRecord(me.done, s), "cudaEventRecord");
-    g->barrier();
+    if (!g->barrier()) { err = "local group aborted: another rank failed"; return -1; }
     for (int r = 0; r < nranks && !rc; ++r) rc |= cuda(cudaStreamWaitEvent(s, g->slots[r].done, 0), "cudaStreamWaitEvent");
-    g->barrier();
+    if (!g->barrier()) { err = "local group aborted: another rank failed"; return -1; }
     return rc;
   }
   const char* error() const override { return err.c_str(); }

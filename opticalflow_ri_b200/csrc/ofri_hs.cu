@@ -323,261 +323,26 @@ static void launch_hs_fused_cfg(const Img& ui, const Img& vi, const Img& uo, con
   kern<<<g, C::NT, C::SMEM_BYTES, s>>>(ui, vi, uo, vo, fx, fy, ft, alpha2);
 }
 
-// tile variants (R rows per thread, NRG row groups, NG float4 column groups, min CTAs/SM for the register cap)
+// one tile shape: 34 x 128 cells (R = 4 rows per thread, 8 row groups, 32 float4 column groups)
 template <int T, bool PRECISE>
-static void launch_hs_fused_T(int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
-                              const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
-  constexpr int HX = (T <= 4) ? 4 : 8;
-  constexpr int NG64 = (64 + 2 * HX) / 4;      // 64-wide output tile: 18 or 20 column groups (not warp aligned)
-  if constexpr (PRECISE) {
-    switch (variant) {
-      default:
-      case 0: launch_hs_fused_cfg<T, 4, 8, 32, true, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-      case 2: launch_hs_fused_cfg<T, 4, 8, 16, true, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    }
-    return;
-  } else {
-    switch (variant) {
-      default:
-      case 0: launch_hs_fused_cfg<T, 4, 8, 32, false, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-      case 2: launch_hs_fused_cfg<T, 6, 6, 32, false, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-      case 4: launch_hs_fused_cfg<T, 4, 8, 16, false, 4>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// register-resident fused Jacobi kernel (hs_regs_kernel): variants >= 8
-// ---------------------------------------------------------------------------------------------------------------
-// Same tile geometry and ownership as hs_fused_kernel (tile SH x 128, thread (lane, rg) owns the 4 x R strip at columns
-// 4 lane.., rows 1 + rg R..), but a thread keeps its strip of U and V in REGISTERS for all T sweeps next to the
-// coefficients: the strip is read from HBM once (LDG.128), swept T times in place (3-row sliding window, halo columns
-// by warp shuffle) and written back once (STG.128).  A warp is exactly one row group (NG = 32), so the only data that
-// crosses warps is the row above / below each strip: every sweep a thread publishes its first and last row in a small
-// double-buffered shared array and reads its neighbours' rows from it -- 4 STS.128 + 4 LDS.128 per thread per sweep
-// instead of 2(R+2) LDS.128 + 2R STS.128, one __syncthreads per sweep.  Shared memory holds only those edge rows
-// (2 buffers x 2 planes x 2(NRG+2) rows).  Arithmetic is the same expression tree (hs_row_update), so results are
-// bit-identical to the other kernels.
-template <int T, int R, int NRG>
-struct HrCfg {
-  static constexpr int HX = (T <= 4) ? 4 : 8;
-  static constexpr int SW = 128;
-  static constexpr int SH = R * NRG + 2;
-  static constexpr int NT = 32 * NRG;
-  static constexpr int TW = SW - 2 * HX;
-  static constexpr int TH = SH - 2 * T;
-  static constexpr int XG = NRG + 2;                     // edge-row slots: g = rg + 1; g = 0 / NRG+1 are the tile halos
-  static constexpr int XPLANE = XG * 2 * SW;             // [g][top / bottom][SW]
-  static constexpr int SMEM_BYTES = 2 * 2 * XPLANE * 4;  // [buffer][U / V]
-  static_assert(TW > 0 && TH > 0 && HX >= T && NT <= 1024, "bad tile");
-};
-
-template <int T, int R, int NRG, bool EDGE, bool PRECISE>
-__device__ __forceinline__ void hs_regs_body(const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
-                                             const Img& fy, const Img& ft, float alpha2, float* smem) {
-  using C = HrCfg<T, R, NRG>;
-  constexpr int SW = C::SW, SH = C::SH, HX = C::HX;
-  const int b = blockIdx.z;
-  const int W = ui.W, H = ui.H;
-  const int x0 = blockIdx.x * C::TW - HX;
-  const int y0 = blockIdx.y * C::TH - T;
-  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-  const int sx = 4 * lane, gx = x0 + sx;
-  const int r0 = 1 + rg * R, gy0 = y0 + r0;
-  const long pitch = ui.pitch;
-  const bool okx = (gx >= 0) && (gx < (int)pitch);
-  const float* gUi = ui.p + (long)b * ui.stride;
-  const float* gVi = vi.p + (long)b * vi.stride;
-  auto X = [&](int buf, int plane, int g, int which) -> float* {
-    return smem + ((buf * 2 + plane) * C::XG + g) * 2 * SW + which * SW + sx;
-  };
-  // ---- tile halo rows (shared row 0 and SH-1): one warp each, into both buffers -----------------------------------
-  if (rg == 0 || rg == NRG - 1) {
-    const int gy = (rg == 0) ? y0 : y0 + SH - 1;
-    const int g = (rg == 0) ? 0 : NRG + 1, which = (rg == 0) ? 1 : 0;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-    if (!EDGE || (okx && gy >= 0 && gy < H)) {
-      a = ldg_f4(gUi + (long)gy * pitch + gx);
-      c = ldg_f4(gVi + (long)gy * pitch + gx);
-    }
-    *reinterpret_cast<float4*>(X(0, 0, g, which)) = a;
-    *reinterpret_cast<float4*>(X(0, 1, g, which)) = c;
-    *reinterpret_cast<float4*>(X(1, 0, g, which)) = a;
-    *reinterpret_cast<float4*>(X(1, 1, g, which)) = c;
-    if (NRG == 1) {   // a single row group owns both halos
-      const int gy2 = y0 + SH - 1;
-      a = c = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!EDGE || (okx && gy2 >= 0 && gy2 < H)) {
-        a = ldg_f4(gUi + (long)gy2 * pitch + gx);
-        c = ldg_f4(gVi + (long)gy2 * pitch + gx);
-      }
-      *reinterpret_cast<float4*>(X(0, 0, NRG + 1, 0)) = a;
-      *reinterpret_cast<float4*>(X(0, 1, NRG + 1, 0)) = c;
-      *reinterpret_cast<float4*>(X(1, 0, NRG + 1, 0)) = a;
-      *reinterpret_cast<float4*>(X(1, 1, NRG + 1, 0)) = c;
-    }
-  }
-  // ---- this thread's strip: U, V and coefficients, HBM -> registers -------------------------------------------------
-  float u[R][4], v[R][4];
-  HsCoef<PRECISE> k[R];
-  {
-    const float* g0 = fx.p + (long)b * fx.stride;
-    const float* g1 = fy.p + (long)b * fy.stride;
-    const float* g2 = ft.p + (long)b * ft.stride;
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int gy = gy0 + j;
-      float4 qu = make_float4(0.f, 0.f, 0.f, 0.f), qv = qu, a = qu, c = qu, d = qu;
-      if (!EDGE || (okx && gy >= 0 && gy < H)) {
-        const long go = (long)gy * pitch + gx;
-        qu = ldg_f4(gUi + go);
-        qv = ldg_f4(gVi + go);
-        a = ldg_f4(g0 + go);
-        c = ldg_f4(g1 + go);
-        d = ldg_f4(g2 + go);
-      }
-      u[j][0] = qu.x; u[j][1] = qu.y; u[j][2] = qu.z; u[j][3] = qu.w;
-      v[j][0] = qv.x; v[j][1] = qv.y; v[j][2] = qv.z; v[j][3] = qv.w;
-      k[j].c0[0] = a.x; k[j].c0[1] = a.y; k[j].c0[2] = a.z; k[j].c0[3] = a.w;
-      k[j].c1[0] = c.x; k[j].c1[1] = c.y; k[j].c1[2] = c.z; k[j].c1[3] = c.w;
-      k[j].c2[0] = d.x; k[j].c2[1] = d.y; k[j].c2[2] = d.z; k[j].c2[3] = d.w;
-    }
-    if constexpr (PRECISE) {
-#pragma unroll
-      for (int j = 0; j < R; ++j)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          k[j].c3[q] = hs_den(k[j].c0[q], k[j].c1[q], alpha2);
-          k[j].c4[q] = rcp_rn(k[j].c3[q]);
-        }
-    }
-  }
-  HsEdge eg;
-  eg.left_edge = EDGE && (gx == 0);
-  eg.right_j = EDGE ? (W - 1) - gx : -1;
-  eg.top_j = EDGE ? -gy0 : -1000;
-  eg.bot_j = EDGE ? (H - 1) - gy0 : -1000;
-  // publish the strip's first / last row for sweep 0
-  *reinterpret_cast<float4*>(X(0, 0, rg + 1, 0)) = make_float4(u[0][0], u[0][1], u[0][2], u[0][3]);
-  *reinterpret_cast<float4*>(X(0, 1, rg + 1, 0)) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
-  *reinterpret_cast<float4*>(X(0, 0, rg + 1, 1)) = make_float4(u[R - 1][0], u[R - 1][1], u[R - 1][2], u[R - 1][3]);
-  *reinterpret_cast<float4*>(X(0, 1, rg + 1, 1)) = make_float4(v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3]);
-  __syncthreads();
-
-  // ---- T sweeps in registers ------------------------------------------------------------------------------------------
-#pragma unroll 1
-  for (int s = 0; s < T; ++s) {
-    const int cur = s & 1;
-    float wu[3][6], wv[3][6];
-    hs_row6_smem<EDGE>(X(cur, 0, rg, 1), X(cur, 1, rg, 1), eg, wu[0], wv[0]);        // last row of the group above
-    hs_row6_vals<EDGE>(u[0], v[0], eg, wu[1], wv[1]);
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int A = j % 3, B = (j + 1) % 3, Cc = (j + 2) % 3;
-      if (j + 1 < R)
-        hs_row6_vals<EDGE>(u[j + 1], v[j + 1], eg, wu[Cc], wv[Cc]);                  // still the old values
-      else
-        hs_row6_smem<EDGE>(X(cur, 0, rg + 2, 0), X(cur, 1, rg + 2, 0), eg, wu[Cc], wv[Cc]);   // first row of the group below
-      float ou[4], ov[4];
-      if (EDGE && j == eg.top_j)
-        hs_row_update<PRECISE>(wu[Cc], wu[B], wu[Cc], wv[Cc], wv[B], wv[Cc], k[j], ou, ov);
-      else if (EDGE && j == eg.bot_j)
-        hs_row_update<PRECISE>(wu[A], wu[B], wu[A], wv[A], wv[B], wv[A], k[j], ou, ov);
-      else
-        hs_row_update<PRECISE>(wu[A], wu[B], wu[Cc], wv[A], wv[B], wv[Cc], k[j], ou, ov);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { u[j][q] = ou[q]; v[j][q] = ov[q]; }
-    }
-    if (s + 1 < T) {
-      const int nxt = cur ^ 1;
-      *reinterpret_cast<float4*>(X(nxt, 0, rg + 1, 0)) = make_float4(u[0][0], u[0][1], u[0][2], u[0][3]);
-      *reinterpret_cast<float4*>(X(nxt, 1, rg + 1, 0)) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
-      *reinterpret_cast<float4*>(X(nxt, 0, rg + 1, 1)) = make_float4(u[R - 1][0], u[R - 1][1], u[R - 1][2], u[R - 1][3]);
-      *reinterpret_cast<float4*>(X(nxt, 1, rg + 1, 1)) = make_float4(v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3]);
-      __syncthreads();
-    }
-  }
-  // ---- interior cells -> HBM ---------------------------------------------------------------------------------------------
-  float* gU = uo.p + (long)b * uo.stride;
-  float* gV = vo.p + (long)b * vo.stride;
-  const bool in_cols = (sx >= HX) && (sx < SW - HX) && (gx < W);
-#pragma unroll
-  for (int j = 0; j < R; ++j) {
-    const int sy = r0 + j, gy = gy0 + j;
-    if (in_cols && (sy >= T) && (sy < SH - T) && (gy < H)) {
-      const long go = (long)gy * uo.pitch + gx;
-      *reinterpret_cast<float4*>(gU + go) = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
-      *reinterpret_cast<float4*>(gV + go) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
-    }
-  }
-}
-
-template <int T, int R, int NRG, bool PRECISE, int MINB>
-__global__ void __launch_bounds__(HrCfg<T, R, NRG>::NT, MINB)
-hs_regs_kernel(Img ui, Img vi, Img uo, Img vo, Img fx, Img fy, Img ft, float alpha2) {
-  using C = HrCfg<T, R, NRG>;
-  extern __shared__ __align__(16) float smem[];
-  const int x0 = blockIdx.x * C::TW - C::HX, y0 = blockIdx.y * C::TH - T;
-  const bool edge = (x0 < 0) || (x0 + C::SW > ui.W) || (y0 < 0) || (y0 + C::SH > ui.H);
-  if (edge)
-    hs_regs_body<T, R, NRG, true, PRECISE>(ui, vi, uo, vo, fx, fy, ft, alpha2, smem);
-  else
-    hs_regs_body<T, R, NRG, false, PRECISE>(ui, vi, uo, vo, fx, fy, ft, alpha2, smem);
-}
-
-template <int T, int R, int NRG, bool PRECISE, int MINB>
-static void launch_hs_regs_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
-                               const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
-  using C = HrCfg<T, R, NRG>;
-  auto kern = hs_regs_kernel<T, R, NRG, PRECISE, MINB>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-  dim3 g((ui.W + C::TW - 1) / C::TW, (ui.H + C::TH - 1) / C::TH, ui.batch);
-  kern<<<g, C::NT, C::SMEM_BYTES, s>>>(ui, vi, uo, vo, fx, fy, ft, alpha2);
-}
-
-template <int T, bool PRECISE>
-static void launch_hs_regs_T(int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
-                             const Img& fy, const Img& ft, float alpha2, cudaStream_t s) {
-  switch (variant) {
-    default:
-    case 8: launch_hs_regs_cfg<T, 4, 8, PRECISE, 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;     // 34 x 128, 256 thr
-    case 10: launch_hs_regs_cfg<T, 8, 8, PRECISE, 1>(ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;    // 66 x 128, 256 thr
-  }
+static void launch_hs_fused_T(const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx, const Img& fy,
+                              const Img& ft, float alpha2, cudaStream_t s) {
+  launch_hs_fused_cfg<T, 4, 8, 32, PRECISE, PRECISE ? 1 : 2>(ui, vi, uo, vo, fx, fy, ft, alpha2, s);
 }
 
 // returns true if the launch honoured `sub` (only the TMA kernel can run a subset of the tile rows)
 static bool launch_hs_fused(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo,
                             const Img& vo, const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s,
                             const HsTileRows* sub = nullptr) {
-  if (variant >= 24) {                        // persistent TMA-fed register-resident kernel (ofri_hs_tma.cu)
-    if (launch_hs_tma(T, variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, s, sub)) return true;
-    variant = 8;                              // other T / no tensor-map support: non-persistent kernels
-  }
-  if (sub && !sub->inside) return false;      // the other kernels always run whole launches: do it in the second part
-  if (variant >= 8 && precise) variant = 2;   // the other register-resident kernels are built for the fast arithmetic only
-  if (variant >= 16) {                        // packed-f32x2 register-resident kernel (ofri_hs_pk.cu)
-    launch_hs_packed(T, variant, ui, vi, uo, vo, fx, fy, ft, s);
-    return true;
-  }
-  if (variant >= 8) {
-#define OFRI_HR_T(TT) \
-  case TT: launch_hs_regs_T<TT, false>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    switch (T) {
-      OFRI_HR_T(1)
-      OFRI_HR_T(2)
-      OFRI_HR_T(3)
-      OFRI_HR_T(4)
-      OFRI_HR_T(5)
-      OFRI_HR_T(6)
-      default: launch_hs_regs_T<8, false>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s); break;
-    }
-#undef OFRI_HR_T
-    return true;
-  }
-#define OFRI_HS_T(TT)                                                                             \
-  case TT:                                                                                        \
-    if (precise) launch_hs_fused_T<TT, true>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s);     \
-    else launch_hs_fused_T<TT, false>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s);            \
+  // hs_variant >= 24: the persistent TMA-fed register-resident kernel (ofri_hs_tma.cu); it covers T in {4, 6, 8}
+  // (reference arithmetic: also 2, 3) on images larger than its ghost frame.  Everything else -- other T (the tail of a
+  // sweep count that is not a multiple of the fuse factor), tiny images, hs_variant = 0 -- runs the shared-memory kernel.
+  if (variant >= 24 && launch_hs_tma(T, variant, precise, ui, vi, uo, vo, fx, fy, ft, alpha2, s, sub)) return true;
+  if (sub && !sub->inside) return false;      // the shared-memory kernel always runs whole launches: do it in the second part
+#define OFRI_HS_T(TT)                                                                     \
+  case TT:                                                                                \
+    if (precise) launch_hs_fused_T<TT, true>(ui, vi, uo, vo, fx, fy, ft, alpha2, s);      \
+    else launch_hs_fused_T<TT, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, s);             \
     break;
   switch (T) {
     OFRI_HS_T(1)
@@ -587,8 +352,8 @@ static bool launch_hs_fused(int T, int variant, bool precise, const Img& ui, con
     OFRI_HS_T(5)
     OFRI_HS_T(6)
     default:
-      if (precise) launch_hs_fused_T<8, true>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s);
-      else launch_hs_fused_T<8, false>(variant, ui, vi, uo, vo, fx, fy, ft, alpha2, s);
+      if (precise) launch_hs_fused_T<8, true>(ui, vi, uo, vo, fx, fy, ft, alpha2, s);
+      else launch_hs_fused_T<8, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, s);
       break;
   }
 #undef OFRI_HS_T

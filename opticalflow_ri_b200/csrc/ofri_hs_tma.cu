@@ -18,7 +18,11 @@
 //      then overlap with
 //   3. T Jacobi sweeps done entirely in registers (3-row sliding window, halo columns by warp shuffle, the rows
 //      above / below a strip exchanged through a small double-buffered shared array, one __syncthreads per sweep), and
-//   4. float4 stores of the (SH - 2T) x (128 - 2 HX) interior straight from registers to HBM.
+//   4. float4 stores of the (SH - 2T) x (128 - 2 HX) interior straight from registers to HBM.  (Round 2 measured two
+//      ways of issuing these stores row by row inside the last sweep so that they drain under its arithmetic: a peeled
+//      last sweep saved 6.8 Mcycles of the 19.5 the burst costs per CTA but the sweeps got 8.6 % slower, predicated
+//      stores in the one sweep body made every sweep 25 % slower (a branch per row ends the scheduling region) --
+//      both were net losses, profiles/r2_phase_hs_store_variants.jsonl; the burst after the sweeps stays.)
 // HBM reads of tile i+1 therefore run under the arithmetic of tile i, with a single CTA (8-12 warps, up to 255
 // registers per thread) per SM and no redundant staging of state through shared memory during the sweeps.
 // Algorithmic HBM traffic: 28 B per pixel per launch (read U, V, a, b, c; write U, V) for T sweeps.
@@ -50,17 +54,43 @@ struct TmCfg {
 
 struct TmTile { int x0, y0, b; };
 
+// Position of a CTA in the launch's tile list as a mixed-radix counter (pair, tile row, tile column): advancing by the
+// grid size is three adds with carries instead of two integer divisions per tile (which sat on the critical path of
+// every tile: 5 % of the kernel's time in the phase profile, profiles/r2_phase_*.jsonl).
+struct TmWalk {
+  int b, by, bx;          // current tile
+  int sb, sy, sx;         // gridDim.x decomposed in the same radix
+  int tiles_x, tiles_y;
+  __device__ __forceinline__ void init(int tile, int step, int tx, int ty) {
+    tiles_x = tx; tiles_y = ty;
+    const int per = tx * ty;
+    b = tile / per;
+    int r = tile - b * per;
+    by = r / tx;
+    bx = r - by * tx;
+    sb = step / per;
+    r = step - sb * per;
+    sy = r / tx;
+    sx = r - sy * tx;
+  }
+  __device__ __forceinline__ void advance() {
+    bx += sx;
+    int c = bx >= tiles_x ? 1 : 0;
+    bx -= c ? tiles_x : 0;
+    by += sy + c;
+    c = by >= tiles_y ? 1 : 0;
+    by -= c ? tiles_y : 0;
+    b += sb + c;
+  }
+};
+
 template <int T, int R, int NRG>
-__device__ __forceinline__ TmTile tm_decode(int tile, int tiles_x, int tiles_y, int4 rows) {
+__device__ __forceinline__ TmTile tm_tile(const TmWalk& w, int4 rows) {
   using C = TmCfg<T, R, NRG>;
-  const int per = tiles_x * tiles_y;
   TmTile t;
-  t.b = tile / per;
-  const int r = tile - t.b * per;
-  int by = r / tiles_x;
-  const int bx = r - by * tiles_x;
-  by += by < rows.x ? rows.y : rows.z;     // tile-row subset of a split launch (rows = {cut, off0, off1, -}); identity otherwise
-  t.x0 = bx * C::TW - C::HX;
+  t.b = w.b;
+  const int by = w.by + (w.by < rows.x ? rows.y : rows.z);   // tile-row subset of a split launch (rows = {cut, off0, off1, -}); identity otherwise
+  t.x0 = w.bx * C::TW - C::HX;
   t.y0 = by * C::TH - T;
   return t;
 }
@@ -405,27 +435,28 @@ hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CU
   const unsigned bar = smem_u32(smem_raw + C::STAGE_BYTES + C::X_BYTES);
   int tile = blockIdx.x;
   if (tile >= ntiles) return;
+  TmWalk walk;
+  walk.init(tile, (int)gridDim.x, tiles_x, tiles_y);
+  TmTile tl = tm_tile<T, R, NRG>(walk, rows);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    const TmTile t0 = tm_decode<T, R, NRG>(tile, tiles_x, tiles_y, rows);
     mbar_expect_tx(bar, (unsigned)C::STAGE_BYTES);
     const unsigned dst = smem_u32(stage);
-    tma_load_3d(dst + 0 * C::PLANE * 4, &mU, t0.x0, t0.y0, t0.b, bar);
-    tma_load_3d(dst + 1 * C::PLANE * 4, &mV, t0.x0, t0.y0, t0.b, bar);
-    tma_load_3d(dst + 2 * C::PLANE * 4, &mA, t0.x0, t0.y0, t0.b, bar);
-    tma_load_3d(dst + 3 * C::PLANE * 4, &mB, t0.x0, t0.y0, t0.b, bar);
-    tma_load_3d(dst + 4 * C::PLANE * 4, &mC, t0.x0, t0.y0, t0.b, bar);
+    tma_load_3d(dst + 0 * C::PLANE * 4, &mU, tl.x0, tl.y0, tl.b, bar);
+    tma_load_3d(dst + 1 * C::PLANE * 4, &mV, tl.x0, tl.y0, tl.b, bar);
+    tma_load_3d(dst + 2 * C::PLANE * 4, &mA, tl.x0, tl.y0, tl.b, bar);
+    tma_load_3d(dst + 3 * C::PLANE * 4, &mB, tl.x0, tl.y0, tl.b, bar);
+    tma_load_3d(dst + 4 * C::PLANE * 4, &mC, tl.x0, tl.y0, tl.b, bar);
   }
   __syncthreads();
   OFRI_PH_INIT;
   unsigned phase = 0;
   for (; tile < ntiles; tile += gridDim.x) {
-    const TmTile tl = tm_decode<T, R, NRG>(tile, tiles_x, tiles_y, rows);
-    const int nt = tile + gridDim.x;
-    const bool has_next = nt < ntiles;
-    const TmTile nx = tm_decode<T, R, NRG>(has_next ? nt : tile, tiles_x, tiles_y, rows);
+    const bool has_next = tile + (int)gridDim.x < ntiles;
+    walk.advance();
+    const TmTile nx = tm_tile<T, R, NRG>(walk, rows);     // only used if has_next
     const bool edge = (tl.x0 < 0) || (tl.x0 + C::SW > W) || (tl.y0 < 0) || (tl.y0 + C::SH > H);   // CTA-uniform
     OFRI_PH(5);
     mbar_wait(bar, phase);
@@ -437,6 +468,7 @@ hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CU
       hs_tma_tile_precise<T, R, NRG>(tl, W, H, uo, vo, stage, xbuf, has_next, nx, &mU, &mV, &mA, &mB, &mC, bar, alpha2);
     else
       hs_tma_tile<T, R, NRG>(tl, W, H, uo, vo, stage, xbuf, has_next, nx, &mU, &mV, &mA, &mB, &mC, bar);
+    tl = nx;
   }
   OFRI_PH_FLUSH;
 }
@@ -488,16 +520,10 @@ template <int T>
 static bool launch_T(int variant, bool precise, const Img& ui, const Img& vi, const Img& uo, const Img& vo,
                      const Img& fx, const Img& fy, const Img& ft, float alpha2, int num_sms, cudaStream_t s,
                      const HsTileRows* sub) {
+  (void)variant;
   if (precise)   // doubles in registers: 4-row strips, 34 x 128 tile, 256 threads
     return launch_cfg<T, 4, 8, true>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);
-  switch (variant) {
-    default:
-    case 24: return launch_cfg<T, 8, 8, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);     // 66 x 128, 256 threads
-    case 25: return launch_cfg<T, 6, 8, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);     // 50 x 128, 256 threads
-    case 26: return launch_cfg<T, 4, 12, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);    // 50 x 128, 384 threads
-    case 27: return launch_cfg<T, 6, 10, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);    // 62 x 128, 320 threads
-    case 28: return launch_cfg<T, 8, 4, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);     // 34 x 128, 128 threads, 2 CTAs / SM
-  }
+  return launch_cfg<T, 8, 8, false>(ui, vi, uo, vo, fx, fy, ft, alpha2, num_sms, s, sub);     // 66 x 128, 256 threads
 }
 
 // T in {4, 6, 8} (precise arithmetic: also 2, 3).  Returns false if this kernel cannot run (other T, no driver entry point, map encoding failed): the

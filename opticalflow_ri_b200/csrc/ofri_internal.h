@@ -117,9 +117,6 @@ void launch_hs_derivs(const Img& im1, const Img& im2, const Img& fx, const Img& 
 int launch_hs_iterate(const Img& ua, const Img& va, const Img& ub, const Img& vb, const Img& fx, const Img& fy,
                       const Img& ft, float alpha, int niter, int fuse, int variant, bool precise, cudaStream_t s,
                       LaunchCounter& lc, const HsHook& hook = HsHook(), const HsSplit* split = nullptr);
-// packed-f32x2 register-resident fused sweeps (ofri_hs_pk.cu): T sweeps ui,vi -> uo,vo on prepared (a, b, c) planes
-void launch_hs_packed(int T, int variant, const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx,
-                      const Img& fy, const Img& ft, cudaStream_t s);
 // persistent TMA-fed register-resident fused sweeps (ofri_hs_tma.cu); false = not applicable, use another kernel
 bool launch_hs_tma(int T, int variant, bool precise, const Img& ui, const Img& vi, const Img& uo, const Img& vo,
                    const Img& fx, const Img& fy, const Img& ft, float alpha2, cudaStream_t s,
@@ -170,6 +167,7 @@ int nccl_unique_id(void* out128, std::string* err);
 Comm* make_nccl_comm(int rank, int nranks, const void* uid128, std::string* err);
 LocalGroup* make_local_group(int n);
 void free_local_group(LocalGroup* g);
+void abort_local_group(LocalGroup* g);   // a rank failed: wake the peers blocked in a collective and make them fail too
 Comm* make_local_comm(LocalGroup* g, int rank, std::string* err);
 
 // persistent TMA-fed fused Liu-Shen block (ofri_ls_tma.cu): T sweeps ui, vi -> uo, vo; false = not applicable

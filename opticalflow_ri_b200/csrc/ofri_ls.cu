@@ -446,27 +446,18 @@ __global__ void ls_select_kernel(Img u0, Img v0, Img u1, Img v1, Img uo, Img vo,
 }
 
 template <int T>
-static void launch_ls_fused_T(int variant, const Img& u0, const Img& v0, const Img& u1, const Img& v1,
-                              const LsPlanes& co, float hpar, int k0, int maxiter, double tol, double* errs,
-                              const LsBand& band, cudaStream_t s) {
-  switch (variant) {
-    default:
-    case 0: launch_ls_fused_cfg<T, 4, 4, 16, 4>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 18 x 64
-    case 1: launch_ls_fused_cfg<T, 4, 8, 16, 2>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 34 x 64
-    case 2: launch_ls_fused_cfg<T, 4, 4, 32, 2>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 18 x 128
-    case 3: launch_ls_fused_cfg<T, 3, 6, 16, 3>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 20 x 64
-    case 4: launch_ls_fused_cfg<T, 2, 8, 16, 4>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 18 x 64
-    case 5: launch_ls_fused_cfg<T, 6, 4, 16, 3>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;   // 26 x 64
-  }
+static void launch_ls_fused_T(const Img& u0, const Img& v0, const Img& u1, const Img& v1, const LsPlanes& co, float hpar,
+                              int k0, int maxiter, double tol, double* errs, const LsBand& band, cudaStream_t s) {
+  launch_ls_fused_cfg<T, 4, 8, 16, 2>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s);   // 34 x 64 tile
 }
-static void launch_ls_fused(int T, int variant, const Img& u0, const Img& v0, const Img& u1, const Img& v1,
+static void launch_ls_fused(int T, const Img& u0, const Img& v0, const Img& u1, const Img& v1,
                             const LsPlanes& co, float hpar, int k0, int maxiter, double tol, double* errs,
                             const LsBand& band, cudaStream_t s) {
   switch (T) {
-    case 1: launch_ls_fused_T<1>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
-    case 2: launch_ls_fused_T<2>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
-    case 3: launch_ls_fused_T<3>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
-    default: launch_ls_fused_T<4>(variant, u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
+    case 1: launch_ls_fused_T<1>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
+    case 2: launch_ls_fused_T<2>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
+    case 3: launch_ls_fused_T<3>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
+    default: launch_ls_fused_T<4>(u0, v0, u1, v1, co, hpar, k0, maxiter, tol, errs, band, s); break;
   }
 }
 
@@ -498,7 +489,7 @@ void launch_ls_solve(const Img& ua, const Img& va, const Img& ub, const Img& vb,
       if (variant >= 8)      // persistent TMA-fed register-resident kernel (ofri_ls_tma.cu); launch i reads buffer (i & 1)
         done = (i & 1) ? launch_ls_tma(T, ub, vb, ua, va, coef, hpar, i * T, maxiter, tol, errs, band, s, variant)
                        : launch_ls_tma(T, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, band, s, variant);
-      if (!done) launch_ls_fused(T, variant >= 8 ? 4 : variant, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, band, s);
+      if (!done) launch_ls_fused(T, ua, va, ub, vb, coef, hpar, i * T, maxiter, tol, errs, band, s);
       lc.n += 1;
       // launch i wrote buffer b (odd launches write a); band mode: sum the block's residuals over all bands and refresh
       // the ghost rows of the buffer just written

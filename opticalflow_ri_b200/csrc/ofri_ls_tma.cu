@@ -47,16 +47,38 @@ struct LtCfg {
 struct LtMaps { CUtensorMap m[10]; };   // u, v, IIx, IIy, II, Ixt, Iyt, B11, B12, B22
 struct LtTile { int x0, y0, b; };
 
+// tile list position as a mixed-radix counter (see TmWalk in ofri_hs_tma.cu): no integer divisions per tile
+struct LtWalk {
+  int b, by, bx, sb, sy, sx, tiles_x, tiles_y;
+  __device__ __forceinline__ void init(int tile, int step, int tx, int ty) {
+    tiles_x = tx; tiles_y = ty;
+    const int per = tx * ty;
+    b = tile / per;
+    int r = tile - b * per;
+    by = r / tx;
+    bx = r - by * tx;
+    sb = step / per;
+    r = step - sb * per;
+    sy = r / tx;
+    sx = r - sy * tx;
+  }
+  __device__ __forceinline__ void advance() {
+    bx += sx;
+    int c = bx >= tiles_x ? 1 : 0;
+    bx -= c ? tiles_x : 0;
+    by += sy + c;
+    c = by >= tiles_y ? 1 : 0;
+    by -= c ? tiles_y : 0;
+    b += sb + c;
+  }
+};
 template <int T, int R, int NRG>
-__device__ __forceinline__ LtTile lt_decode(int tile, int tiles_x, int tiles_y) {
+__device__ __forceinline__ LtTile lt_tile(const LtWalk& w) {
   using C = LtCfg<T, R, NRG>;
-  const int per = tiles_x * tiles_y;
   LtTile t;
-  t.b = tile / per;
-  const int r = tile - t.b * per;
-  const int by = r / tiles_x, bx = r - by * tiles_x;
-  t.x0 = bx * C::TW - C::HX;
-  t.y0 = by * C::TH - T;
+  t.b = w.b;
+  t.x0 = w.bx * C::TW - C::HX;
+  t.y0 = w.by * C::TH - T;
   return t;
 }
 
@@ -91,12 +113,15 @@ __device__ __forceinline__ void lt_row6_smem(const float* __restrict__ pu, const
 }
 
 // per-CTA shared bookkeeping behind the staging + exchange buffers
+constexpr int LT_STOP_WORDS = 48;   // stop flags of up to 1536 pairs per launch as a bit mask in shared memory
 struct LtShared {
   unsigned long long bar;
   int stop;
   int pad;
   double acc[4][12][2];  // residual sums of the current pair, per fused sweep and WARP (own slot: no atomics)
+  unsigned stopbits[LT_STOP_WORDS];
 };
+static_assert(sizeof(LtShared) <= 1024, "LtShared must fit the reserve behind the exchange buffers");
 
 template <int T, int R, int NRG>
 __global__ void __launch_bounds__(LtCfg<T, R, NRG>::NT, LtCfg<T, R, NRG>::CTAS)
@@ -120,13 +145,28 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
 #pragma unroll
     for (int c = 0; c < 10; ++c) tma_load_3d(dst + c * C::PLANE * 4, &maps.m[c], t.x0, t.y0, t.b, bar);
   };
+  LtWalk walk;
+  walk.init(tile, (int)gridDim.x, tiles_x, tiles_y);
+  LtTile tl = lt_tile<T, R, NRG>(walk);
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    issue(lt_decode<T, R, NRG>(tile, tiles_x, tiles_y));
+    issue(tl);
   }
   if (tid < 4 * 12 * 2) (&sh->acc[0][0][0])[tid] = 0.0;
+  // Stopping rule (LS:141) of every pair of the launch, evaluated ONCE per CTA by all threads in parallel (it used to be
+  // evaluated by one thread per tile -- global loads + double-precision square roots on the critical path of every
+  // tile: 22 % of the kernel's time in the phase profile).  The previous launches are complete (stream order), so the
+  // sums are final.  Launches with more pairs than the mask holds fall back to the per-tile evaluation.
+  const int npairs = ntiles / (tiles_x * tiles_y);
+  const bool use_mask = npairs <= 32 * LT_STOP_WORDS;
+  if (use_mask && k0 > 0) {
+    for (int w = tid; w < LT_STOP_WORDS; w += C::NT) sh->stopbits[w] = 0u;
+    __syncthreads();
+    for (int b = tid; b < npairs; b += C::NT)
+      if (ls_stopped_before(errs + (long)b * maxiter * 2, k0, tol, band.npix, T)) atomicOr(&sh->stopbits[b >> 5], 1u << (b & 31));
+  }
   __syncthreads();
   auto X = [&](int buf, int plane, int g, int which) -> float* {
     return xbuf + ((buf * 2 + plane) * C::XROWS + 2 * g + which - 1) * SW + sx;   // (g = 0: which = 1; g = NRG + 1: which = 0)
@@ -148,15 +188,21 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
     __syncthreads();
   };
   for (; tile < ntiles; tile += gridDim.x) {
-    const LtTile tl = lt_decode<T, R, NRG>(tile, tiles_x, tiles_y);
-    const int nt = tile + gridDim.x;
-    const bool has_next = nt < ntiles;
+    const bool has_next = tile + (int)gridDim.x < ntiles;
+    walk.advance();
+    const LtTile nxt_tile = lt_tile<T, R, NRG>(walk);
     if (tl.b != acc_pair) {
       flush();
       acc_pair = tl.b;
     }
-    if (tid == 0)
-      sh->stop = (k0 > 0 && ls_stopped_before(errs + (long)tl.b * maxiter * 2, k0, tol, band.npix, T)) ? 1 : 0;
+    bool stopped;         // CTA-uniform: this pair stopped in an earlier block (LS:141)
+    if (use_mask) {
+      stopped = k0 > 0 && ((sh->stopbits[tl.b >> 5] >> (tl.b & 31)) & 1u);
+    } else {
+      if (tid == 0)
+        sh->stop = (k0 > 0 && ls_stopped_before(errs + (long)tl.b * maxiter * 2, k0, tol, band.npix, T)) ? 1 : 0;
+      stopped = false;    // read after the barrier below
+    }
     OFRI_PH(5);
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -202,10 +248,12 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
     OFRI_PH(2);
     if (has_next && tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      issue(lt_decode<T, R, NRG>(nt, tiles_x, tiles_y));
+      issue(nxt_tile);
     }
-    if (sh->stop) {      // CTA-uniform: this pair stopped in an earlier block (LS:141)
+    if (!use_mask) stopped = sh->stop != 0;
+    if (stopped) {
       __syncthreads();
+      tl = nxt_tile;
       continue;
     }
     const bool edge = (tl.x0 < 0) || (tl.x0 + SW > W) || (tl.y0 < 0) || (tl.y0 + SH > H);   // CTA-uniform
@@ -291,6 +339,7 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
     OFRI_PH(3);
     __syncthreads();   // exchange buffers free for the next tile
     OFRI_PH(4);
+    tl = nxt_tile;
   }
   flush();
   OFRI_PH_FLUSH;
@@ -331,13 +380,7 @@ bool launch_ls_tma(int T, const Img& ui, const Img& vi, const Img& uo, const Img
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  if (variant == 9) {   // 18 x 128 tiles, 128 threads, two CTAs per SM
-    switch (T) {
-      case 2: return launch_cfg<2, 4, 4>(ui, vi, uo, vo, co, hpar, k0, maxiter, tol, errs, band, num_sms, s);
-      case 3: return launch_cfg<3, 4, 4>(ui, vi, uo, vo, co, hpar, k0, maxiter, tol, errs, band, num_sms, s);
-      default: return false;
-    }
-  }
+  (void)variant;
   switch (T) {
     case 2: return launch_cfg<2, 4, 8>(ui, vi, uo, vo, co, hpar, k0, maxiter, tol, errs, band, num_sms, s);
     case 3: return launch_cfg<3, 4, 8>(ui, vi, uo, vo, co, hpar, k0, maxiter, tol, errs, band, num_sms, s);

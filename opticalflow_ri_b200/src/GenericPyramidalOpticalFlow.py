@@ -9,7 +9,9 @@ When the adapters are this package's HSOpticalFlowAlgoAdapter / LiuShenOpticalFl
 (down-sample, spline up-sample, warp, pre-filters, HS sweeps, Liu-Shen sweeps, accumulation) is ONE native call
 (ofri_pyramidal_flow) and the data never leaves the GPU between stages.  Any other duck-typed adapter
 (compute / getAlgoName / hasGenericPyramidalDefaults / getGenericPyramidalDefaults, reference :256-290) still works:
-the level stages run as GPU kernels and the adapter's own compute() is called with numpy arrays.
+the driver, the level stages and the native adapter of the pair (e.g. the Liu-Shen refinement behind a foreign main
+adapter) stay on the GPU, and only the foreign adapter's own compute() is called on the host with numpy arrays
+(ofri_pyramidal_flow_external: one D2H of the level's frames, one H2D of the adapter's result per call).
 
 Behaviour mirrored from the reference (line numbers of its GenericPyramidalOpticalFlow.py): adapter-default override
 304-327; level sizes int32(round(n*scale)) from the ORIGINAL frames 336-343; 'Invalid scale level' 345; level
@@ -78,17 +80,23 @@ def _apply_adapter_defaults(main, warping, biLinear, interScaling, finalScaling)
 
 
 def _native_algo(adapter, ncalls):
-    """ofri_algo for one of this package's adapters; HS consumes `ncalls` alphas from the END of the caller's list
-    exactly like the per-call pop of the reference (HornSchunck.py:36)."""
+    """ofri_algo for one of this package's adapters.  HS takes `ncalls` alphas from the END of the caller's list in the
+    order the reference's per-call pop would (HornSchunck.py:36) -- WITHOUT consuming them: _consume_alphas() removes
+    them only after the native call has succeeded (the reference consumes one alpha per compute() that actually runs)."""
     kind = getattr(adapter, '_ofri_native_kind', None)
     if kind == 'HS':
-        used = []
-        for _ in range(ncalls):
-            used.append(adapter.alphas.pop())       # IndexError here == the reference's failure mode
+        if len(adapter.alphas) < ncalls:
+            raise IndexError('pop from empty list')  # the reference's failure mode, raised before anything ran
+        used = list(adapter.alphas[len(adapter.alphas) - ncalls:])[::-1]
         return ofri.hs_algo(used, adapter.Niter)
     if kind == 'LS':
         return ofri.ls_algo(adapter.alpha)
     return None
+
+
+def _consume_alphas(adapter, ncalls):
+    if getattr(adapter, '_ofri_native_kind', None) == 'HS':
+        del adapter.alphas[len(adapter.alphas) - ncalls:]
 
 
 def _is_native(adapter):
@@ -105,76 +113,39 @@ def _run(im1, im2, FILTER, main, pyramidalLevels, kLevels, FILTER_OPT, optional,
         raise Exception('Invalid scale level: ' + str(1.0 / (2.0 ** (pyramidalLevels - 1))))
     if optional is not None and FILTER_OPT is None:
         raise TypeError("'>' not supported between instances of 'NoneType' and 'float'")
-    if _is_native(main) and (optional is None or _is_native(optional)):
-        ncalls = pyramidalLevels * kLevels
-        params = ofri.make_params(_native_algo(main, ncalls),
-                                  _native_algo(optional, ncalls) if optional is not None else None,
-                                  filter_sigma=FILTER, filter_opt_sigma=FILTER_OPT, pyramid_levels=pyramidalLevels,
-                                  k_levels=kLevels, warping=warping, bilinear=biLinear,
-                                  intermediate_scaling=interScaling, final_scaling=finalScaling)
-        return _native.handle().pyramidal_flow(im1, im2, params)
-    return _generic_adapters(im1, im2, FILTER, main, pyramidalLevels, kLevels, FILTER_OPT, optional, warping, biLinear,
-                             interScaling, finalScaling)
-
-
-def _generic_adapters(im1, im2, FILTER, main, L, KL, FILTER_OPT, optional, warping, biLinear, interScaling,
-                      finalScaling):
-    """Foreign adapters: GPU stages + the adapter's own compute() on numpy arrays (one pair at a time)."""
-    if np.ndim(im1) != 2:
+    ncalls = pyramidalLevels * kLevels
+    native_all = _is_native(main) and (optional is None or _is_native(optional))
+    if not native_all and np.ndim(im1) != 2:
         raise ValueError("batched input needs this package's HS / Liu-Shen adapters")
-    h = _native.handle()
-    im1 = np.ascontiguousarray(im1, dtype=np.float32)
-    im2 = np.ascontiguousarray(im2, dtype=np.float32)
-    H, W = im1.shape
-    taps_main = ofri.gaussian_taps(FILTER, 3) if FILTER > 1e-3 else None
-    taps_opt = ofri.gaussian_taps(FILTER_OPT, 5) if (optional is not None and FILTER_OPT > 1e-3) else None
-    scale = 1.0 / (2.0 ** (L - 1))
-    Uacc = Vacc = U = V = None
-    prev = None
-    for level in range(1, L + 1):
-        last = level == L
-        local_scaling = finalScaling if last else interScaling
-        if scale < 1.0 and not last:
-            hl, wl = h.level_size(H, scale), h.level_size(W, scale)
-            n1, n2 = h.resize_bicubic(im1, hl, wl), h.resize_bicubic(im2, hl, wl)
-        elif scale > 1.0:
-            raise Exception('Invalid scale level: ' + str(scale))
-        else:
-            n1, n2 = im1, im2
-        if level > 1:
-            w1, w2, Uacc, Vacc, U, V = updateNextPyramidalLevel(n1, prev, n2, Uacc, Vacc, U, V, warping, biLinear,
-                                                                local_scaling)
-        else:
-            w1, w2 = n1, n2
-            U, V, Uacc, Vacc = (np.zeros(n1.shape, dtype=np.float32) for _ in range(4))
-        work1 = h.gauss_px(w1, taps_main) if taps_main is not None else w1.copy()
-        work2 = h.gauss_px(w2, taps_main) if taps_main is not None else w2
-        if optional is not None:
-            opt1 = h.gauss_px(n1, taps_opt) if taps_opt is not None else n1.copy()
-            opt2 = h.gauss_px(n2, taps_opt) if taps_opt is not None else n2
-        for k in range(KL):
-            log('Level=', level, ' kIter=', k)
-            if k > 0:
-                if warping:
-                    w1, w2, Uacc, Vacc, U, V = updateNextPyramidalLevel(n1.copy(), n1, n2, Uacc, Vacc, U, V, warping,
-                                                                        biLinear, False)
-                    if FILTER > 1:
-                        work1, work2 = h.gauss_px(w1, taps_main), h.gauss_px(w2, taps_main)
-                    else:
-                        work1, work2 = w1.copy(), w2
-                else:
-                    work1, work2, Uacc, Vacc, U, V = updateNextPyramidalLevel(work1, work1, work2, Uacc, Vacc, U, V,
-                                                                              warping, biLinear, False)
-            U, V, err = main.compute(work1, work2, U, V)
-            log(main.getAlgoName() + ' estimated error for image registration: ' + str(err))
-            if optional is not None:
-                U, V, err2 = optional.compute(np.copy(opt1), np.copy(opt2), U, V)
-                log(optional.getAlgoName() + ' estimated error for image registration: ' + str(err2))
-            Uacc = np.float32(Uacc) + np.float32(U)
-            Vacc = np.float32(Vacc) + np.float32(V)
-        prev = work1
-        scale *= 2
-    return Uacc, Vacc
+
+    def algo_of(adapter):
+        return _native_algo(adapter, ncalls) if _is_native(adapter) else ofri.external_algo()
+
+    params = ofri.make_params(algo_of(main), algo_of(optional) if optional is not None else None,
+                              filter_sigma=FILTER, filter_opt_sigma=FILTER_OPT, pyramid_levels=pyramidalLevels,
+                              k_levels=kLevels, warping=warping, bilinear=biLinear,
+                              intermediate_scaling=interScaling, final_scaling=finalScaling)
+    if native_all:
+        out = _native.handle().pyramidal_flow(im1, im2, params)
+    else:
+        # Foreign adapters (any object with the reference's duck-typed protocol, e.g. a dense Lucas-Kanade or Farneback
+        # main adapter refined by this package's Liu-Shen: examples/LiuSE_denseLK_Fs2_0_PyrLvls2.py:68-74): the whole
+        # driver still runs natively -- level stages, the native adapter of the pair (if any) and the accumulation stay
+        # on the GPU; only the foreign adapter's own compute() runs on the host, fed with numpy copies of the level's
+        # frames and the current flow (ofri_pyramidal_flow_external).
+        def wrap(adapter):
+            def compute(i1, i2, U, V):
+                res = adapter.compute(i1, i2, U, V)
+                log(adapter.getAlgoName() + ' estimated error for image registration: ' + str(res[2]))
+                return res
+            return compute
+        out = _native.handle().pyramidal_flow_external(
+            im1, im2, params, compute_main=None if _is_native(main) else wrap(main),
+            compute_optional=None if (optional is None or _is_native(optional)) else wrap(optional))
+    _consume_alphas(main, ncalls)
+    if optional is not None:
+        _consume_alphas(optional, ncalls)
+    return out
 
 
 # ---- public entry points ----------------------------------------------------------------------------------------------

@@ -75,6 +75,27 @@ def test_band_spline_halo_path(ofri, nb, shape):
     same(V, Vref, "V all-gather nb=%d" % nb)
 
 
+@pytest.mark.parametrize("nb", [1, 2, 4])
+def test_band_reference_golden_2048(ofri, big2048, nb):
+    """The row-band path against the REFERENCE itself (not against this library's single-GPU path): one seeded synthetic
+    2048 x 2048 pair, full EX3 parameters, nb virtual bands on one GPU (N = 2, 4: ghost-row exchanges every 32 sweeps,
+    all-reduced Liu-Shen maxima / residuals, halo-fed windowed spline solve)."""
+    from opticalflow_ri_b200 import banded
+    g = big2048
+    mk = lambda: CASES_FULL(ofri)
+    U, V = banded.flow_banded_local(g["im0"], g["im1"], mk, nb)
+    du, dv = float(np.max(np.abs(U - g["U"]))), float(np.max(np.abs(V - g["V"])))
+    Ut, Vt = O.poiseuille_truth(2048, 2048)
+    de = abs(O.epe_rmse(U, V, Ut, Vt) - O.epe_rmse(g["U"], g["V"], Ut, Vt))
+    print("\n2048^2, %d band(s) vs reference: max|dU| %.3g max|dV| %.3g |dEPE-RMSE| %.3g" % (nb, du, dv, de))
+    assert du <= 1e-4 and dv <= 1e-4 and de <= 1e-6, (du, dv, de)
+
+
+def CASES_FULL(o):
+    return o.make_params(o.hs_algo([45, 21], 600), o.ls_algo(5), filter_sigma=3.4, filter_opt_sigma=0.48,
+                         pyramid_levels=2, **HS_DEF)
+
+
 def test_band_plan_and_errors(ofri):
     h = ofri.Handle(0)
     try:

@@ -206,7 +206,7 @@ def test_hs_fused_bit_identical_to_simple(h, shape):
             h.set_option("hs_fuse", 0)
             Ur, Vr = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
             for T in (1, 2, 3, 4, 5, 6, 8):
-                for variant in ((0, 2, 4, 8, 10, 16, 18, 24, 25, 26, 27, 28) if precise == 0 else (0, 2, 24)):
+                for variant in (0, 24):      # shared-memory kernel / persistent TMA kernel
                     h.set_option("hs_fuse", T)
                     h.set_option("hs_variant", variant)
                     U, V = h.hs_iterate(U0, V0, fx, fy, ft, 7.5, nit)
@@ -295,7 +295,7 @@ def test_ls_fused_bit_identical_and_midblock_stop(h, shape):
             h.set_option("ls_fuse", 0)
             Ur, Vr, er, itr = h.ls_compute(g1, g2, U0, V0, 5, maxiter=maxiter, tol=tol)
             for T in (1, 2, 3, 4):
-                for lv in (0, 1, 2, 3, 4, 5, 8, 9):
+                for lv in (0, 8):            # shared-memory kernel / persistent TMA kernel
                     h.set_option("ls_fuse", T)
                     h.set_option("ls_variant", lv)
                     U, V, e, it = h.ls_compute(g1, g2, U0, V0, 5, maxiter=maxiter, tol=tol)
@@ -533,6 +533,64 @@ def test_full_size_properties_1024(h, ofri):
     close(V2[0], V[0], 2e-5)
 
 
+def test_reference_golden_1024_config4(h, ofri, big1024):
+    """BASELINE config 4's frame size against the REFERENCE itself: one seeded synthetic 1024 x 1024 pair, full EX3
+    parameters (HS 600 sweeps alphas [21, 45] + Liu-Shen h = 5, 2 levels), default options -- alone and as a member of a
+    64-pair chunk (the launch shape of the benchmark: 9 x 18 tiles per pair, border tiles in x and y)."""
+    g = big1024
+    mk = lambda: ofri.make_params(ofri.hs_algo([45, 21], 600), ofri.ls_algo(5), filter_sigma=3.4, filter_opt_sigma=0.48,
+                                  pyramid_levels=2, **HS_DEF)
+    Ut, Vt = O.poiseuille_truth(1024, 1024)
+    e_ref = O.epe_rmse(g["U"], g["V"], Ut, Vt)
+    hd = ofri.Handle(0)                     # a fresh handle: every option at its default (auto_fuse included)
+    try:
+        U, V = hd.pyramidal_flow(g["im0"], g["im1"], mk())
+        du, dv = float(np.max(np.abs(U - g["U"]))), float(np.max(np.abs(V - g["V"])))
+        de = abs(O.epe_rmse(U, V, Ut, Vt) - e_ref)
+        print("\n1024^2 single vs reference: max|dU| %.3g max|dV| %.3g |dEPE-RMSE| %.3g (EPE-RMSE ref %.4f)" % (du, dv, de, e_ref))
+        assert du <= TOL_FLOW and dv <= TOL_FLOW and de <= TOL_EPE, (du, dv, de)
+        import torch                         # device memory only (the bench's device-pointer call, 64 pairs per chunk)
+        other = O.synthetic_piv_pair(1024, 1024, seed=3)
+        a = torch.from_numpy(np.stack([other[0]] * 64)).cuda()
+        b = torch.from_numpy(np.stack([other[1]] * 64)).cuda()
+        a[37], b[37] = torch.from_numpy(g["im0"]).cuda(), torch.from_numpy(g["im1"]).cuda()
+        ub, vb = torch.empty_like(a), torch.empty_like(a)
+        torch.cuda.synchronize()
+        hd.pyramidal_flow_ptr(a.data_ptr(), b.data_ptr(), 64, 1024, 1024, mk(), ub.data_ptr(), vb.data_ptr(), None, device=True)
+        hd.synchronize()
+        assert hd.get_option("last_chunk_pairs") == 64
+        Ub, Vb = ub[37].cpu().numpy(), vb[37].cpu().numpy()
+        du, dv = float(np.max(np.abs(Ub - g["U"]))), float(np.max(np.abs(Vb - g["V"])))
+        print("1024^2 in a 64-pair chunk vs reference: max|dU| %.3g max|dV| %.3g" % (du, dv))
+        assert du <= TOL_FLOW and dv <= TOL_FLOW, (du, dv)
+        same(Ub, U)                         # and bit-identical to the single-pair call
+        same(Vb, V)
+    finally:
+        hd.close()
+
+
+def test_k_loop_weak_regularisation_goldens(h, ofri, configs_extra):
+    """kLevels = 2 with alpha = 1 and no Liu-Shen refinement: every Horn-Schunck result but the last is consumed by a
+    re-warp (GPOF:392-404), also on the LAST level, so those solves must run the reference arithmetic
+    (hs_needs_precise / feeds_warp in run_pyramid)."""
+    s = configs_extra
+    c0, c1 = s["crop0"], s["crop1"]
+    cases = {
+        "k2a1": lambda: flow(h, ofri, c0, c1, 3.4, ofri.hs_algo([1.0] * 4, 100), 2, 2, **HS_DEF),
+        "l1k2a1": lambda: flow(h, ofri, c0, c1, 3.4, ofri.hs_algo([1.0] * 2, 100), 1, 2, **HS_DEF),
+        "l3k2": lambda: flow(h, ofri, c0, c1, 2.0, ofri.hs_algo([2.0, 2.0, 2.0, 2.0, 0.5, 0.5], 60), 3, 2, **HS_DEF),
+    }
+    bad = []
+    for name, fn in cases.items():
+        U, V = fn()
+        du = float(np.max(np.abs(U - s[name + "_U"])))
+        dv = float(np.max(np.abs(V - s[name + "_V"])))
+        print("\n%s: max|dU| %.3g max|dV| %.3g" % (name, du, dv))
+        if not (du <= TOL_FLOW and dv <= TOL_FLOW):
+            bad.append((name, du, dv))
+    assert not bad, bad
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # biLinear = False: the "Liu-Shen warp" branch (GPOF:190-196, 204-221)
 # ---------------------------------------------------------------------------------------------------------------
@@ -677,3 +735,114 @@ def test_dropin_foreign_adapter_generic_path(ofri, configs_small):
     U, V = genericPyramidalOpticalFlow(s["crop0"], s["crop1"], 3.4, Foreign(), 2, 1)
     same(U, s["bom_HS_Fs3_4_PyrLvls2_U"])      # GPU stages are bit-exact and the oracle HS is bit-exact
     same(V, s["bom_HS_Fs3_4_PyrLvls2_V"])
+
+
+def test_dropin_foreign_main_native_liu_shen_refinement(ofri, configs_bundled, bundled_pair):
+    """SURVEY 8f-3 (examples/LiuSE_denseLK_Fs2_0_PyrLvls2.py:68-74, LiuSE_Farneback_Fs0_0_PyrLvls2.py:70-76): a FOREIGN
+    main adapter refined by this package's Liu-Shen adapter.  Foreign main = the oracle's Horn-Schunck wrapped as a
+    third-party plugin, optional = the native Liu-Shen adapter, BASELINE config 3 parameters on the bundled pair: the
+    level stages, the refinement and the accumulation stay on the GPU (ofri_pyramidal_flow_external), only the foreign
+    compute() runs on the host -- and the result must match the reference's c3 golden."""
+    sys.path.insert(0, ofri.SRC_DIR)
+    try:
+        from GenericPyramidalOpticalFlow import genericPyramidalOpticalFlow
+        from PhysicsBasedOpticalFlowLiuShen import LiuShenOpticalFlowAlgoAdapter
+    finally:
+        sys.path.remove(ofri.SRC_DIR)
+    calls = []
+
+    class ForeignHS(object):
+        def __init__(self):
+            self.alphas = [21, 45]
+
+        def compute(self, im1, im2, U, V):
+            calls.append(im1.shape)
+            return O.hs_compute(im1, im2, self.alphas.pop(), 600, U, V)
+
+        def getAlgoName(self):
+            return "foreign HS"
+
+        def hasGenericPyramidalDefaults(self):
+            return True
+
+        def getGenericPyramidalDefaults(self):
+            return {"warping": True, "biLinear": True, "scaling": True}
+
+    I0, I1 = bundled_pair
+    h = ofri.default_handle(0)
+    n0 = h.launch_count
+    U, V = genericPyramidalOpticalFlow(I0, I1, 3.4, ForeignHS(), 2, 1, 0.48, LiuShenOpticalFlowAlgoAdapter(5))
+    assert calls == [(256, 256), (512, 512)]
+    assert h.get_option("last_ls_fuse") > 0 and h.launch_count - n0 > 30        # the refinement ran natively
+    Ur, Vr = configs_bundled["c3_U"], configs_bundled["c3_V"]
+    du, dv = float(np.max(np.abs(U - Ur))), float(np.max(np.abs(V - Vr)))
+    Ut, Vt = O.poiseuille_truth(512, 512)
+    de = abs(O.epe_rmse(U, V, Ut, Vt) - O.epe_rmse(Ur, Vr, Ut, Vt))
+    print("\nforeign HS + native Liu-Shen vs reference c3: max|dU| %.3g max|dV| %.3g |dEPE-RMSE| %.3g" % (du, dv, de))
+    assert du <= TOL_FLOW and dv <= TOL_FLOW and de <= TOL_EPE, (du, dv, de)
+
+    class Failing(ForeignHS):
+        def compute(self, im1, im2, U, V):
+            raise RuntimeError("adapter exploded")
+
+    with pytest.raises(RuntimeError, match="adapter exploded"):      # the adapter's own exception reaches the caller
+        genericPyramidalOpticalFlow(I0, I1, 3.4, Failing(), 2, 1, 0.48, LiuShenOpticalFlowAlgoAdapter(5))
+
+
+def test_sequence_pipeline(ofri, tmp_path):
+    """File -> GPU -> file pipeline (opticalflow_ri_b200/pipeline.py): packbits TIFF frames decoded into a
+    ring of page-locked slots, one native call per slot, .mat files in the reference's layout -- results identical to the
+    direct call on the same frames."""
+    Image = pytest.importorskip("PIL.Image")
+    sio = pytest.importorskip("scipy.io")
+    from opticalflow_ri_b200.pipeline import SequencePipeline
+    H, W, n = 96, 160, 7
+    frames = []
+    for i in range(n + 1):
+        a, b = O.synthetic_piv_pair(H, W, seed=40 + i // 2)
+        f = a if i % 2 == 0 else b
+        frames.append(f)
+        Image.fromarray(f.astype(np.uint8)).save(tmp_path / ("fr_%02d.tif" % i), compression="packbits")
+    mk = lambda: ofri.make_params(ofri.hs_algo([45, 21], 40), ofri.ls_algo(5), filter_sigma=3.4, filter_opt_sigma=0.48,
+                                  pyramid_levels=2, **HS_DEF)
+    hd = ofri.Handle(0)
+    try:
+        pin = hd.pinned_empty((3, 5))
+        pin[...] = 7.0
+        assert pin.shape == (3, 5) and float(pin.sum()) == 105.0
+        pipe = SequencePipeline(hd, mk, H, W, batch=3, ring=2, decode_workers=2)
+        pairs = [(str(tmp_path / ("fr_%02d.tif" % i)), str(tmp_path / ("fr_%02d.tif" % (i + 1))), "flow_%02d" % i)
+                 for i in range(n)]
+        out = tmp_path / "out"
+        st = pipe.run(pairs, out_dir=str(out))
+        assert st["pairs"] == n and hd.get_option("last_host_path") == 1          # pinned slots: direct asynchronous copies
+        Ud, Vd = hd.pyramidal_flow(np.stack(frames[:-1]), np.stack(frames[1:]), mk())
+        for i in range(n):
+            m = sio.loadmat(str(out / ("flow_%02d.mat" % i)), squeeze_me=True, struct_as_record=False)
+            same(m["velocities"].u, Ud[i])
+            same(m["velocities"].v, Vd[i])
+    finally:
+        hd.close()
+
+
+def test_pageable_bounce_ring_equals_direct(ofri):
+    """Host-pointer call with PAGEABLE numpy arrays over several chunks: the pinned bounce ring (two host threads) must
+    deliver exactly what the direct-copy path delivers, errors included."""
+    rng = np.random.default_rng(5)
+    a = np.stack([rand_img(rng, 64, 80) for _ in range(11)])
+    b = np.stack([rand_img(rng, 64, 80) for _ in range(11)])
+    mk = lambda: ofri.make_params(ofri.hs_algo([45, 21], 20), ofri.ls_algo(5), filter_sigma=3.4, filter_opt_sigma=0.48,
+                                  pyramid_levels=2, **HS_DEF)
+    hd = ofri.Handle(0)
+    try:
+        hd.set_option("chunk_pairs", 3)                      # 4 chunks, the last one ragged
+        U, V, E = hd.pyramidal_flow(a, b, mk(), want_errors=True)
+        assert hd.get_option("last_host_path") == 2
+        hd.set_option("host_bounce", 0)
+        U0, V0, E0 = hd.pyramidal_flow(a, b, mk(), want_errors=True)
+        assert hd.get_option("last_host_path") == 1
+        same(U, U0)
+        same(V, V0)
+        same(E, E0)
+    finally:
+        hd.close()

@@ -33,11 +33,23 @@ def test_band_protocol_gloo(world):
 
 
 def test_bench_reference_arm_under_torchrun():
-    r = torchrun(2, "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-sample", "40",
-                 "--cpu-cores", "2")
+    r = torchrun(2, "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1", "--cpu-sample", "40",
+                 "--cpu-cores", "2", "--ref-port")
     assert r.returncode == 0, r.stderr[-4000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["gpu_launches"] == 0 and d["value"] > 0
+    assert d["steps"] == 2 and d["steps_requested"] == 2 and d["warmup"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert set(d["config"]) == {"workload", "pairs_per_gpu", "H", "W", "parallelism", "l2"}     # no tuning keys: same as the GPU arm's
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="the unmodified reference is only present in the build container")
+def test_bench_reference_arm_uses_the_real_reference_when_present():
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "48",
+                        "--cpu-cores", "1"], cwd=ROOT, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0, r.stderr[-4000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["kind"] == "reference" and d["value"] > 0
