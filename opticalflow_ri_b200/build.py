@@ -43,7 +43,7 @@ def build(force=False, verbose=False, phase_timing=False):
     os.makedirs(bdir, exist_ok=True)
     for s in SOURCES:
         o = os.path.join(bdir, s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-DOFRI_PHASE_TIMING"] if phase_timing else []) + \
+        cmd = [nvcc] + NVCC_FLAGS + (["-DOFRI_PHASE_TIMING"] + os.environ.get("OFRI_EXTRA_DEFS", "").split() if phase_timing else []) + \
             (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)

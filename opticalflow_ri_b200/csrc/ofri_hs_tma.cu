@@ -26,6 +26,14 @@
 // HBM reads of tile i+1 therefore run under the arithmetic of tile i, with a single CTA (8-12 warps, up to 255
 // registers per thread) per SM and no redundant staging of state through shared memory during the sweeps.
 // Algorithmic HBM traffic: 28 B per pixel per launch (read U, V, a, b, c; write U, V) for T sweeps.
+//
+// Tried in round 2 and removed again (profiles/r2_cluster_experiment.md): the same kernel as thread-block CLUSTERS of two
+// CTAs that form one 130-row tile, the row between the halves exchanged every sweep through distributed shared memory
+// (st.async + mbarrier in the partner's shared memory, split cluster barrier per tile, the lower CTA holding its half
+// upside down so that both run the same sweep code).  Bit-identical and dead-lock free, but slower: the row group that
+// talks to the partner carries the extra mbarrier test / arm / st.async latency on its critical path in EVERY sweep and
+// all other row groups wait for it at the sweep's CTA barrier (+21 % per sweep, phase profile), which eats the 14 % more
+// useful rows per tile: 56.8 ms per 64 pairs at T = 8 against 55.2 (T = 8) / 54.2 (T = 4) for this kernel.
 #include "ofri_hs_common.cuh"
 #include "ofri_tma.cuh"
 
@@ -472,6 +480,7 @@ hs_tma_kernel(const __grid_constant__ CUtensorMap mU, const __grid_constant__ CU
   }
   OFRI_PH_FLUSH;
 }
+
 
 template <int T, int R, int NRG, bool PRECISE>
 static bool launch_cfg(const Img& ui, const Img& vi, const Img& uo, const Img& vo, const Img& fx, const Img& fy,

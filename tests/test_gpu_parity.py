@@ -188,7 +188,7 @@ def test_hs_compute_golden(h, stages, nit, fuse):
         h.set_option("hs_precise", 1)
 
 
-@pytest.mark.parametrize("shape", [(45, 58), (301, 517), (512, 512), (2, 2), (9, 1030)])
+@pytest.mark.parametrize("shape", [(45, 58), (301, 517), (512, 512), (2, 2), (9, 1030), (122, 130), (247, 120)])
 def test_hs_fused_bit_identical_to_simple(h, shape):
     """Temporal blocking must not change a single bit: every (T, tile variant) against one-sweep-per-launch."""
     rng = np.random.default_rng(shape[0] * 1000 + shape[1])

@@ -20,7 +20,7 @@ from opticalflow_ri_b200.synthetic import synthetic_piv_pair  # noqa: E402
 
 P = int(os.environ.get("SWEEP_PAIRS", "64"))
 H = W = int(os.environ.get("SWEEP_SIZE", "1024"))
-HS_NAMES = ["tma_wait", "ghosts", "stage_to_regs", "sweeps", "stores", "decode", "-", "-"]
+HS_NAMES = ["tma_wait", "ghosts", "stage_to_regs", "sweeps", "stores", "decode", "cluster_barrier", "partner_wait(in sweeps)"]
 LS_NAMES = ["tma_wait", "-", "stage_to_regs", "sweeps+stores", "final_barrier", "bookkeeping", "-", "-"]
 h = ofri.Handle(0)
 base = [synthetic_piv_pair(H, W, s) for s in range(4)]
@@ -52,7 +52,6 @@ def run(tag, **opts):
     print(json.dumps(out), flush=True)
 
 
-run("default")
-run("hs_T8", hs_fuse=8)
-run("hs_T4_ls_T4", hs_fuse=4, ls_fuse=4)
-run("hs_precise_everywhere", hs_precise=2, ls_fuse=2)
+for spec in os.environ.get("PHASE_RUNS", "default;hs_T8:hs_fuse=8;hs_precise_everywhere:hs_precise=2").split(";"):
+    tag, _, kv = spec.partition(":")
+    run(tag, **{k: int(v) for k, v in (x.split("=") for x in kv.split(",") if x)})
