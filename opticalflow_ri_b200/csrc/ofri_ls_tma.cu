@@ -268,16 +268,42 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
     float* const pV0 = vo.p + ((long)tl.b * vo.stride + (long)gy0 * vo.pitch + gx);
     const long qU = uo.pitch, qV = vo.pitch;
 
+    // which strip rows count for the residual (the tile's own output cells of the rows this band owns: every pixel is
+    // counted by exactly one tile) and which are stored -- one bit per row, so the sweep body has no per-row branches
+    // (they end ptxas' scheduling regions: 6 % of the sweep's samples were branch_resolving in the round-1 profile)
+    unsigned resmask = 0u, stmask = 0u;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int sy = r0 + j, gy = gy0 + j;
+      const bool own = in_cols && (sy >= T) && (sy < SH - T) && (gy < H);
+      if (own && gy >= own_lo_ && gy < own_hi_) resmask |= 1u << j;
+      if (own && gx < W) stmask |= 1u << j;
+    }
     auto sweep_all = [&](auto edge_tag) {
       constexpr bool EDGE = decltype(edge_tag)::value;
+      float pu2 = 0.0f, pv2 = 0.0f;        // residual partial sums of the PREVIOUS sweep, reduced under this sweep's arithmetic
+      auto reduce_pending = [&](int sweep) {
+        // f32 butterfly over the warp (a balanced tree: relative error ~1e-7, below the f32 rounding of the reference's
+        // own BLAS norm), then f64 accumulation in the warp's own shared slot (no atomics)
+        float su = pu2, sv = pv2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          su = fadd(su, __shfl_xor_sync(0xffffffffu, su, o));
+          sv = fadd(sv, __shfl_xor_sync(0xffffffffu, sv, o));
+        }
+        if (lane == 0) {
+          sh->acc[sweep][rg][0] += (double)su;
+          sh->acc[sweep][rg][1] += (double)sv;
+        }
+      };
 #pragma unroll 1
       for (int s = 0; s < T; ++s) {
         const int cur = s & 1;
-        const bool last = s + 1 == T;
         float du2 = 0.0f, dv2 = 0.0f;
         float wu[3][6], wv[3][6];
         lt_row6_smem<EDGE>(X(cur, 0, rg, 1), X(cur, 1, rg, 1), eg, wu[0], wv[0]);
         lt_row6_vals<EDGE>(u[0], v[0], eg, wu[1], wv[1]);
+        if (s > 0) reduce_pending(s - 1);  // its 10 dependent shuffles hide under the rows below instead of before the barrier
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           const int A = j % 3, B = (j + 1) % 3, Cc = (j + 2) % 3;
@@ -292,39 +318,24 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
             ls_row_update_regs<EDGE>(wu[A], wu[B], wu[B], wv[A], wv[B], wv[B], k[j], hpar, false, true, eg, ou, ov);
           else
             ls_row_update_regs<EDGE>(wu[A], wu[B], wu[Cc], wv[A], wv[B], wv[Cc], k[j], hpar, false, false, eg, ou, ov);
-          // residual over the tile's own output cells (each pixel counted by exactly one tile) of the owned rows
-          const int sy = r0 + j, gy = gy0 + j;
-          const bool own = in_cols && (sy >= T) && (sy < SH - T) && (gy < H);
-          if (own && gy >= own_lo_ && gy < own_hi_) {
+          // residual of the row (LS:79), weighted 1 / 0 by the row's bit; EDGE: cells beyond the last column do not count
+          float ru = 0.0f, rv = 0.0f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (!EDGE || gx + q < W) {
-                const float eu = fsub(ou[q], wu[B][q + 1]), ev = fsub(ov[q], wv[B][q + 1]);
-                du2 = fmaf(eu, eu, du2);
-                dv2 = fmaf(ev, ev, dv2);
-              }
-            }
+          for (int q = 0; q < 4; ++q) {
+            float eu = fsub(ou[q], wu[B][q + 1]), ev = fsub(ov[q], wv[B][q + 1]);
+            if (EDGE && gx + q >= W) { eu = 0.0f; ev = 0.0f; }
+            ru = fmaf(eu, eu, ru);
+            rv = fmaf(ev, ev, rv);
           }
-          if (last && own && gx < W) {
-            *reinterpret_cast<float4*>(pU0 + j * qU) = make_float4(ou[0], ou[1], ou[2], ou[3]);
-            *reinterpret_cast<float4*>(pV0 + j * qV) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-          }
+          const float wj = (resmask >> j) & 1u ? 1.0f : 0.0f;
+          du2 = fmaf(wj, ru, du2);
+          dv2 = fmaf(wj, rv, dv2);
 #pragma unroll
           for (int q = 0; q < 4; ++q) { u[j][q] = ou[q]; v[j][q] = ov[q]; }
         }
-        // residual: f32 butterfly over the warp (a balanced tree: relative error ~1e-7, below the f32 rounding of the
-        // reference's own BLAS norm), then f64 accumulation in the warp's own shared slot (no atomics)
-        float su = du2, sv = dv2;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          su = fadd(su, __shfl_xor_sync(0xffffffffu, su, o));
-          sv = fadd(sv, __shfl_xor_sync(0xffffffffu, sv, o));
-        }
-        if (lane == 0) {
-          sh->acc[s][rg][0] += (double)su;
-          sh->acc[s][rg][1] += (double)sv;
-        }
-        if (!last) {
+        pu2 = du2;
+        pv2 = dv2;
+        if (s + 1 < T) {
           const int nxt = cur ^ 1;
           *reinterpret_cast<float4*>(X(nxt, 0, rg + 1, 0)) = make_float4(u[0][0], u[0][1], u[0][2], u[0][3]);
           *reinterpret_cast<float4*>(X(nxt, 1, rg + 1, 0)) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
@@ -333,9 +344,18 @@ ls_tma_kernel(const __grid_constant__ LtMaps maps, Img uo, Img vo, int W, int H,
           __syncthreads();
         }
       }
+      reduce_pending(T - 1);
     };
     if (edge) sweep_all(std::true_type{});
     else sweep_all(std::false_type{});
+    // the tile's own cells -> HBM from the registers of the last sweep (4 rows x 2 planes per thread)
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if ((stmask >> j) & 1u) {
+        *reinterpret_cast<float4*>(pU0 + j * qU) = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
+        *reinterpret_cast<float4*>(pV0 + j * qV) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+      }
+    }
     OFRI_PH(3);
     __syncthreads();   // exchange buffers free for the next tile
     OFRI_PH(4);
