@@ -869,7 +869,7 @@ int finish(ofri_handle h) {
 //   * Pillow's resample and the warp use GLOBAL row coordinates (tap tables of the whole image; float32 rounding of
 //     y +- v/2 depends on the magnitude of y).
 // Owned rows are therefore bit-identical to the single-GPU result (tested with N virtual bands on one GPU).
-struct BandLevel { int Hl, Wl, own0, own1, ext0, ext1; };
+struct BandLevel { int Hl, Wl, own0, own1, ext0, ext1, G; };
 struct BandPlanInt {
   int L = 0, E = 0, Rw = 0, G = 0, in0 = 0, in1 = 0;
   BandLevel lv[16];
@@ -913,8 +913,17 @@ int make_band_plan_opts(ofri_handle h, int H, int W, const ofri_params* p, int r
                   per, E);
     b.own0 = rank * per;
     b.own1 = b.own0 + per;
-    b.ext0 = b.own0 - bp->G < 0 ? 0 : b.own0 - bp->G;
-    b.ext1 = b.own1 + bp->G > b.Hl ? b.Hl : b.own1 + bp->G;
+    // ghost rows of this level: E sweeps between exchanges + the derivative and Gaussian rows, + the rows the warp may
+    // reach on every level that is warped (all but the coarsest): the coarsest level's smaller frame saves a tile row of
+    // its bands (8 ranks, 16384^2: 1092 instead of 1108 rows = 22 instead of 23 tile rows = 11 instead of 12 waves)
+    // (rows the one-off stages spoil at a band edge: main pre-filter half-width + 1 derivative row, or optional
+    // pre-filter half-width + 1 Liu-Shen coefficient row)
+    int spoil = p->n_taps_main / 2 + 1;
+    if (p->opt_algo.kind != OFRI_ALGO_NONE && p->n_taps_opt / 2 + 1 > spoil) spoil = p->n_taps_opt / 2 + 1;
+    if (p->main_algo.kind == OFRI_ALGO_LS && spoil < 2) spoil = 2;
+    b.G = l > 0 ? E + (spoil > 2 ? spoil : 2) + bp->Rw : E + spoil;
+    b.ext0 = b.own0 - b.G < 0 ? 0 : b.own0 - b.G;
+    b.ext1 = b.own1 + b.G > b.Hl ? b.Hl : b.own1 + b.G;
     long lo = (long)f * b.ext0 - (f > 1 ? 2L * f : 0), hi = (long)f * (b.ext1 - 1) + (f > 1 ? 3L * f : 1);
     if (lo < in0) in0 = lo;
     if (hi > in1) in1 = hi;
@@ -1173,8 +1182,8 @@ int run_pyramid_banded(ofri_handle h, const float* d_im1, const float* d_im2, in
       // all-gather of the whole coarse plane.
       int halo = 0;
       for (int rr = 0; rr < n; ++rr) {
-        const int e0 = rr * per_f - bp.G < 0 ? 0 : rr * per_f - bp.G;
-        const int e1 = (rr + 1) * per_f + bp.G > bl.Hl ? bl.Hl : (rr + 1) * per_f + bp.G;
+        const int e0 = rr * per_f - bl.G < 0 ? 0 : rr * per_f - bl.G;
+        const int e1 = (rr + 1) * per_f + bl.G > bl.Hl ? bl.Hl : (rr + 1) * per_f + bl.G;
         int lo, hi;
         spline_rows_needed(e0, e1 - e0, pl.Hl, bl.Hl, sy, &lo, &hi);
         if (rr * per_c - lo > halo) halo = rr * per_c - lo;
@@ -2043,7 +2052,7 @@ int ofri_band_plan(ofri_handle h, int H, int W, const ofri_params* p, int rank, 
   out->rank = rank; out->nranks = nranks;
   out->own0 = f.own0; out->own1 = f.own1;
   out->in0 = bp.in0; out->in1 = bp.in1;
-  out->ghost = bp.G; out->exchange = bp.E;
+  out->ghost = f.G; out->exchange = bp.E;
   return OFRI_OK;
 }
 int ofri_band_plan_host(int H, int W, const ofri_params* p, int rank, int nranks, int hs_fuse, int band_exchange,
@@ -2056,7 +2065,7 @@ int ofri_band_plan_host(int H, int W, const ofri_params* p, int rank, int nranks
   out->rank = rank; out->nranks = nranks;
   out->own0 = f.own0; out->own1 = f.own1;
   out->in0 = bp.in0; out->in1 = bp.in1;
-  out->ghost = bp.G; out->exchange = bp.E;
+  out->ghost = f.G; out->exchange = bp.E;
   return OFRI_OK;
 }
 int ofri_pyramidal_flow_banded_dev(ofri_handle h, const float* d_im1_rows, const float* d_im2_rows, int H, int W,
