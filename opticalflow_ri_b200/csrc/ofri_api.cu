@@ -1460,6 +1460,10 @@ int ofri_set_option(ofri_handle h, const char* key, int value) {
 }
 int ofri_get_option(ofri_handle h, const char* key, int* value) {
   OFRI_ENTER(h);
+  if (key && value && !strcmp(key, "comm_peer_allreduce")) {      // read-only: which all-reduce the communicator uses
+    *value = h->comm ? h->comm->peer_allreduce() : 0;
+    return OFRI_OK;
+  }
   int* s = option_slot(h, key);
   if (!s || !value) return fail(h, OFRI_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
   *value = *s;

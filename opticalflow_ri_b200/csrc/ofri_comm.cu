@@ -1,8 +1,9 @@
 // ofri_comm.cu -- communication back ends of the row-band (domain-decomposed) driver.  Host code only.
 //
-//   NcclComm   one process per GPU (torchrun): ncclSend/ncclRecv for the ghost rows, ncclAllReduce for the scalar
-//              reductions (Liu-Shen image maxima and residual sums, Horn-Schunck error sums), ncclAllGather for the
-//              coarse flow before the spline up-sample.  libnccl.so.2 is opened with dlopen at first use (the copy
+//   NcclComm   one process per GPU (torchrun): ncclSend/ncclRecv for the ghost rows, ncclAllGather for the coarse flow
+//              before the spline up-sample; the scalar reductions (Liu-Shen image maxima and residual sums,
+//              Horn-Schunck error sums) go through a one-kernel all-reduce over NVLink peer memory (CUDA IPC mailboxes,
+//              below) and fall back to ncclAllReduce when IPC is not available.  libnccl.so.2 is opened with dlopen at first use (the copy
 //              already loaded by torch.distributed when there is one), so libofri.so has no link-time NCCL dependency.
 //   LocalComm  N bands driven by N host threads of ONE process (on one GPU or on peer-accessible GPUs): stream-ordered
 //              device-to-device copies synchronised with CUDA events and host barriers -- no kernel ever waits on
@@ -10,6 +11,7 @@
 //              reproduce the single-band result bit for bit) and of single-process multi-GPU runs.
 // The reference has no counterpart (it is single-process, single-threaded).
 #include <dlfcn.h>
+#include <stdlib.h>
 
 #include <condition_variable>
 #include <cstring>
@@ -22,12 +24,73 @@
 namespace ofri {
 
 // ---------------------------------------------------------------------------------------------------------------
+// Small-payload all-reduce over NVLink peer memory (one process per GPU, CUDA IPC).
+//
+// The row-band driver all-reduces a handful of scalars many times per solve -- 2 x T residual sums after every fused
+// Liu-Shen block (the next block's stopping rule needs them, so the reduction sits on the critical path: 15 per pyramid
+// level), the image maxima, the Horn-Schunck error sums.  An NCCL all-reduce of 8 doubles costs a kernel launch plus
+// ~20-30 us of protocol at 8 ranks; this one is a single 1-CTA kernel of our own: every rank writes its values straight
+// into a mailbox in EVERY peer's HBM (peer stores through the IPC mapping), raises a flag there, waits for the flags of
+// all ranks in its own mailbox and sums the contributions in RANK ORDER (so all ranks compute bit-identical results and
+// take identical decisions).  Mailboxes are double buffered by the parity of a sequence number: a rank cannot be two
+// reductions ahead of a peer (it needs the peer's contribution to the one in between), so parity never collides.
+// Ranks run on different GPUs, so the kernels that wait on one another are guaranteed to run concurrently; a generous
+// timeout traps instead of hanging the GPU if a peer has died.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMailRanks = 8;      // one NVSwitch box
+constexpr int kMailVals = 64;      // values per reduction
+struct PeerMail {
+  unsigned long long data[2][kMailRanks][kMailVals];   // [parity][sender][i]: doubles or uint32 as 64-bit words
+  unsigned flag[2][kMailRanks];                         // [parity][sender] = sequence number once the data is in place
+};
+struct PeerMailPtrs { PeerMail* m[kMailRanks]; };
+
+template <bool IS_MAX>
+__global__ void __launch_bounds__(kMailVals)
+peer_allreduce_kernel(PeerMailPtrs peers, int rank, int nranks, unsigned seq, void* values, int n) {
+  const int t = threadIdx.x, par = (int)(seq & 1u);
+  unsigned long long mine = 0ull;
+  if (t < n) mine = IS_MAX ? (unsigned long long)reinterpret_cast<unsigned*>(values)[t]
+                           : reinterpret_cast<unsigned long long*>(values)[t];
+  if (t < n)
+    for (int r = 0; r < nranks; ++r) peers.m[r]->data[par][rank][t] = mine;      // peer stores over NVLink (r == rank: local)
+  __threadfence_system();
+  __syncthreads();
+  if (t < nranks) {
+    *reinterpret_cast<volatile unsigned*>(&peers.m[t]->flag[par][rank]) = seq;  // "rank's data for #seq is in your mailbox"
+    volatile unsigned* f = &peers.m[rank]->flag[par][t];                         // wait for rank t's contribution
+    long long t0 = clock64();
+    while (*f != seq) {
+      __nanosleep(200);
+      if (clock64() - t0 > 120000000000ll) __trap();                             // ~60 s: a peer died; fail instead of hanging
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < n) {
+    volatile unsigned long long* d = &peers.m[rank]->data[par][0][t];
+    if (IS_MAX) {
+      unsigned m = 0u;
+      for (int r = 0; r < nranks; ++r) {
+        const unsigned v = (unsigned)d[(size_t)r * kMailVals];
+        m = v > m ? v : m;
+      }
+      reinterpret_cast<unsigned*>(values)[t] = m;
+    } else {
+      double acc = 0.0;
+      for (int r = 0; r < nranks; ++r) acc += __longlong_as_double((long long)d[(size_t)r * kMailVals]);   // rank order: deterministic
+      reinterpret_cast<double*>(values)[t] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // NCCL through dlopen (minimal declarations of the stable C API, NCCL 2.x)
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 typedef void* ncclComm_t;
 struct ncclUniqueId { char internal[128]; };
-enum { kNcclUint32 = 3, kNcclFloat32 = 7, kNcclFloat64 = 8 };
+enum { kNcclInt8 = 0, kNcclUint32 = 3, kNcclFloat32 = 7, kNcclFloat64 = 8 };
 enum { kNcclSum = 0, kNcclMax = 2 };
 struct NcclApi {
   void* lib = nullptr;
@@ -78,8 +141,67 @@ struct NcclComm : Comm {
   NcclApi* a = nullptr;
   ncclComm_t comm = nullptr;
   std::string err;
+  // peer mailboxes of the small-payload all-reduce (null = not available: NCCL does those reductions too)
+  PeerMail* mail = nullptr;
+  PeerMailPtrs peers = {};
+  bool have_mail = false;
+  unsigned seq = 0;
   ~NcclComm() override {
+    if (have_mail)
+      for (int r = 0; r < nranks; ++r)
+        if (r != rank && peers.m[r]) cudaIpcCloseMemHandle(peers.m[r]);
+    if (mail) cudaFree(mail);
     if (comm) a->CommDestroy(comm);
+  }
+  // exchange CUDA IPC handles of the mailboxes through the communicator itself; any failure leaves have_mail = false
+  void setup_mail() {
+    if (nranks < 2 || nranks > kMailRanks) return;
+    if (getenv("OFRI_NO_PEER_ALLREDUCE")) return;
+    cudaIpcMemHandle_t mine;
+    char* d_handles = nullptr;
+    std::vector<char> h_handles((size_t)nranks * sizeof(cudaIpcMemHandle_t));
+    bool ok = cudaMalloc(&mail, sizeof(PeerMail)) == cudaSuccess && cudaMemset(mail, 0, sizeof(PeerMail)) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine, mail) == cudaSuccess &&
+              cudaMalloc(&d_handles, h_handles.size()) == cudaSuccess;
+    if (ok)
+      ok = cudaMemcpy(d_handles + (size_t)rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess &&
+           a->AllGather(d_handles + (size_t)rank * sizeof(mine), d_handles, sizeof(mine), kNcclInt8, comm, nullptr) == 0 &&
+           cudaDeviceSynchronize() == cudaSuccess &&
+           cudaMemcpy(h_handles.data(), d_handles, h_handles.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+    // every rank must reach the same verdict: all-reduce "ok" with NCCL itself (min over ranks as max of the negation)
+    unsigned* d_flag = nullptr;
+    int opened = 0;
+    if (ok) {
+      for (int r = 0; r < nranks && ok; ++r) {
+        if (r == rank) { peers.m[r] = mail; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, h_handles.data() + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        ok = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        peers.m[r] = (PeerMail*)p;
+        if (ok) ++opened;
+      }
+    }
+    unsigned bad = ok ? 0u : 1u;
+    if (cudaMalloc(&d_flag, sizeof(unsigned)) == cudaSuccess) {
+      cudaMemcpy(d_flag, &bad, sizeof(bad), cudaMemcpyHostToDevice);
+      if (a->AllReduce(d_flag, d_flag, 1, kNcclUint32, kNcclMax, comm, nullptr) != 0) bad = 1u;
+      cudaDeviceSynchronize();
+      unsigned any = 1u;
+      cudaMemcpy(&any, d_flag, sizeof(any), cudaMemcpyDeviceToHost);
+      bad |= any;
+      cudaFree(d_flag);
+    } else {
+      bad = 1u;
+    }
+    if (d_handles) cudaFree(d_handles);
+    cudaGetLastError();
+    have_mail = bad == 0u;
+    if (!have_mail) {
+      for (int r = 0; r < nranks; ++r)
+        if (r != rank && peers.m[r]) { cudaIpcCloseMemHandle(peers.m[r]); peers.m[r] = nullptr; }
+      (void)opened;
+    }
   }
   int check(int rc, const char* what) {
     if (rc == 0) return 0;
@@ -104,9 +226,17 @@ struct NcclComm : Comm {
     return check(rc ? rc : rc2, "ncclSend/ncclRecv");
   }
   int allreduce_sum(double* p, size_t n, cudaStream_t s) override {
+    if (have_mail && n <= (size_t)kMailVals) {
+      peer_allreduce_kernel<false><<<1, kMailVals, 0, s>>>(peers, rank, nranks, ++seq, p, (int)n);
+      return cudaPeekAtLastError() == cudaSuccess ? 0 : (err = "peer all-reduce launch failed", -1);
+    }
     return check(a->AllReduce(p, p, n, kNcclFloat64, kNcclSum, comm, s), "ncclAllReduce(sum)");
   }
   int allreduce_max_u32(unsigned* p, size_t n, cudaStream_t s) override {
+    if (have_mail && n <= (size_t)kMailVals) {
+      peer_allreduce_kernel<true><<<1, kMailVals, 0, s>>>(peers, rank, nranks, ++seq, p, (int)n);
+      return cudaPeekAtLastError() == cudaSuccess ? 0 : (err = "peer all-reduce launch failed", -1);
+    }
     return check(a->AllReduce(p, p, n, kNcclUint32, kNcclMax, comm, s), "ncclAllReduce(max)");
   }
   int allgather(const float* send, float* recv, size_t count, cudaStream_t s) override {
@@ -114,6 +244,7 @@ struct NcclComm : Comm {
   }
   const char* error() const override { return err.c_str(); }
   bool uses_sms() const override { return true; }
+  int peer_allreduce() const override { return have_mail ? 1 : 0; }
 };
 }  // namespace
 
@@ -143,6 +274,7 @@ Comm* make_nccl_comm(int rank, int nranks, const void* uid128, std::string* err)
     delete c;
     return nullptr;
   }
+  c->setup_mail();      // small-payload all-reduces over peer memory when CUDA IPC works between the ranks
   return c;
 }
 

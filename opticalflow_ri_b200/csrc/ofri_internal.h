@@ -161,6 +161,7 @@ struct Comm {
   virtual int allgather(const float* send, float* recv, size_t count, cudaStream_t s) = 0;   // recv: [nranks][count]
   virtual const char* error() const = 0;
   virtual bool uses_sms() const { return false; }   // true: exchanges run as kernels (NCCL) and need free SMs to overlap
+  virtual int peer_allreduce() const { return 0; }  // 1: the scalar all-reduces run as our own kernel over NVLink peer memory
 };
 struct LocalGroup;
 int nccl_unique_id(void* out128, std::string* err);

@@ -112,7 +112,7 @@ def main():
     st = h.stage_timings()
     if rank == 0:
         px_it = 1.25 * N * N * (args.hs_niter + 60)
-        out.update({"reserve_sms": h.get_option("band_reserve_sms"), "size": N, "ms_per_pair": round(best, 2), "ms_per_pair_all": [round(x, 2) for x in times], "stat": "median", "pairs_per_s": round(1e3 / best, 4),
+        out.update({"peer_allreduce": h.get_option("comm_peer_allreduce"), "reserve_sms": h.get_option("band_reserve_sms"), "size": N, "ms_per_pair": round(best, 2), "ms_per_pair_all": [round(x, 2) for x in times], "stat": "median", "pairs_per_s": round(1e3 / best, 4),
                     "gpix_iter_per_s": round(px_it / (best / 1e3) / 1e9, 1), "rows_owned": band.own1 - band.own0,
                     "rows_supplied": band.in1 - band.in0, "ghost": band.ghost, "exchange_every_sweeps": band.exchange,
                     "finite": bool(torch.isfinite(u).all().item()), "stages_rank0_ms": {k: round(x, 1) for k, x in st.items()}})
