@@ -57,7 +57,8 @@ typedef enum {
 
 /* OFRI_ALGO_EXTERNAL: a foreign adapter (any object with the reference's duck-typed compute(), GPOF:256-290) driven
  * through a callback -- only valid with ofri_pyramidal_flow_external */
-typedef enum { OFRI_ALGO_NONE = -1, OFRI_ALGO_HS = 0, OFRI_ALGO_LS = 1, OFRI_ALGO_EXTERNAL = 2 } ofri_algo_kind;
+typedef enum { OFRI_ALGO_NONE = -1, OFRI_ALGO_HS = 0, OFRI_ALGO_LS = 1, OFRI_ALGO_EXTERNAL = 2,
+               OFRI_ALGO_FB = 3 /* Farneback: parameters from ofri_set_farneback */ } ofri_algo_kind;
 
 /* One optical-flow algorithm adapter (the reference's plugin protocol: compute(im1, im2, U, V) -> (U, V, error),
  * GenericPyramidalOpticalFlow.py:256-290).
@@ -130,6 +131,32 @@ OFRI_API int ofri_debug_phase_read(ofri_handle h, int family, unsigned long long
  * err_out: optional [batch][levels*k_levels][2] = (main error, optional error) per compute call, or NULL. */
 OFRI_API int ofri_pyramidal_flow(ofri_handle h, const float* im1, const float* im2, int batch, int H, int W,
                         const ofri_params* p, float* u_out, float* v_out, float* err_out);
+/* ---- Farneback adapter: replaces Farneback_PyCL (Farneback_PyCL.py:65-616) and its six OpenCL kernels
+ *      (optical_flow_farneback.cl:72-429) -----------------------------------------------------------------------------
+ * Constructor parameters (FB:70-71) plus the coefficient tables the reference computes on the host (the caller passes
+ * them so that they are bit-identical to the reference's: FarnebackPrepareGaussian FB:124-176, setGaussianBlurKernel /
+ * getGaussianKernelBitExact FB:194-207).  extra_levels = pyramidalLevels - 1 (the adapter's INTERNAL pyramid, FB:78);
+ * level k of it runs at scale pyr_scale^k and pre-blurs the frames with blur_kernel[k][0 .. n_blur[k]] (centre + right
+ * half).  win_kernel: centre + right half of the window kernel (use_gaussian), window_size / 2 + 1 entries. */
+#define OFRI_FB_MAX_HALF 64
+#define OFRI_FB_MAX_LEVELS 12
+typedef struct {
+  uint32_t size;                     /* sizeof(ofri_farneback_params) */
+  int32_t  window_size, n_iters, poly_n, use_gaussian, extra_levels;
+  float    pyr_scale;
+  float    g[8], xg[8], xxg[8], ig[4];
+  float    win_kernel[OFRI_FB_MAX_HALF + 1];
+  int32_t  n_blur[OFRI_FB_MAX_LEVELS];
+  float    blur_kernel[OFRI_FB_MAX_LEVELS][OFRI_FB_MAX_HALF + 1];
+} ofri_farneback_params;
+/* compute(im1, im2, U, V) -> (U, V) of the adapter (FB:462-604); u0 / v0 NULL = zero initial flow */
+OFRI_API int ofri_farneback_compute(ofri_handle h, const float* im1, const float* im2, const float* u0, const float* v0,
+                                    int batch, int H, int W, const ofri_farneback_params* fp, float* u_out, float* v_out);
+/* imresize of Farneback_PyCL.py:61-62: Pillow BILINEAR (antialiased triangle filter), up- and down-sampling */
+OFRI_API int ofri_resize_bilinear(ofri_handle h, const float* in, int batch, int H, int W, int out_h, int out_w, float* out);
+/* the parameters an adapter of kind OFRI_ALGO_FB uses inside ofri_pyramidal_flow* (copied into the handle) */
+OFRI_API int ofri_set_farneback(ofri_handle h, const ofri_farneback_params* fp);
+
 /* page-locked host memory for callers without a CUDA binding of their own (opticalflow_ri_b200/pipeline.py: the frame
  * ring of the file -> GPU -> file pipeline): buffers from here make the host-pointer call above fully asynchronous */
 OFRI_API int ofri_host_alloc(ofri_handle h, size_t bytes, void** out);

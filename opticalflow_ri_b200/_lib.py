@@ -11,7 +11,8 @@ HEADER = os.path.join(HERE, "..", "include", "ofri.h")
 
 OFRI_MAX_GAUSS_TAPS = 129
 OFRI_MAX_ALPHAS = 64
-ALGO_NONE, ALGO_HS, ALGO_LS, ALGO_EXTERNAL = -1, 0, 1, 2
+ALGO_NONE, ALGO_HS, ALGO_LS, ALGO_EXTERNAL, ALGO_FB = -1, 0, 1, 2, 3
+OFRI_FB_MAX_HALF, OFRI_FB_MAX_LEVELS = 64, 12
 
 OK = 0
 ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_ALPHAS, ERR_FILTER_OPT, ERR_TOO_SMALL, ERR_UNSUPPORTED, ERR_COMM, \
@@ -40,6 +41,14 @@ class Params(C.Structure):
                 ("taps_lsw", C.c_float * OFRI_MAX_GAUSS_TAPS)]
 
 
+class FarnebackParams(C.Structure):
+    _fields_ = [("size", C.c_uint32), ("window_size", C.c_int32), ("n_iters", C.c_int32), ("poly_n", C.c_int32),
+                ("use_gaussian", C.c_int32), ("extra_levels", C.c_int32), ("pyr_scale", C.c_float),
+                ("g", C.c_float * 8), ("xg", C.c_float * 8), ("xxg", C.c_float * 8), ("ig", C.c_float * 4),
+                ("win_kernel", C.c_float * (OFRI_FB_MAX_HALF + 1)), ("n_blur", C.c_int32 * OFRI_FB_MAX_LEVELS),
+                ("blur_kernel", (C.c_float * (OFRI_FB_MAX_HALF + 1)) * OFRI_FB_MAX_LEVELS)]
+
+
 class Band(C.Structure):
     _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("own0", C.c_int32), ("own1", C.c_int32),
                 ("in0", C.c_int32), ("in1", C.c_int32), ("ghost", C.c_int32), ("exchange", C.c_int32)]
@@ -65,6 +74,9 @@ _SIGNATURES = {
     "ofri_debug_phase_read": (C.c_int, [_H, C.c_int, C.POINTER(C.c_ulonglong)]),
     "ofri_pyramidal_flow": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Params),
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ofri_farneback_compute": (C.c_int, [_H, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(FarnebackParams), _fp, _fp]),
+    "ofri_set_farneback": (C.c_int, [_H, C.POINTER(FarnebackParams)]),
+    "ofri_resize_bilinear": (C.c_int, [_H, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "ofri_host_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),
     "ofri_host_free": (C.c_int, [_H, C.c_void_p]),
     "ofri_pyramidal_flow_external": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Params), ADAPTER_FN,

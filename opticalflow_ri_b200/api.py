@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import ALGO_EXTERNAL, ALGO_HS, ALGO_LS, ALGO_NONE, Algo, Band, OfriError, Params
+from ._lib import ALGO_EXTERNAL, ALGO_FB, ALGO_HS, ALGO_LS, ALGO_NONE, Algo, Band, FarnebackParams, OfriError, Params
 
 _EXC = {_lib.ERR_INVALID: ValueError, _lib.ERR_ALPHAS: IndexError, _lib.ERR_FILTER_OPT: TypeError,
         _lib.ERR_TOO_SMALL: ValueError, _lib.ERR_UNSUPPORTED: NotImplementedError, _lib.ERR_OOM: MemoryError,
@@ -64,6 +64,36 @@ def external_algo():
     a = Algo()
     a.kind = ALGO_EXTERNAL
     return a
+
+
+def fb_algo():
+    """The Farneback adapter as main / optional adapter of make_params; its parameters go to the handle separately
+    (Handle.set_farneback), they do not fit the fixed-size ofri_algo."""
+    a = Algo()
+    a.kind = ALGO_FB
+    return a
+
+
+def farneback_params(window_size, n_iters, poly_n, use_gaussian, extra_levels, pyr_scale, g_half, xg_half, xxg_half, ig,
+                     win_half, blur_halves):
+    """ofri_farneback_params from the adapter's constructor values and its host-side coefficient tables."""
+    p = FarnebackParams()
+    p.size = C.sizeof(FarnebackParams)
+    p.window_size, p.n_iters, p.poly_n = int(window_size), int(n_iters), int(poly_n)
+    p.use_gaussian, p.extra_levels, p.pyr_scale = int(bool(use_gaussian)), int(extra_levels), float(pyr_scale)
+    if int(extra_levels) >= _lib.OFRI_FB_MAX_LEVELS or int(window_size) // 2 > _lib.OFRI_FB_MAX_HALF:
+        raise ValueError("Farneback: too many internal levels / window too large")
+    for dst, src in ((p.g, g_half), (p.xg, xg_half), (p.xxg, xxg_half), (p.ig, ig), (p.win_kernel, win_half)):
+        for i, v in enumerate(np.asarray(src, np.float32).ravel()):
+            dst[i] = float(v)
+    for k, bk in enumerate(blur_halves):
+        bk = np.asarray(bk, np.float32).ravel()
+        if len(bk) - 1 > _lib.OFRI_FB_MAX_HALF:
+            raise ValueError("Farneback: pre-blur kernel too long")
+        p.n_blur[k] = len(bk) - 1
+        for i, v in enumerate(bk):
+            p.blur_kernel[k][i] = float(v)
+    return p
 
 
 def no_algo():
@@ -331,6 +361,32 @@ class Handle:
         out = np.empty((B, out_h, out_w), np.float32)
         self._check(self._L.ofri_resize_bicubic(self._h, _ptr(a), B, H, W, int(out_h), int(out_w), _ptr(out)))
         return out[0] if single else out
+
+    def resize_bilinear(self, img, out_h, out_w):
+        """Pillow-BILINEAR resample (Farneback_PyCL.py:61-62), both directions."""
+        a, single = _batched(img)
+        B, H, W = a.shape
+        out = np.empty((B, out_h, out_w), np.float32)
+        self._check(self._L.ofri_resize_bilinear(self._h, _ptr(a), B, H, W, int(out_h), int(out_w), _ptr(out)))
+        return out[0] if single else out
+
+    def set_farneback(self, fb_params):
+        self._check(self._L.ofri_set_farneback(self._h, C.byref(fb_params)))
+
+    def farneback_compute(self, im1, im2, U0, V0, fb_params):
+        """Farneback_PyCL.compute (FB:462-604): (U, V) initial flow in, refined flow out."""
+        a, single = _batched(im1)
+        b, _ = _batched(im2)
+        u0 = _batched(U0)[0] if U0 is not None else None
+        v0 = _batched(V0)[0] if V0 is not None else None
+        _same_shape(a, im2=b, U0=u0, V0=v0)
+        B, H, W = a.shape
+        U = np.empty((B, H, W), np.float32)
+        V = np.empty((B, H, W), np.float32)
+        self._check(self._L.ofri_farneback_compute(self._h, _ptr(a), _ptr(b), _ptr(u0) if u0 is not None else None,
+                                                   _ptr(v0) if v0 is not None else None, B, H, W, C.byref(fb_params),
+                                                   _ptr(U), _ptr(V)))
+        return (U[0], V[0]) if single else (U, V)
 
     def level_size(self, n, scale):
         return int(self._L.ofri_level_size(int(n), float(scale)))

@@ -57,7 +57,9 @@ struct ofri_ctx {
   std::vector<float> ext_buf;         // dense host copies handed to the callback: im1, im2, U, V
   int last_host_path = 0;        // read-only: 1 = direct copies (pinned caller buffers / one chunk), 2 = pinned bounce ring
   int last_hs_fuse_fine = 0, last_hs_fuse_coarse = 0, last_ls_fuse = 0;   // read-only: fuse factors the last call used
-  std::map<std::pair<int, int>, DevResizeTaps> taps;
+  std::map<std::pair<int, int>, DevResizeTaps> taps, taps_bilinear;
+  ofri_farneback_params fb = {};      // parameters of adapters of kind OFRI_ALGO_FB (ofri_set_farneback)
+  bool fb_set = false;
   std::map<int, DevSplineSys> splines;
   LaunchCounter lc;
   // options
@@ -174,11 +176,12 @@ Img dense(const float* p, int batch, int H, int W) {
 }
 
 // ---- cached per-size tables ----------------------------------------------------------------------------------------
-int get_resize_taps(ofri_handle h, int in_size, int out_size, ResizeTaps* out) {
+int get_resize_taps(ofri_handle h, int in_size, int out_size, ResizeTaps* out, bool bilinear = false) {
   auto key = std::make_pair(in_size, out_size);
-  auto it = h->taps.find(key);
-  if (it == h->taps.end()) {
-    HostResizeTaps t = build_resize_taps(in_size, out_size);
+  auto& cache = bilinear ? h->taps_bilinear : h->taps;
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    HostResizeTaps t = build_resize_taps(in_size, out_size, bilinear);
     DevResizeTaps d;
     d.kmax = t.kmax;
     OFRI_CUDA(h, cudaMalloc(&d.xmin, sizeof(int) * out_size));
@@ -187,7 +190,7 @@ int get_resize_taps(ofri_handle h, int in_size, int out_size, ResizeTaps* out) {
     OFRI_CUDA(h, cudaMemcpy(d.xmin, t.xmin.data(), sizeof(int) * out_size, cudaMemcpyHostToDevice));
     OFRI_CUDA(h, cudaMemcpy(d.cnt, t.cnt.data(), sizeof(int) * out_size, cudaMemcpyHostToDevice));
     OFRI_CUDA(h, cudaMemcpy(d.w, t.w.data(), sizeof(double) * t.w.size(), cudaMemcpyHostToDevice));
-    it = h->taps.emplace(key, d).first;
+    it = cache.emplace(key, d).first;
   }
   out->xmin = it->second.xmin;
   out->cnt = it->second.cnt;
@@ -282,6 +285,10 @@ int check_params(ofri_handle h, const ofri_params* p, int H, int W) {
   const ofri_algo* algos[2] = {&p->main_algo, &p->opt_algo};
   for (int a = 0; a < 2; ++a) {
     const ofri_algo* g = algos[a];
+    if (g->kind == OFRI_ALGO_FB) {
+      if (!h || !h->fb_set) return fail(h, OFRI_ERR_INVALID, "Farneback adapter without ofri_set_farneback");
+      continue;
+    }
     const bool ext_ok = g->kind == OFRI_ALGO_EXTERNAL && h && h->ext_fn;
     if (a == 0 && g->kind != OFRI_ALGO_HS && g->kind != OFRI_ALGO_LS && !ext_ok)
       return fail(h, OFRI_ERR_INVALID, "main adapter must be HS or LS (external adapters: ofri_pyramidal_flow_external)");
@@ -326,7 +333,22 @@ struct Workspace {
   int* ls_state = nullptr;
   unsigned* ls_max = nullptr;
   int* lsw_flag = nullptr;
+  FbWorkspace fb;
 };
+
+void plan_fb_workspace(Bump& b, int batch, int H, int W, FbWorkspace* f) {
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) f->flow[i][j] = b.plane(batch, H, W);
+  f->blur = b.plane(batch, H, W);
+  f->level = b.plane(batch, H, W);
+  f->tmp = b.plane(batch, H, W);
+  for (int i = 0; i < 3; ++i) f->poly[i] = b.plane(batch, H, W);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 5; ++j) f->R[i][j] = b.plane(batch, H, W);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 5; ++j) f->M[i][j] = b.plane(batch, H, W);
+  f->d_imgs = (Img*)b.take(sizeof(Img) * 16);
+}
 
 void plan_workspace(Bump& b, int batch, int H, int W, const ofri_params* p, Workspace* ws) {
   const bool multi = p->pyramid_levels > 1;
@@ -366,6 +388,7 @@ void plan_workspace(Bump& b, int batch, int H, int W, const ofri_params* p, Work
     ws->ls_max = (unsigned*)b.take(sizeof(unsigned) * 2 * batch);
   }
   ws->hs_acc = (double*)b.take(sizeof(double) * 2 * batch);
+  if (p->main_algo.kind == OFRI_ALGO_FB || p->opt_algo.kind == OFRI_ALGO_FB) plan_fb_workspace(b, batch, H, W, &ws->fb);
   if (p->warping && !p->bilinear && (multi || p->k_levels > 1)) {
     if (!multi) { ws->lvl1 = b.plane(batch, H, W); }
     ws->lsw_sc = b.plane(batch, H, W);
@@ -469,6 +492,14 @@ int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws
     if (d_err) cudaMemcpyAsync(d_err, &err, sizeof(float), cudaMemcpyHostToDevice, s);
     if (cudaStreamSynchronize(s) != cudaSuccess)      // the host buffers are reused by the next compute()
       return h->ext_rc = fail(h, OFRI_ERR_CUDA, "H2D after the external adapter failed: %s", cudaGetErrorString(cudaGetLastError())), -1;
+    return cur;
+  }
+  if (a.kind == OFRI_ALGO_FB) {                       // Farneback_PyCL.compute: (U, V) in -> (U, V) out, error 'Unknown'
+    Timed t(h, "farneback");
+    int rc = launch_farneback(im1, im2, U[cur], V[cur], &h->fb, ws.fb,
+                              [h](int in, int out, ResizeTaps* t) { return get_resize_taps(h, in, out, t, true); }, s, h->lc);
+    if (rc) return h->ext_rc = fail(h, rc, "Farneback adapter failed (level %d x %d)", Hl, Wl), -1;
+    if (d_err) cudaMemsetAsync(d_err, 0, sizeof(float), s);
     return cur;
   }
   if (a.kind == OFRI_ALGO_HS) {
@@ -888,6 +919,9 @@ int make_band_plan_opts(ofri_handle h, int H, int W, const ofri_params* p, int r
   if (n < 1 || rank < 0 || rank >= n) return fail(h, OFRI_ERR_INVALID, "bad rank %d of %d", rank, n);
   const int L = p->pyramid_levels;
   if (p->k_levels != 1) return fail(h, OFRI_ERR_UNSUPPORTED, "row-band mode supports kLevels = 1 only");
+  if ((p->main_algo.kind != OFRI_ALGO_HS && p->main_algo.kind != OFRI_ALGO_LS) ||
+      (p->opt_algo.kind != OFRI_ALGO_NONE && p->opt_algo.kind != OFRI_ALGO_HS && p->opt_algo.kind != OFRI_ALGO_LS))
+    return fail(h, OFRI_ERR_UNSUPPORTED, "row-band mode supports the HS and Liu-Shen adapters only");
   if (L > 1 && (!p->warping || !p->bilinear))
     return fail(h, OFRI_ERR_UNSUPPORTED, "row-band mode needs warping = biLinear = True");
   const int fmax = 1 << (L - 1);
@@ -1381,6 +1415,7 @@ int ofri_destroy(ofri_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (auto& kv : h->taps) { cudaFree(kv.second.xmin); cudaFree(kv.second.cnt); cudaFree(kv.second.w); }
+  for (auto& kv : h->taps_bilinear) { cudaFree(kv.second.xmin); cudaFree(kv.second.cnt); cudaFree(kv.second.w); }
   for (auto& kv : h->splines) { cudaFree(kv.second.lo); cudaFree(kv.second.cp); cudaFree(kv.second.den); }
   if (h->arena) cudaFree(h->arena);
   if (h->stage) cudaFree(h->stage);
@@ -1674,6 +1709,73 @@ int ofri_pyramidal_flow(ofri_handle h, const float* im1, const float* im2, int b
   OFRI_CUDA(h, cudaStreamSynchronize(h->s_out));
   rc = finish(h);
   return rc;
+}
+
+int ofri_resize_bilinear(ofri_handle h, const float* in, int batch, int H, int W, int out_h, int out_w, float* out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!in || !out || out_h < 1 || out_w < 1) return fail(h, OFRI_ERR_INVALID, "bad resize arguments");
+  const int mh = out_h > H ? out_h : H, mw = out_w > W ? out_w : W;
+  int rc = arena_reserve(h, (sizeof(float) * (size_t)round_up(mw, 4) * mh * batch + 256) * 3 + 4096);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img i = b.plane(batch, H, W), t = b.plane(batch, H, out_w), o = b.plane(batch, out_h, out_w);
+  ResizeTaps tx, ty;
+  if ((rc = get_resize_taps(h, W, out_w, &tx, true)) || (rc = get_resize_taps(h, H, out_h, &ty, true))) return rc;
+  if ((rc = upload(h, i, in))) return rc;
+  launch_resize(i, t, o, tx, ty, h->stream, h->lc);
+  if ((rc = download(h, out, o))) return rc;
+  return finish(h);
+}
+
+static int check_fb(ofri_handle h, const ofri_farneback_params* fp) {
+  if (!fp) return fail(h, OFRI_ERR_INVALID, "Farneback parameters are NULL");
+  if (fp->size != sizeof(ofri_farneback_params))
+    return fail(h, OFRI_ERR_INVALID, "ofri_farneback_params.size = %u, library expects %zu (ABI mismatch)", fp->size,
+                sizeof(ofri_farneback_params));
+  if (!(fp->window_size & 1)) return fail(h, OFRI_ERR_INVALID, "windowSize must be an odd value");      // FB:97-98
+  if (fp->window_size < 1 || fp->window_size / 2 > OFRI_FB_MAX_HALF) return fail(h, OFRI_ERR_INVALID, "windowSize out of range");
+  if (fp->poly_n != 5 && fp->poly_n != 7) return fail(h, OFRI_ERR_INVALID, "polyN must be 5 or 7");    // FB:463
+  if (!(fp->pyr_scale > 0.0f && fp->pyr_scale < 1.0f)) return fail(h, OFRI_ERR_INVALID, "pyrScale must be in (0, 1)");
+  if (fp->n_iters < 0 || fp->extra_levels < 0 || fp->extra_levels >= OFRI_FB_MAX_LEVELS)
+    return fail(h, OFRI_ERR_INVALID, "bad Farneback iteration / level count");
+  for (int k = 0; k <= fp->extra_levels; ++k)
+    if (fp->n_blur[k] < 0 || fp->n_blur[k] > OFRI_FB_MAX_HALF) return fail(h, OFRI_ERR_INVALID, "pre-blur kernel too long");
+  return OFRI_OK;
+}
+int ofri_set_farneback(ofri_handle h, const ofri_farneback_params* fp) {
+  OFRI_ENTER(h);
+  int rc = check_fb(h, fp);
+  if (rc) return rc;
+  h->fb = *fp;
+  h->fb_set = true;
+  return OFRI_OK;
+}
+int ofri_farneback_compute(ofri_handle h, const float* im1, const float* im2, const float* u0, const float* v0, int batch,
+                           int H, int W, const ofri_farneback_params* fp, float* u_out, float* v_out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!im1 || !im2 || !u_out || !v_out) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
+  int rc = check_fb(h, fp);
+  if (rc) return rc;
+  rc = arena_reserve(h, (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 40 + 8192);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img i1 = b.plane(batch, H, W), i2 = b.plane(batch, H, W), U = b.plane(batch, H, W), V = b.plane(batch, H, W);
+  FbWorkspace ws;
+  plan_fb_workspace(b, batch, H, W, &ws);
+  if ((rc = upload(h, i1, im1)) || (rc = upload(h, i2, im2))) return rc;
+  if (!u0 || !v0) {
+    cudaMemsetAsync(U.p, 0, sizeof(float) * U.stride * batch, h->stream);
+    cudaMemsetAsync(V.p, 0, sizeof(float) * V.stride * batch, h->stream);
+  } else if ((rc = upload(h, U, u0)) || (rc = upload(h, V, v0))) {
+    return rc;
+  }
+  rc = launch_farneback(i1, i2, U, V, fp, ws, [h](int in, int out, ResizeTaps* t) { return get_resize_taps(h, in, out, t, true); },
+                        h->stream, h->lc);
+  if (rc) return fail(h, rc, "Farneback adapter failed");
+  if ((rc = download(h, u_out, U)) || (rc = download(h, v_out, V))) return rc;
+  return finish(h);
 }
 
 int ofri_host_alloc(ofri_handle h, size_t bytes, void** out) {

@@ -179,6 +179,17 @@ bool launch_ls_tma(int T, const Img& ui, const Img& vi, const Img& uo, const Img
 void hs_tma_phase_read(unsigned long long* out8);
 void ls_tma_phase_read(unsigned long long* out8);
 
+// ---- Farneback adapter (ofri_farneback.cu) ------------------------------------------------------------------------------
+struct FbWorkspace {
+  Img flow[2][2];      // current flow of the internal level (ping-pong between levels)
+  Img blur, level, tmp, poly[3];
+  Img R[2][5], M[3][5];
+  Img* d_imgs = nullptr;   // device scratch for 15 Img structs (plane tables of the filter kernels)
+};
+int launch_farneback(const Img& im1, const Img& im2, const Img& u_io, const Img& v_io, const ofri_farneback_params* fp,
+                     const FbWorkspace& ws, const std::function<int(int, int, ResizeTaps*)>& resize_taps, cudaStream_t s,
+                     LaunchCounter& lc);
+
 const char* kernel_build_info();
 
 }  // namespace ofri

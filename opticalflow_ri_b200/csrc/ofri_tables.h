@@ -13,12 +13,13 @@ struct HostResizeTaps {
   std::vector<int> xmin, cnt;
   std::vector<double> w;   // [out][kmax]
 };
-// Pillow precompute_coeffs (libImaging/Resample.c) for the BICUBIC filter (support 2), antialiased
-inline HostResizeTaps build_resize_taps(int in_size, int out_size) {
+// Pillow precompute_coeffs (libImaging/Resample.c), antialiased: the BICUBIC filter (support 2; the driver's
+// down-sampling, GPOF:67-68) or, bilinear = true, the BILINEAR one (support 1; Farneback_PyCL.py:61-62, both directions)
+inline HostResizeTaps build_resize_taps(int in_size, int out_size, bool bilinear = false) {
   HostResizeTaps t;
   const double scale = (double)in_size / (double)out_size;
   const double fs = scale < 1.0 ? 1.0 : scale;
-  const double support = 2.0 * fs;
+  const double support = (bilinear ? 1.0 : 2.0) * fs;
   t.kmax = (int)std::ceil(support) * 2 + 1;
   t.xmin.assign(out_size, 0);
   t.cnt.assign(out_size, 0);
@@ -34,7 +35,8 @@ inline HostResizeTaps build_resize_taps(int in_size, int out_size) {
     double tot = 0.0;
     double* k = &t.w[(size_t)i * t.kmax];
     for (int x = 0; x < n; ++x) {
-      double v = bicubic_filter((x + lo - center + 0.5) * ss);
+      const double arg = (x + lo - center + 0.5) * ss;
+      double v = bilinear ? (std::fabs(arg) < 1.0 ? 1.0 - std::fabs(arg) : 0.0) : bicubic_filter(arg);
       k[x] = v;
       tot += v;
     }

@@ -91,6 +91,8 @@ def _native_algo(adapter, ncalls):
         return ofri.hs_algo(used, adapter.Niter)
     if kind == 'LS':
         return ofri.ls_algo(adapter.alpha)
+    if kind == 'FB':
+        return ofri.fb_algo()          # its parameters travel separately (Handle.set_farneback in _run)
     return None
 
 
@@ -100,7 +102,7 @@ def _consume_alphas(adapter, ncalls):
 
 
 def _is_native(adapter):
-    return getattr(adapter, '_ofri_native_kind', None) in ('HS', 'LS')
+    return getattr(adapter, '_ofri_native_kind', None) in ('HS', 'LS', 'FB')
 
 
 def _run(im1, im2, FILTER, main, pyramidalLevels, kLevels, FILTER_OPT, optional, warping, biLinear, interScaling,
@@ -117,6 +119,12 @@ def _run(im1, im2, FILTER, main, pyramidalLevels, kLevels, FILTER_OPT, optional,
     native_all = _is_native(main) and (optional is None or _is_native(optional))
     if not native_all and np.ndim(im1) != 2:
         raise ValueError("batched input needs this package's HS / Liu-Shen adapters")
+
+    fb = [a for a in (main, optional) if getattr(a, '_ofri_native_kind', None) == 'FB']
+    if len(fb) == 2 and fb[0] is not fb[1]:
+        raise NotImplementedError('two different Farneback adapters in one pair: the handle holds one parameter set')
+    if fb:
+        _native.handle().set_farneback(fb[0].native_params())
 
     def algo_of(adapter):
         return _native_algo(adapter, ncalls) if _is_native(adapter) else ofri.external_algo()

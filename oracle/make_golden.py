@@ -249,7 +249,7 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
-if __name__ == "__main__" and "--lswarp" not in sys.argv and "--big" not in sys.argv and "--extra" not in sys.argv:
+if __name__ == "__main__" and not ({"--lswarp", "--big", "--extra", "--farneback"} & set(sys.argv)):
     main()
 
 
@@ -358,3 +358,34 @@ if __name__ == "__main__" and "--big" in sys.argv:
     main_big(sys.argv[sys.argv.index("--big") + 1])
 if __name__ == "__main__" and "--extra" in sys.argv:
     main_extra()
+
+
+def main_farneback():
+    """`python oracle/make_golden.py --farneback`: the HOST-SIDE coefficient tables of the reference's Farneback adapter
+    (tests/golden/farneback_tables.npz).  The adapter's kernels need an OpenCL runtime this image does not have, so only
+    its pure-Python table generators are run (pyopencl is stubbed; the constructor, which opens an OpenCL context, is
+    bypassed with object.__new__): FarnebackPrepareGaussian, setPolynomialExpansionConsts, setGaussianBlurKernel."""
+    import_reference()
+    for n in ("pyopencl", "pyopencl.array"):
+        sys.modules[n] = types.ModuleType(n)
+    sys.modules["pyopencl"].array = sys.modules["pyopencl.array"]
+    import Farneback_PyCL as FB
+    g = {}
+    for tag, (n, sigma) in {"7_15": (7, 1.5), "5_11": (5, 1.1), "5_0": (5, 0.0), "7_12": (7, 1.2)}.items():
+        o = object.__new__(FB.Farneback_PyCL)
+        o.polyN, o.polySigma = n, sigma
+        o.setPolynomialExpansionConsts()
+        g["g_" + tag], g["xg_" + tag], g["xxg_" + tag] = o.matrixG[0], o.matrixXG[0], o.matrixXXG[0]
+        g["ig_" + tag], g["igd_" + tag] = o.matrixIG, o.matrixIGD
+    for tag, (size, sigma) in {"33": (33, 33 / 2 * 0.3), "13": (13, 13 / 2 * 0.3), "3_0": (3, 0.0), "3_05": (3, 0.5),
+                               "7_15": (7, 1.5), "17_35": (17, 3.5)}.items():
+        o = object.__new__(FB.Farneback_PyCL)
+        o.setGaussianBlurKernel(size, sigma)
+        g["blur_" + tag] = o.matrixGKernel[0]
+    out = os.path.join(OUT, "farneback_tables.npz")
+    np.savez_compressed(out, **g)
+    print(out, os.path.getsize(out))
+
+
+if __name__ == "__main__" and "--farneback" in sys.argv:
+    main_farneback()

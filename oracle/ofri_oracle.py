@@ -105,11 +105,18 @@ def _bicubic(x: float) -> float:
     return 0.0
 
 
-def resize_taps(in_size: int, out_size: int):
-    """Per-output tap window [xmin, xmin+cnt) and normalised f64 weights (Pillow precompute_coeffs)."""
+def _bilinear(x: float) -> float:
+    x = abs(x)
+    return 1.0 - x if x < 1.0 else 0.0
+
+
+def resize_taps(in_size: int, out_size: int, kind: str = "bicubic"):
+    """Per-output tap window [xmin, xmin+cnt) and normalised f64 weights (Pillow precompute_coeffs); kind = "bicubic"
+    (support 2; the driver's down-sampling, GPOF:67-68) or "bilinear" (support 1; Farneback_PyCL.py:61-62)."""
+    filt, fsup = (_bicubic, 2.0) if kind == "bicubic" else (_bilinear, 1.0)
     scale = in_size / out_size
     fs = max(scale, 1.0)
-    sup = 2.0 * fs
+    sup = fsup * fs
     kmax = int(math.ceil(sup)) * 2 + 1
     xmin = np.zeros(out_size, dtype=np.int32)
     cnt = np.zeros(out_size, dtype=np.int32)
@@ -126,7 +133,7 @@ def resize_taps(in_size: int, out_size: int):
         n = hi - lo
         tot = 0.0
         for x in range(n):
-            v = _bicubic((x + lo - c + 0.5) * ss)
+            v = filt((x + lo - c + 0.5) * ss)
             w[i, x] = v
             tot += v
         for x in range(n):
@@ -137,9 +144,9 @@ def resize_taps(in_size: int, out_size: int):
     return xmin, cnt, w
 
 
-def _resample_last_axis(a: np.ndarray, out_size: int) -> np.ndarray:
+def _resample_last_axis(a: np.ndarray, out_size: int, kind: str = "bicubic") -> np.ndarray:
     n = a.shape[-1]
-    xmin, cnt, w = resize_taps(n, out_size)
+    xmin, cnt, w = resize_taps(n, out_size, kind)
     out = np.empty(a.shape[:-1] + (out_size,), dtype=F32)
     a64 = a.astype(F64)
     for i in range(out_size):
@@ -159,6 +166,17 @@ def imresize_bicubic(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
     if out_h != H:
         a = np.ascontiguousarray(_resample_last_axis(np.ascontiguousarray(a.T), out_h).T)
     return np.ascontiguousarray(a)
+
+
+def imresize_filter(img: np.ndarray, out_w: int, out_h: int, kind: str) -> np.ndarray:
+    """Image.resize with another Pillow filter (same two-pass scheme); an unchanged size returns a copy, as Pillow does."""
+    a = np.ascontiguousarray(img, dtype=F32)
+    H, W = a.shape
+    if out_w != W:
+        a = _resample_last_axis(a, out_w, kind)
+    if out_h != H:
+        a = np.ascontiguousarray(_resample_last_axis(np.ascontiguousarray(a.T), out_h, kind).T)
+    return np.ascontiguousarray(a).copy()
 
 
 def level_size(n: int, scale: float) -> int:
