@@ -1,7 +1,8 @@
 """GPU parity tests of the Farneback adapter (csrc/ofri_farneback.cu behind src/Farneback_PyCL.py) against
 oracle/ofri_farneback_oracle.py on seeded inputs.  The oracle rounds every multiply and add separately in the order the
-reference's OpenCL kernels write them and so does the CUDA path (explicit __fmul_rn / __fadd_rn), hence the tolerance is
-far below the north-star 1e-4 px; the division in updateFlow is IEEE in both."""
+reference's OpenCL kernels write them and so does the CUDA path (explicit __fmul_rn / __fadd_rn), hence the stand-alone
+compute() is required to be BIT-IDENTICAL to the oracle (the division in updateFlow is IEEE in both); inside the generic
+driver the north-star tolerance of the driver's own stages applies (1e-4 px)."""
 import sys
 
 import numpy as np
@@ -13,7 +14,7 @@ from test_farneback_cpu import piv_pair
 
 pytestmark = pytest.mark.gpu
 
-TOL = 2e-5
+TOL = 0.0          # measured on B200: every case bit-identical to the oracle
 
 
 @pytest.fixture(scope="module")
@@ -114,18 +115,18 @@ def test_farneback_argument_errors(ofri, h, mods):
         FB.Farneback_PyCL(polyN=6).compute(z, z, z, z)
     p = FB.Farneback_PyCL().native_params()
     p.poly_n = 6
-    with pytest.raises(ofri.OfriError, match="polyN"):
+    with pytest.raises(ValueError, match="polyN"):
         h.farneback_compute(z, z, None, None, p)
     p = FB.Farneback_PyCL().native_params()
     p.size = 12
-    with pytest.raises(ofri.OfriError, match="ABI"):
+    with pytest.raises(ValueError, match="ABI"):
         h.farneback_compute(z, z, None, None, p)
     h2 = ofri.Handle(0)
     try:
         params = ofri.make_params(ofri.fb_algo(), None, filter_sigma=0.0, pyramid_levels=1, k_levels=1)
-        with pytest.raises(ofri.OfriError, match="ofri_set_farneback"):
+        with pytest.raises(ValueError, match="ofri_set_farneback"):
             h2.pyramidal_flow(z, z, params)
-        with pytest.raises(ofri.OfriError, match="row-band"):
+        with pytest.raises(NotImplementedError, match="row-band"):
             h2.band_plan(64, 64, params, 0, 2)
     finally:
         h2.close()
