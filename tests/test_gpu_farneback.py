@@ -126,6 +126,7 @@ def test_farneback_argument_errors(ofri, h, mods):
         params = ofri.make_params(ofri.fb_algo(), None, filter_sigma=0.0, pyramid_levels=1, k_levels=1)
         with pytest.raises(ValueError, match="ofri_set_farneback"):
             h2.pyramidal_flow(z, z, params)
+        h2.set_farneback(FB.Farneback_PyCL().native_params())
         with pytest.raises(NotImplementedError, match="row-band"):
             h2.band_plan(64, 64, params, 0, 2)
     finally:
