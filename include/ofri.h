@@ -58,7 +58,8 @@ typedef enum {
 /* OFRI_ALGO_EXTERNAL: a foreign adapter (any object with the reference's duck-typed compute(), GPOF:256-290) driven
  * through a callback -- only valid with ofri_pyramidal_flow_external */
 typedef enum { OFRI_ALGO_NONE = -1, OFRI_ALGO_HS = 0, OFRI_ALGO_LS = 1, OFRI_ALGO_EXTERNAL = 2,
-               OFRI_ALGO_FB = 3 /* Farneback: parameters from ofri_set_farneback */ } ofri_algo_kind;
+               OFRI_ALGO_FB = 3 /* Farneback: parameters from ofri_set_farneback */,
+               OFRI_ALGO_LK = 4 /* dense Lucas-Kanade: parameters from ofri_set_lk */ } ofri_algo_kind;
 
 /* One optical-flow algorithm adapter (the reference's plugin protocol: compute(im1, im2, U, V) -> (U, V, error),
  * GenericPyramidalOpticalFlow.py:256-290).
@@ -156,6 +157,24 @@ OFRI_API int ofri_farneback_compute(ofri_handle h, const float* im1, const float
 OFRI_API int ofri_resize_bilinear(ofri_handle h, const float* in, int batch, int H, int W, int out_h, int out_w, float* out);
 /* the parameters an adapter of kind OFRI_ALGO_FB uses inside ofri_pyramidal_flow* (copied into the handle) */
 OFRI_API int ofri_set_farneback(ofri_handle h, const ofri_farneback_params* fp);
+
+/* ---- dense Lucas-Kanade adapter (reference: src/denseLucasKanade_PyCL.py LK:line + the OpenCL kernel
+ * lkDense, src/pyrlkDenseLargeW.cl) ------------------------------------------------------------------------------------
+ * Constructor parameters (LK:34): n_iters (Niter), half_window (window = 2 half_window + 1 on both axes; the kernel's
+ * sample grid covers at most 32 x 32).  asym = {left, right, top, bottom}: the asymmetric-window switches the adapter
+ * derives from the mean vorticity of the incoming flow when enableVorticityEnhancement is set (LK:75-92); all zero
+ * otherwise.  The OpenCL original leaves three operations to the device (sampler filter precision, mad, division):
+ * this library uses the OpenCL-specification bilinear filter in full float32, fused multiply-add and IEEE division. */
+typedef struct {
+  uint32_t size;                     /* sizeof(ofri_lk_params) */
+  int32_t  n_iters, half_window;
+  int32_t  asym[4];
+} ofri_lk_params;
+/* compute(im1, im2, U, V) -> (U, V) of the adapter (LK:113-169); u0 / v0 NULL = zero initial flow */
+OFRI_API int ofri_lk_compute(ofri_handle h, const float* im1, const float* im2, const float* u0, const float* v0,
+                             int batch, int H, int W, const ofri_lk_params* lp, float* u_out, float* v_out);
+/* the parameters an adapter of kind OFRI_ALGO_LK uses inside ofri_pyramidal_flow* (copied into the handle) */
+OFRI_API int ofri_set_lk(ofri_handle h, const ofri_lk_params* lp);
 
 /* page-locked host memory for callers without a CUDA binding of their own (opticalflow_ri_b200/pipeline.py: the frame
  * ring of the file -> GPU -> file pipeline): buffers from here make the host-pointer call above fully asynchronous */

@@ -9,9 +9,9 @@ There is no CPU implementation here: importing is cheap, but any computation nee
 import os
 
 from ._lib import ALGO_EXTERNAL, ALGO_HS, ALGO_LS, ALGO_NONE, Algo, OfriError, Params, declared_symbols, lib  # noqa: F401
-from .api import (Handle, LocalGroup, band_plan_host, default_handle, external_algo, farneback_params, fb_algo, gaussian_taps, hs_algo, ls_algo, make_params, no_algo,  # noqa: F401
+from .api import (Handle, LocalGroup, band_plan_host, default_handle, external_algo, farneback_params, fb_algo, lk_algo, lk_params, gaussian_taps, hs_algo, ls_algo, make_params, no_algo,  # noqa: F401
                   nccl_unique_id)
 
 SRC_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "src")
-__all__ = ["Handle", "LocalGroup", "nccl_unique_id", "band_plan_host", "default_handle", "make_params", "hs_algo", "ls_algo", "no_algo", "external_algo", "fb_algo", "farneback_params", "gaussian_taps", "Params", "Algo",
+__all__ = ["Handle", "LocalGroup", "nccl_unique_id", "band_plan_host", "default_handle", "make_params", "hs_algo", "ls_algo", "no_algo", "external_algo", "fb_algo", "farneback_params", "lk_algo", "lk_params", "gaussian_taps", "Params", "Algo",
            "OfriError", "lib", "declared_symbols", "SRC_DIR"]

@@ -11,7 +11,7 @@ HEADER = os.path.join(HERE, "..", "include", "ofri.h")
 
 OFRI_MAX_GAUSS_TAPS = 129
 OFRI_MAX_ALPHAS = 64
-ALGO_NONE, ALGO_HS, ALGO_LS, ALGO_EXTERNAL, ALGO_FB = -1, 0, 1, 2, 3
+ALGO_NONE, ALGO_HS, ALGO_LS, ALGO_EXTERNAL, ALGO_FB, ALGO_LK = -1, 0, 1, 2, 3, 4
 OFRI_FB_MAX_HALF, OFRI_FB_MAX_LEVELS = 64, 12
 
 OK = 0
@@ -49,6 +49,10 @@ class FarnebackParams(C.Structure):
                 ("blur_kernel", (C.c_float * (OFRI_FB_MAX_HALF + 1)) * OFRI_FB_MAX_LEVELS)]
 
 
+class LkParams(C.Structure):
+    _fields_ = [("size", C.c_uint32), ("n_iters", C.c_int32), ("half_window", C.c_int32), ("asym", C.c_int32 * 4)]
+
+
 class Band(C.Structure):
     _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("own0", C.c_int32), ("own1", C.c_int32),
                 ("in0", C.c_int32), ("in1", C.c_int32), ("ghost", C.c_int32), ("exchange", C.c_int32)]
@@ -76,6 +80,8 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "ofri_farneback_compute": (C.c_int, [_H, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(FarnebackParams), _fp, _fp]),
     "ofri_set_farneback": (C.c_int, [_H, C.POINTER(FarnebackParams)]),
+    "ofri_lk_compute": (C.c_int, [_H, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(LkParams), _fp, _fp]),
+    "ofri_set_lk": (C.c_int, [_H, C.POINTER(LkParams)]),
     "ofri_resize_bilinear": (C.c_int, [_H, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "ofri_host_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),
     "ofri_host_free": (C.c_int, [_H, C.c_void_p]),

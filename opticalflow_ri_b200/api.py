@@ -5,7 +5,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import ALGO_EXTERNAL, ALGO_FB, ALGO_HS, ALGO_LS, ALGO_NONE, Algo, Band, FarnebackParams, OfriError, Params
+from ._lib import (ALGO_EXTERNAL, ALGO_FB, ALGO_HS, ALGO_LK, ALGO_LS, ALGO_NONE, Algo, Band, FarnebackParams, LkParams,
+                   OfriError, Params)
 
 _EXC = {_lib.ERR_INVALID: ValueError, _lib.ERR_ALPHAS: IndexError, _lib.ERR_FILTER_OPT: TypeError,
         _lib.ERR_TOO_SMALL: ValueError, _lib.ERR_UNSUPPORTED: NotImplementedError, _lib.ERR_OOM: MemoryError,
@@ -72,6 +73,23 @@ def fb_algo():
     a = Algo()
     a.kind = ALGO_FB
     return a
+
+
+def lk_algo():
+    """The dense Lucas-Kanade adapter as main / optional adapter of make_params (parameters: Handle.set_lk)."""
+    a = Algo()
+    a.kind = ALGO_LK
+    return a
+
+
+def lk_params(n_iters=5, half_window=13, asym=(0, 0, 0, 0)):
+    """ofri_lk_params: Niter, halfWindow (LK:34) and the asymmetric-window switches [left, right, top, bottom]."""
+    p = LkParams()
+    p.size = C.sizeof(LkParams)
+    p.n_iters, p.half_window = int(n_iters), int(half_window)
+    for i in range(4):
+        p.asym[i] = int(asym[i])
+    return p
 
 
 def farneback_params(window_size, n_iters, poly_n, use_gaussian, extra_levels, pyr_scale, g_half, xg_half, xxg_half, ig,
@@ -369,6 +387,24 @@ class Handle:
         out = np.empty((B, out_h, out_w), np.float32)
         self._check(self._L.ofri_resize_bilinear(self._h, _ptr(a), B, H, W, int(out_h), int(out_w), _ptr(out)))
         return out[0] if single else out
+
+    def set_lk(self, lk_params_):
+        self._check(self._L.ofri_set_lk(self._h, C.byref(lk_params_)))
+
+    def lk_compute(self, im1, im2, U0, V0, lk_params_):
+        """denseLucasKanade_PyCl.compute (LK:113-169): (U, V) initial flow in, refined flow out."""
+        a, single = _batched(im1)
+        b, _ = _batched(im2)
+        u0 = _batched(U0)[0] if U0 is not None else None
+        v0 = _batched(V0)[0] if V0 is not None else None
+        _same_shape(a, im2=b, U0=u0, V0=v0)
+        B, H, W = a.shape
+        U = np.empty((B, H, W), np.float32)
+        V = np.empty((B, H, W), np.float32)
+        self._check(self._L.ofri_lk_compute(self._h, _ptr(a), _ptr(b), _ptr(u0) if u0 is not None else None,
+                                            _ptr(v0) if v0 is not None else None, B, H, W, C.byref(lk_params_),
+                                            _ptr(U), _ptr(V)))
+        return (U[0], V[0]) if single else (U, V)
 
     def set_farneback(self, fb_params):
         self._check(self._L.ofri_set_farneback(self._h, C.byref(fb_params)))

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libofri.so")
-SOURCES = ["ofri_api.cu", "ofri_stages.cu", "ofri_hs.cu", "ofri_hs_tma.cu", "ofri_ls.cu", "ofri_ls_tma.cu", "ofri_comm.cu", "ofri_farneback.cu"]
+SOURCES = ["ofri_api.cu", "ofri_stages.cu", "ofri_hs.cu", "ofri_hs_tma.cu", "ofri_ls.cu", "ofri_ls_tma.cu", "ofri_comm.cu", "ofri_farneback.cu", "ofri_lk.cu"]
 HEADERS = ["ofri_internal.h", "ofri_pixel.cuh", "ofri_hs_common.cuh", "ofri_ls_common.cuh", "ofri_tma.cuh", "ofri_tables.h", "ofri_spline.cuh", os.path.join("..", "..", "include", "ofri.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--cudart", "static"]

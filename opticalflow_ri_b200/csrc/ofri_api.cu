@@ -60,6 +60,8 @@ struct ofri_ctx {
   std::map<std::pair<int, int>, DevResizeTaps> taps, taps_bilinear;
   ofri_farneback_params fb = {};      // parameters of adapters of kind OFRI_ALGO_FB (ofri_set_farneback)
   bool fb_set = false;
+  ofri_lk_params lk = {};             // parameters of adapters of kind OFRI_ALGO_LK (ofri_set_lk)
+  bool lk_set = false;
   std::map<int, DevSplineSys> splines;
   LaunchCounter lc;
   // options
@@ -289,6 +291,10 @@ int check_params(ofri_handle h, const ofri_params* p, int H, int W) {
       if (!h || !h->fb_set) return fail(h, OFRI_ERR_INVALID, "Farneback adapter without ofri_set_farneback");
       continue;
     }
+    if (g->kind == OFRI_ALGO_LK) {
+      if (!h || !h->lk_set) return fail(h, OFRI_ERR_INVALID, "Lucas-Kanade adapter without ofri_set_lk");
+      continue;
+    }
     const bool ext_ok = g->kind == OFRI_ALGO_EXTERNAL && h && h->ext_fn;
     if (a == 0 && g->kind != OFRI_ALGO_HS && g->kind != OFRI_ALGO_LS && !ext_ok)
       return fail(h, OFRI_ERR_INVALID, "main adapter must be HS or LS (external adapters: ofri_pyramidal_flow_external)");
@@ -500,6 +506,14 @@ int run_adapter(ofri_handle h, const ofri_algo& a, int call_index, Workspace& ws
                               [h](int in, int out, ResizeTaps* t) { return get_resize_taps(h, in, out, t, true); }, s, h->lc);
     if (rc) return h->ext_rc = fail(h, rc, "Farneback adapter failed (level %d x %d)", Hl, Wl), -1;
     if (d_err) cudaMemsetAsync(d_err, 0, sizeof(float), s);
+    return cur;
+  }
+  if (a.kind == OFRI_ALGO_LK) {                       // denseLucasKanade_PyCl.compute: (U, V) in -> (U, V) out, error `True`
+    Timed t(h, "lucas_kanade");
+    int rc = launch_lk(im1, im2, U[cur], V[cur], &h->lk, s, h->lc);
+    if (rc) return h->ext_rc = fail(h, rc, "Lucas-Kanade adapter failed (level %d x %d)", Hl, Wl), -1;
+    static const float one = 1.0f;                    // the reference returns `calcErr` (= True) as the error (LK:169)
+    if (d_err) cudaMemcpyAsync(d_err, &one, sizeof(float), cudaMemcpyHostToDevice, s);
     return cur;
   }
   if (a.kind == OFRI_ALGO_HS) {
@@ -1725,6 +1739,49 @@ int ofri_resize_bilinear(ofri_handle h, const float* in, int batch, int H, int W
   if ((rc = upload(h, i, in))) return rc;
   launch_resize(i, t, o, tx, ty, h->stream, h->lc);
   if ((rc = download(h, out, o))) return rc;
+  return finish(h);
+}
+
+static int check_lk(ofri_handle h, const ofri_lk_params* lp) {
+  if (!lp) return fail(h, OFRI_ERR_INVALID, "Lucas-Kanade parameters are NULL");
+  if (lp->size != sizeof(ofri_lk_params))
+    return fail(h, OFRI_ERR_INVALID, "ofri_lk_params.size = %u, library expects %zu (ABI mismatch)", lp->size,
+                sizeof(ofri_lk_params));
+  if (lp->n_iters < 0 || lp->half_window < 0 || lp->half_window > 4096)
+    return fail(h, OFRI_ERR_INVALID, "bad Lucas-Kanade iteration count / window");
+  for (int i = 0; i < 4; ++i)
+    if (lp->asym[i] != 0 && lp->asym[i] != 1) return fail(h, OFRI_ERR_INVALID, "asymmetric-window switches must be 0 or 1");
+  return OFRI_OK;
+}
+int ofri_set_lk(ofri_handle h, const ofri_lk_params* lp) {
+  OFRI_ENTER(h);
+  int rc = check_lk(h, lp);
+  if (rc) return rc;
+  h->lk = *lp;
+  h->lk_set = true;
+  return OFRI_OK;
+}
+int ofri_lk_compute(ofri_handle h, const float* im1, const float* im2, const float* u0, const float* v0, int batch, int H,
+                    int W, const ofri_lk_params* lp, float* u_out, float* v_out) {
+  OFRI_ENTER(h);
+  OFRI_DIMS(h, batch, H, W);
+  if (!im1 || !im2 || !u_out || !v_out) return fail(h, OFRI_ERR_INVALID, "NULL pointer");
+  int rc = check_lk(h, lp);
+  if (rc) return rc;
+  rc = arena_reserve(h, (sizeof(float) * (size_t)round_up(W, 4) * H * batch + 256) * 4 + 4096);
+  if (rc) return rc;
+  Bump b(h->arena, h->arena_cap, false);
+  Img i1 = b.plane(batch, H, W), i2 = b.plane(batch, H, W), U = b.plane(batch, H, W), V = b.plane(batch, H, W);
+  if ((rc = upload(h, i1, im1)) || (rc = upload(h, i2, im2))) return rc;
+  if (!u0 || !v0) {
+    cudaMemsetAsync(U.p, 0, sizeof(float) * U.stride * batch, h->stream);
+    cudaMemsetAsync(V.p, 0, sizeof(float) * V.stride * batch, h->stream);
+  } else if ((rc = upload(h, U, u0)) || (rc = upload(h, V, v0))) {
+    return rc;
+  }
+  rc = launch_lk(i1, i2, U, V, lp, h->stream, h->lc);
+  if (rc) return fail(h, rc, "Lucas-Kanade adapter failed");
+  if ((rc = download(h, u_out, U)) || (rc = download(h, v_out, V))) return rc;
   return finish(h);
 }
 

@@ -189,6 +189,9 @@ struct FbWorkspace {
 int launch_farneback(const Img& im1, const Img& im2, const Img& u_io, const Img& v_io, const ofri_farneback_params* fp,
                      const FbWorkspace& ws, const std::function<int(int, int, ResizeTaps*)>& resize_taps, cudaStream_t s,
                      LaunchCounter& lc);
+// dense Lucas-Kanade adapter (ofri_lk.cu): u_io / v_io initial flow in, refined flow out
+int launch_lk(const Img& im1, const Img& im2, const Img& u_io, const Img& v_io, const ofri_lk_params* lp, cudaStream_t s,
+              LaunchCounter& lc);
 
 const char* kernel_build_info();
 

@@ -1,0 +1,204 @@
+// ofri_lk.cu -- the dense Lucas-Kanade adapter of the reference as an sm_100a kernel.
+//
+// Replaces denseLucasKanade_PyCl.compute (denseLucasKanade_PyCL.py:113-169) and its OpenCL kernel lkDense
+// (pyrlkDenseLargeW.cl:305-669, the non-CPU branch).  Per pixel: the structure tensor of a (2 hw + 1)^2 window of
+// frame 1 (Scharr derivatives of the clamped image), then up to n_iters Gauss-Newton steps, each sampling frame 2
+// bilinearly at the displaced window, until both components of the step fall below 0.01 px.
+//
+// Work split (the reference's, which fixes the order of every floating-point sum): 64 work-items per pixel, work-item
+// (xid, yid) owns the 4 x 4 grid of window samples (xid + 8 tx, yid + 8 ty) with 0/1 weights that cut the 32 x 32
+// grid down to the window; per-work-item sums accumulate in that order by FMA, the 64 partial sums are added by the
+// fixed tree s[t] += s[t + 32], + 16, + 8, + 4, (s0 + s1) + (s2 + s3).  Here: one 64-thread CTA per pixel (persistent
+// grid, pixels taken round-robin), the tree's first level through shared memory (warp 1 -> warp 0), the rest by warp
+// shuffles in the same operand order.  The three device-defined operations of the OpenCL original are fixed as in
+// oracle/ofri_lk_oracle.c (see its header): image sampler = OpenCL-specification bilinear filter in full float32 with
+// clamp-to-edge addressing, `mad` = fused multiply-add, IEEE division -- so the result is bit-identical to that oracle.
+#include "ofri_internal.h"
+#include "ofri_pixel.cuh"
+
+namespace ofri {
+
+namespace {
+
+struct LkWeights { float wx[8][4], wy[8][4]; };
+
+__device__ __forceinline__ float lk_texel(const float* __restrict__ im, int H, int W, long pitch, int y, int x) {
+  x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
+  y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
+  return __ldg(im + (long)y * pitch + x);
+}
+
+// read_imagef(.., unnormalised coordinates | clamp to edge | linear filter, (x, y)) (pyrlkDenseLargeW.cl:236)
+__device__ __forceinline__ float lk_sample(const float* __restrict__ im, int H, int W, long pitch, float x, float y) {
+  const float fx = fsub(x, 0.5f), fy = fsub(y, 0.5f);
+  const float ix = floorf(fx), iy = floorf(fy);
+  const float a = fsub(fx, ix), b = fsub(fy, iy);
+  const int x0 = (int)ix, y0 = (int)iy;
+  const float t00 = lk_texel(im, H, W, pitch, y0, x0), t10 = lk_texel(im, H, W, pitch, y0, x0 + 1);
+  const float t01 = lk_texel(im, H, W, pitch, y0 + 1, x0), t11 = lk_texel(im, H, W, pitch, y0 + 1, x0 + 1);
+  const float oa = fsub(1.0f, a), ob = fsub(1.0f, b);
+  float r = fmul(fmul(oa, ob), t00);
+  r = fadd(r, fmul(fmul(a, ob), t10));
+  r = fadd(r, fmul(fmul(oa, b), t01));
+  r = fadd(r, fmul(fmul(a, b), t11));
+  return r;
+}
+
+// The reference's work-group sum of N values per work-item at once (pyrlkDenseLargeW.cl:113-155), 64 threads.
+// sm: N x 33 floats.  Every thread returns the totals.
+template <int N>
+__device__ __forceinline__ void lk_group_sum(float (&val)[N], float* sm, int tid) {
+  if (tid >= 32) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) sm[n * 33 + tid - 32] = val[n];
+  }
+  __syncthreads();
+  if (tid < 32) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      float s = fadd(val[n], sm[n * 33 + tid]);
+      s = fadd(s, __shfl_down_sync(0xffffffffu, s, 16));
+      s = fadd(s, __shfl_down_sync(0xffffffffu, s, 8));
+      s = fadd(s, __shfl_down_sync(0xffffffffu, s, 4));
+      const float s1 = __shfl_sync(0xffffffffu, s, 1), s2 = __shfl_sync(0xffffffffu, s, 2),
+                  s3 = __shfl_sync(0xffffffffu, s, 3);
+      if (tid == 0) sm[n * 33 + 32] = fadd(fadd(s, s1), fadd(s2, s3));
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int n = 0; n < N; ++n) val[n] = sm[n * 33 + 32];
+}
+
+__global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V, int iters, float hw, LkWeights wt) {
+  __shared__ float patch[34 * 34];
+  __shared__ float red[3 * 33];
+  const int tid = threadIdx.x, xid = tid & 7, yid = tid >> 3;
+  const int H = I.H, W = I.W;
+  const long npix = (long)H * W;
+  const float* __restrict__ pI = I.at(blockIdx.y);
+  const float* __restrict__ pJ = J.at(blockIdx.y);
+  float* pU = U.at(blockIdx.y);
+  float* pV = V.at(blockIdx.y);
+  float w[4][4];
+#pragma unroll
+  for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+    for (int tx = 0; tx < 4; ++tx) w[ty][tx] = fmul(wt.wy[yid][ty], wt.wx[xid][tx]);
+  const int ihw = (int)hw;
+  for (long gid = blockIdx.x; gid < npix; gid += gridDim.x) {
+    const int i = (int)(gid / W), j = (int)(gid - (long)i * W);
+    const int px = j - ihw, py = i - ihw;
+    __syncthreads();                                   // the previous pixel's patch is no longer read
+    for (int e = tid; e < 34 * 34; e += 64) {
+      const int yy = e / 34, xx = e - yy * 34;
+      patch[e] = lk_texel(pI, H, W, I.pitch, py + yy - 1, px + xx - 1);
+    }
+    __syncthreads();
+    float pv[4][4], dxs[4][4], dys[4][4];
+    float acc[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+      for (int tx = 0; tx < 4; ++tx) {
+        const float* c = patch + (ty * 8 + yid + 1) * 34 + (tx * 8 + xid + 1);
+        const float sx = fsub(fsub(fadd(c[-34 + 1], c[34 + 1]), c[-34 - 1]), c[34 - 1]);
+        const float sy = fsub(fsub(fadd(c[34 - 1], c[34 + 1]), c[-34 - 1]), c[-34 + 1]);
+        const float dx = fmul(__fmaf_rn(sx, 3.0f, fmul(fsub(c[1], c[-1]), 10.0f)), w[ty][tx]);
+        const float dy = fmul(__fmaf_rn(sy, 3.0f, fmul(fsub(c[34], c[-34]), 10.0f)), w[ty][tx]);
+        pv[ty][tx] = c[0];
+        dxs[ty][tx] = dx;
+        dys[ty][tx] = dy;
+        acc[0] = __fmaf_rn(dx, dx, acc[0]);
+        acc[1] = __fmaf_rn(dx, dy, acc[1]);
+        acc[2] = __fmaf_rn(dy, dy, acc[2]);
+      }
+    lk_group_sum<3>(acc, red, tid);
+    float A11 = acc[0], A12 = acc[1], A22 = acc[2];
+    const float D = __fmaf_rn(A11, A22, -fmul(A12, A12));
+    if (D < 1.192092896e-07f) continue;                // CTA-uniform: the pixel's flow stays as it came in
+    A11 = __fdiv_rn(A11, D);
+    A12 = __fdiv_rn(A12, D);
+    A22 = __fdiv_rn(A22, D);
+    float ppx = fsub(fadd((float)j, pU[(long)i * U.pitch + j]), hw);
+    float ppy = fsub(fadd((float)i, pV[(long)i * V.pitch + j]), hw);
+    float lx[4], ly[4];
+    lx[0] = fadd(ppx, fadd((float)xid, 0.5f));
+    ly[0] = fadd(ppy, fadd((float)yid, 0.5f));
+#pragma unroll
+    for (int t = 1; t < 4; ++t) {
+      lx[t] = fadd(lx[t - 1], 8.0f);
+      ly[t] = fadd(ly[t - 1], 8.0f);
+    }
+    for (int k = 0; k < iters; ++k) {
+      if (ppx < -hw || ppx >= (float)W || ppy < -hw || ppy >= (float)H) break;
+      float b[2] = {0.0f, 0.0f};
+#pragma unroll
+      for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < 4; ++tx) {
+          const float diff = fmul(fsub(lk_sample(pJ, H, W, J.pitch, lx[tx], ly[ty]), pv[ty][tx]), w[ty][tx]);
+          b[0] = __fmaf_rn(diff, dxs[ty][tx], b[0]);
+          b[1] = __fmaf_rn(diff, dys[ty][tx], b[1]);
+        }
+      lk_group_sum<2>(b, red, tid);
+      const float ddx = fmul(__fmaf_rn(A12, b[1], -fmul(A22, b[0])), 32.0f);
+      const float ddy = fmul(__fmaf_rn(A12, b[0], -fmul(A11, b[1])), 32.0f);
+      ppx = fadd(ppx, ddx);
+      ppy = fadd(ppy, ddy);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        lx[t] = fadd(lx[t], ddx);
+        ly[t] = fadd(ly[t], ddy);
+      }
+      if (fabsf(ddx) < 0.01f && fabsf(ddy) < 0.01f) break;
+    }
+    if (tid == 0) {
+      pU[(long)i * U.pitch + j] = fsub(fadd(ppx, hw), (float)j);
+      pV[(long)i * V.pitch + j] = fsub(fadd(ppy, hw), (float)i);
+    }
+  }
+}
+
+// per-axis 0/1 weights of the four grid columns (rows) of work-item `id` (pyrlkDenseLargeW.cl:339-372): `win` = window
+// extent, lo / hi = the asymmetric-window switches of the axis (left / right, top / bottom)
+void axis_weights(int id, int win, int lo, int hi, float* w) {
+  w[0] = 1.0f;
+  if (win >= 16) {
+    w[1] = id == 0 ? (float)(1 - lo) : 1.0f;
+    w[2] = (16 + id < win - hi) ? 1.0f : 0.0f;
+    w[3] = (24 + id < win - hi) ? 1.0f : 0.0f;
+  } else {
+    w[1] = id == 0 ? (float)(1 - lo) : ((8 + id < win - hi) ? 1.0f : 0.0f);
+    w[2] = 0.0f;
+    w[3] = 0.0f;
+  }
+}
+
+}  // namespace
+
+// u_io / v_io: initial flow in, refined flow out (every CTA touches only its own pixel's entry)
+int launch_lk(const Img& im1, const Img& im2, const Img& u_io, const Img& v_io, const ofri_lk_params* lp, cudaStream_t s,
+              LaunchCounter& lc) {
+  const int win = 2 * lp->half_window + 1;
+  LkWeights wt;
+  for (int id = 0; id < 8; ++id) {
+    axis_weights(id, win, lp->asym[0], lp->asym[1], wt.wx[id]);
+    axis_weights(id, win, lp->asym[2], lp->asym[3], wt.wy[id]);
+  }
+  const long npix = (long)im1.H * im1.W;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const long want = (long)num_sms * 24;                 // 24 resident 64-thread CTAs per SM (shared memory: 5 KB each)
+  dim3 grid((unsigned)(npix < want ? npix : want), (unsigned)im1.batch);
+  lk_dense_kernel<<<grid, 64, 0, s>>>(im1, im2, u_io, v_io, lp->n_iters, (float)((win - 1) >> 1), wt);
+  ++lc.n;
+  return cudaGetLastError() == cudaSuccess ? OFRI_OK : OFRI_ERR_CUDA;
+}
+
+}  // namespace ofri

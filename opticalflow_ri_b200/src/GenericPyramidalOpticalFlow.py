@@ -93,6 +93,8 @@ def _native_algo(adapter, ncalls):
         return ofri.ls_algo(adapter.alpha)
     if kind == 'FB':
         return ofri.fb_algo()          # its parameters travel separately (Handle.set_farneback in _run)
+    if kind == 'LK':
+        return ofri.lk_algo()          # likewise (Handle.set_lk)
     return None
 
 
@@ -102,7 +104,7 @@ def _consume_alphas(adapter, ncalls):
 
 
 def _is_native(adapter):
-    return getattr(adapter, '_ofri_native_kind', None) in ('HS', 'LS', 'FB')
+    return getattr(adapter, '_ofri_native_kind', None) in ('HS', 'LS', 'FB', 'LK')
 
 
 def _run(im1, im2, FILTER, main, pyramidalLevels, kLevels, FILTER_OPT, optional, warping, biLinear, interScaling,
@@ -125,6 +127,12 @@ def _run(im1, im2, FILTER, main, pyramidalLevels, kLevels, FILTER_OPT, optional,
         raise NotImplementedError('two different Farneback adapters in one pair: the handle holds one parameter set')
     if fb:
         _native.handle().set_farneback(fb[0].native_params())
+
+    lk = [a for a in (main, optional) if getattr(a, '_ofri_native_kind', None) == 'LK']
+    if len(lk) == 2 and lk[0] is not lk[1]:
+        raise NotImplementedError('two different Lucas-Kanade adapters in one pair: the handle holds one parameter set')
+    if lk:
+        _native.handle().set_lk(lk[0].native_params())
 
     def algo_of(adapter):
         return _native_algo(adapter, ncalls) if _is_native(adapter) else ofri.external_algo()

@@ -15,6 +15,18 @@ def handle():
     return ofri.default_handle(int(os.environ.get("OFRI_DEVICE", "0")))
 
 
+_aux = None
+
+
+def aux_handle():
+    """A second handle on the same device for adapters whose compute() can be called back from inside a native call on
+    the default handle (a handle is not re-entrant)."""
+    global _aux
+    if _aux is None:
+        _aux = ofri.Handle(int(os.environ.get("OFRI_DEVICE", "0")))
+    return _aux
+
+
 def log(*a):
     if VERBOSE:
         print(*a)
