@@ -60,7 +60,7 @@ def test_compute_bit_identical_to_oracle(ofri, h, case):
     d = max(np.abs(U - Uo).max(), np.abs(V - Vo).max())
     print("lucas-kanade case %d: max|d| %.3g, bit-identical px %.4f" % (case, d, np.mean((U == Uo) & (V == Vo))))
     assert np.array_equal(U, Uo) and np.array_equal(V, Vo)
-    assert np.array_equal(U[:5, :10], U0[:5, :10])
+    assert np.array_equal(U[:3, :10], U0[:3, :10])      # windows (incl. the derivative's reach) entirely inside the flat corner
 
 
 def test_compute_batched_equals_single(ofri, h, mods):
