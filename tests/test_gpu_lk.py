@@ -136,3 +136,38 @@ def test_lk_argument_errors(ofri, h):
             h2.pyramidal_flow(z, z, params)
     finally:
         h2.close()
+
+
+EXAMPLES = {   # the reference's example scripts (examples/*.py) beyond the three BASELINE ones: (main, FILTER, levels, LS h, kwargs)
+    "Farneback_Fs0_0": ("fb", 0, 1, None, {}),
+    "Farneback_Fs0_0_PyrLvls2": ("fb", 0, 2, None, {}),
+    "LiuSE_Farneback_Fs0_0_PyrLvls2": ("fb", 0, 2, 10, {}),
+    "denseLK_Fs2_0": ("lk", 2, 1, None, dict(warping=False)),
+    "LiuSE_denseLK_Fs2_0_PyrLvls2": ("lk", 2, 2, 10, dict(warping=False)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EXAMPLES))
+def test_reference_example_configurations(ofri, mods, bundled_pair, name):
+    """The Farneback / dense-LK example scripts of the reference, with their parameters, on a crop of the bundled
+    Poiseuille pair: drop-in modules (GPU) against the oracle driver with the oracle adapters."""
+    import ofri_farneback_oracle as FBO
+    LK, G, LS = mods
+    sys.path.insert(0, ofri.SRC_DIR)
+    try:
+        import Farneback_PyCL as FB
+    finally:
+        sys.path.remove(ofri.SRC_DIR)
+    main, FILTER, levels, ls_h, kw = EXAMPLES[name]
+    a = np.ascontiguousarray(bundled_pair[0][180:340, 160:336])
+    b = np.ascontiguousarray(bundled_pair[1][180:340, 160:336])
+    if main == "fb":
+        ours, theirs = FB.Farneback_PyCL(platformID=0), FBO.FBParams()
+    else:
+        ours, theirs = LK.denseLucasKanade_PyCl(Niter=5, halfWindow=13, platformID=0), LKO.LKParams(5, 13)
+    Uo, Vo = O.pyramidal_flow(a, b, FILTER, theirs, levels, 1, 0.48, O.LSParams(ls_h) if ls_h else None, **kw)[:2]
+    U, V = G.genericPyramidalOpticalFlow(a, b, FILTER, ours, levels, 1, 0.48,
+                                         LS.LiuShenOpticalFlowAlgoAdapter(ls_h) if ls_h else None, **kw)
+    d = max(np.abs(U - Uo).max(), np.abs(V - Vo).max())
+    print("%s: max|d| %.3g px, flow range U [%.3f, %.3f]" % (name, d, U.min(), U.max()))
+    assert d <= 1e-4

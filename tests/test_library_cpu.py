@@ -34,14 +34,17 @@ def test_exports_every_declared_symbol(ofri):
 
 def test_struct_layout_matches_c(ofri, tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ofri.h"\nint main(){printf("%zu %zu %zu %zu %zu",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ofri.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu",'
                    'sizeof(ofri_params),sizeof(ofri_algo),offsetof(ofri_params,taps_opt),offsetof(ofri_params,main_algo),'
-                   'offsetof(ofri_algo,ls_tol));return 0;}')
+                   'offsetof(ofri_algo,ls_tol),sizeof(ofri_farneback_params),offsetof(ofri_farneback_params,win_kernel),'
+                   'offsetof(ofri_farneback_params,blur_kernel),sizeof(ofri_lk_params),offsetof(ofri_lk_params,asym));'
+                   'return 0;}')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
-    P, A = ofri.Params, ofri.Algo
-    assert got == [C.sizeof(P), C.sizeof(A), P.taps_opt.offset, P.main_algo.offset, A.ls_tol.offset]
+    P, A, F, K = ofri.Params, ofri.Algo, ofri._lib.FarnebackParams, ofri._lib.LkParams
+    assert got == [C.sizeof(P), C.sizeof(A), P.taps_opt.offset, P.main_algo.offset, A.ls_tol.offset, C.sizeof(F),
+                   F.win_kernel.offset, F.blur_kernel.offset, C.sizeof(K), K.asym.offset]
 
 
 def test_host_helpers_without_gpu(ofri):
