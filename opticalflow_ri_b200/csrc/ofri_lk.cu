@@ -9,8 +9,10 @@
 // (xid, yid) owns the 4 x 4 grid of window samples (xid + 8 tx, yid + 8 ty) with 0/1 weights that cut the 32 x 32
 // grid down to the window; per-work-item sums accumulate in that order by FMA, the 64 partial sums are added by the
 // fixed tree s[t] += s[t + 32], + 16, + 8, + 4, (s0 + s1) + (s2 + s3).  Here: one 64-thread CTA per pixel (persistent
-// grid, pixels taken round-robin), the tree's first level through shared memory (warp 1 -> warp 0), the rest by warp
-// shuffles in the same operand order.  The three device-defined operations of the OpenCL original are fixed as in
+// grid, runs of 8 neighbouring pixels per CTA), the tree's first level through shared memory (warp 1 -> warp 0), the
+// rest by warp shuffles in the same operand order.  Frame 1's 34 x 34 patch and, per Gauss-Newton step, the 36 x 36
+// window of frame 2 that the step's 1024 bilinear samples fall into are staged in shared memory with the clamp-to-edge
+// rule applied while loading (row-coalesced reads instead of four scattered cache lines per warp and tap).  The three device-defined operations of the OpenCL original are fixed as in
 // oracle/ofri_lk_oracle.c (see its header): image sampler = OpenCL-specification bilinear filter in full float32 with
 // clamp-to-edge addressing, `mad` = fused multiply-add, IEEE division -- so the result is bit-identical to that oracle.
 #include "ofri_internal.h"
@@ -22,26 +24,45 @@ namespace {
 
 struct LkWeights { float wx[8][4], wy[8][4]; };
 
-__device__ __forceinline__ float lk_texel(const float* __restrict__ im, int H, int W, long pitch, int y, int x) {
-  x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
-  y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
-  return __ldg(im + (long)y * pitch + x);
-}
-
-// read_imagef(.., unnormalised coordinates | clamp to edge | linear filter, (x, y)) (pyrlkDenseLargeW.cl:236)
-__device__ __forceinline__ float lk_sample(const float* __restrict__ im, int H, int W, long pitch, float x, float y) {
+// read_imagef(.., unnormalised coordinates | clamp to edge | linear filter, (x, y)) (pyrlkDenseLargeW.cl:236) out of the
+// CTA's staged window of frame 2: win[yy][xx] holds J at (by + yy, bx + xx) with the clamp-to-edge rule already applied.
+// Weights and texel indices are computed per sample exactly as for a direct image read (the float32 roundings of the
+// sample position differ from sample to sample); the index clamp into the window is a memory-safety guard only (the
+// window is one texel wider on every side than the positions can reach).
+constexpr int LK_WIN = 36, LK_WPITCH = 40;            // pitch 40: the 8 x 4 sample lattice of a warp hits 32 different banks
+__device__ __forceinline__ float lk_sample(const float* __restrict__ win, int bx, int by, float x, float y) {
   const float fx = fsub(x, 0.5f), fy = fsub(y, 0.5f);
   const float ix = floorf(fx), iy = floorf(fy);
   const float a = fsub(fx, ix), b = fsub(fy, iy);
-  const int x0 = (int)ix, y0 = (int)iy;
-  const float t00 = lk_texel(im, H, W, pitch, y0, x0), t10 = lk_texel(im, H, W, pitch, y0, x0 + 1);
-  const float t01 = lk_texel(im, H, W, pitch, y0 + 1, x0), t11 = lk_texel(im, H, W, pitch, y0 + 1, x0 + 1);
+  int x0 = (int)ix - bx, y0 = (int)iy - by;
+  x0 = min(max(x0, 0), LK_WIN - 2);
+  y0 = min(max(y0, 0), LK_WIN - 2);
+  const float* c = win + y0 * LK_WPITCH + x0;
+  const float t00 = c[0], t10 = c[1], t01 = c[LK_WPITCH], t11 = c[LK_WPITCH + 1];
   const float oa = fsub(1.0f, a), ob = fsub(1.0f, b);
   float r = fmul(fmul(oa, ob), t00);
   r = fadd(r, fmul(fmul(a, ob), t10));
   r = fadd(r, fmul(fmul(oa, b), t01));
   r = fadd(r, fmul(fmul(a, b), t11));
   return r;
+}
+
+// Stage an N x N window of `im` whose top-left texel is (y0, x0) into shared memory (row pitch `pitch_s`), clamp-to-edge
+// applied while loading.  The two warps take alternate rows; a lane loads column `lane` and, for the first N - 32 lanes,
+// column 32 + lane: one clamped column offset per lane for the whole window, one clamped row pointer per row.
+template <int N>
+__device__ __forceinline__ void lk_stage_window(const float* __restrict__ im, int H, int W, long pitch, int y0, int x0,
+                                                float* __restrict__ dst, int pitch_s, int tid) {
+  static_assert(N > 32 && N <= 64, "two column loads per lane");
+  const int lane = tid & 31, half = tid >> 5;
+  const int c0 = min(max(x0 + lane, 0), W - 1), c1 = min(max(x0 + 32 + lane, 0), W - 1);
+  const bool second = lane < N - 32;
+#pragma unroll 2
+  for (int yy = half; yy < N; yy += 2) {
+    const float* row = im + (long)min(max(y0 + yy, 0), H - 1) * pitch;
+    dst[yy * pitch_s + lane] = __ldg(row + c0);
+    if (second) dst[yy * pitch_s + 32 + lane] = __ldg(row + c1);
+  }
 }
 
 // The reference's work-group sum of N values per work-item at once (pyrlkDenseLargeW.cl:113-155), 64 threads.
@@ -72,6 +93,7 @@ __device__ __forceinline__ void lk_group_sum(float (&val)[N], float* sm, int tid
 
 __global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V, int iters, float hw, LkWeights wt) {
   __shared__ float patch[34 * 34];
+  __shared__ float jwin[LK_WIN * LK_WPITCH];
   __shared__ float red[3 * 33];
   const int tid = threadIdx.x, xid = tid & 7, yid = tid >> 3;
   const int H = I.H, W = I.W;
@@ -86,14 +108,13 @@ __global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V
 #pragma unroll
     for (int tx = 0; tx < 4; ++tx) w[ty][tx] = fmul(wt.wy[yid][ty], wt.wx[xid][tx]);
   const int ihw = (int)hw;
-  for (long gid = blockIdx.x; gid < npix; gid += gridDim.x) {
+  // pixels in runs of 8 consecutive indices per CTA (round-robin over the runs): the windows of a run overlap almost
+  // entirely, so its image reads stay in L1
+  for (long gid = (long)blockIdx.x * 8; gid < npix; gid = ((gid & 7) == 7) ? gid - 7 + (long)gridDim.x * 8 : gid + 1) {
     const int i = (int)(gid / W), j = (int)(gid - (long)i * W);
     const int px = j - ihw, py = i - ihw;
     __syncthreads();                                   // the previous pixel's patch is no longer read
-    for (int e = tid; e < 34 * 34; e += 64) {
-      const int yy = e / 34, xx = e - yy * 34;
-      patch[e] = lk_texel(pI, H, W, I.pitch, py + yy - 1, px + xx - 1);
-    }
+    lk_stage_window<34>(pI, H, W, I.pitch, py - 1, px - 1, patch, 34, tid);
     __syncthreads();
     float pv[4][4], dxs[4][4], dys[4][4];
     float acc[3] = {0.0f, 0.0f, 0.0f};
@@ -132,12 +153,17 @@ __global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V
     }
     for (int k = 0; k < iters; ++k) {
       if (ppx < -hw || ppx >= (float)W || ppy < -hw || ppy >= (float)H) break;
+      // stage the window of frame 2 this step samples (all 64 x 16 positions lie in [ppx, ppx + 32] x [ppy, ppy + 32];
+      // the previous step's reads ended before the barriers of its work-group sum)
+      const int bx = (int)floorf(ppx) - 1, by = (int)floorf(ppy) - 1;
+      lk_stage_window<LK_WIN>(pJ, H, W, J.pitch, by, bx, jwin, LK_WPITCH, tid);
+      __syncthreads();
       float b[2] = {0.0f, 0.0f};
 #pragma unroll
       for (int ty = 0; ty < 4; ++ty)
 #pragma unroll
         for (int tx = 0; tx < 4; ++tx) {
-          const float diff = fmul(fsub(lk_sample(pJ, H, W, J.pitch, lx[tx], ly[ty]), pv[ty][tx]), w[ty][tx]);
+          const float diff = fmul(fsub(lk_sample(jwin, bx, by, lx[tx], ly[ty]), pv[ty][tx]), w[ty][tx]);
           b[0] = __fmaf_rn(diff, dxs[ty][tx], b[0]);
           b[1] = __fmaf_rn(diff, dys[ty][tx], b[1]);
         }
@@ -194,8 +220,10 @@ int launch_lk(const Img& im1, const Img& im2, const Img& u_io, const Img& v_io, 
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  const long want = (long)num_sms * 24;                 // 24 resident 64-thread CTAs per SM (shared memory: 5 KB each)
-  dim3 grid((unsigned)(npix < want ? npix : want), (unsigned)im1.batch);
+  const long want = (long)num_sms * 8;                  // 8 resident 64-thread CTAs per SM (128 registers per thread; 12 CTAs at 80
+                                                        // registers measured 4 % slower: the kernel is issue-bound)
+  const long runs = (npix + 7) / 8;
+  dim3 grid((unsigned)(runs < want ? runs : want), (unsigned)im1.batch);
   lk_dense_kernel<<<grid, 64, 0, s>>>(im1, im2, u_io, v_io, lp->n_iters, (float)((win - 1) >> 1), wt);
   ++lc.n;
   return cudaGetLastError() == cudaSuccess ? OFRI_OK : OFRI_ERR_CUDA;
