@@ -26,24 +26,28 @@ struct LkWeights { float wx[8][4], wy[8][4]; };
 
 // read_imagef(.., unnormalised coordinates | clamp to edge | linear filter, (x, y)) (pyrlkDenseLargeW.cl:236) out of the
 // CTA's staged window of frame 2: win[yy][xx] holds J at (by + yy, bx + xx) with the clamp-to-edge rule already applied.
-// Weights and texel indices are computed per sample exactly as for a direct image read (the float32 roundings of the
-// sample position differ from sample to sample); the index clamp into the window is a memory-safety guard only (the
-// window is one texel wider on every side than the positions can reach).
+// The filter separates per axis: texel index and weight pair depend on x (resp. y) alone, so a work-item prepares them
+// once for each of its 4 sample columns and 4 sample rows (LkAxis) and combines them per sample -- the same float32
+// operations on the same operands as a direct image read, hence the same bits.  The index clamp into the window is a
+// memory-safety guard only (the window is one texel wider on every side than the positions can reach).
 constexpr int LK_WIN = 36, LK_WPITCH = 40;            // pitch 40: the 8 x 4 sample lattice of a warp hits 32 different banks
-__device__ __forceinline__ float lk_sample(const float* __restrict__ win, int bx, int by, float x, float y) {
-  const float fx = fsub(x, 0.5f), fy = fsub(y, 0.5f);
-  const float ix = floorf(fx), iy = floorf(fy);
-  const float a = fsub(fx, ix), b = fsub(fy, iy);
-  int x0 = (int)ix - bx, y0 = (int)iy - by;
-  x0 = min(max(x0, 0), LK_WIN - 2);
-  y0 = min(max(y0, 0), LK_WIN - 2);
-  const float* c = win + y0 * LK_WPITCH + x0;
+struct LkAxis { float a, oa; int off; };             // weight of the upper texel, of the lower texel, window offset
+__device__ __forceinline__ LkAxis lk_axis(float x, int base, int scale) {
+  const float fx = fsub(x, 0.5f);
+  const float ix = floorf(fx);
+  LkAxis r;
+  r.a = fsub(fx, ix);
+  r.oa = fsub(1.0f, r.a);
+  r.off = min(max((int)ix - base, 0), LK_WIN - 2) * scale;
+  return r;
+}
+__device__ __forceinline__ float lk_sample(const float* __restrict__ win, const LkAxis& X, const LkAxis& Y) {
+  const float* c = win + Y.off + X.off;
   const float t00 = c[0], t10 = c[1], t01 = c[LK_WPITCH], t11 = c[LK_WPITCH + 1];
-  const float oa = fsub(1.0f, a), ob = fsub(1.0f, b);
-  float r = fmul(fmul(oa, ob), t00);
-  r = fadd(r, fmul(fmul(a, ob), t10));
-  r = fadd(r, fmul(fmul(oa, b), t01));
-  r = fadd(r, fmul(fmul(a, b), t11));
+  float r = fmul(fmul(X.oa, Y.oa), t00);
+  r = fadd(r, fmul(fmul(X.a, Y.oa), t10));
+  r = fadd(r, fmul(fmul(X.oa, Y.a), t01));
+  r = fadd(r, fmul(fmul(X.a, Y.a), t11));
   return r;
 }
 
@@ -92,7 +96,7 @@ __device__ __forceinline__ void lk_group_sum(float (&val)[N], float* sm, int tid
 }
 
 __global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V, int iters, float hw, LkWeights wt) {
-  __shared__ float patch[34 * 34];
+  __shared__ float patch[34 * LK_WPITCH];
   __shared__ float jwin[LK_WIN * LK_WPITCH];
   __shared__ float red[3 * 33];
   const int tid = threadIdx.x, xid = tid & 7, yid = tid >> 3;
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V
     const int i = (int)(gid / W), j = (int)(gid - (long)i * W);
     const int px = j - ihw, py = i - ihw;
     __syncthreads();                                   // the previous pixel's patch is no longer read
-    lk_stage_window<34>(pI, H, W, I.pitch, py - 1, px - 1, patch, 34, tid);
+    lk_stage_window<34>(pI, H, W, I.pitch, py - 1, px - 1, patch, LK_WPITCH, tid);
     __syncthreads();
     float pv[4][4], dxs[4][4], dys[4][4];
     float acc[3] = {0.0f, 0.0f, 0.0f};
@@ -122,11 +126,12 @@ __global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V
     for (int ty = 0; ty < 4; ++ty)
 #pragma unroll
       for (int tx = 0; tx < 4; ++tx) {
-        const float* c = patch + (ty * 8 + yid + 1) * 34 + (tx * 8 + xid + 1);
-        const float sx = fsub(fsub(fadd(c[-34 + 1], c[34 + 1]), c[-34 - 1]), c[34 - 1]);
-        const float sy = fsub(fsub(fadd(c[34 - 1], c[34 + 1]), c[-34 - 1]), c[-34 + 1]);
+        constexpr int P = LK_WPITCH;
+        const float* c = patch + (ty * 8 + yid + 1) * P + (tx * 8 + xid + 1);
+        const float sx = fsub(fsub(fadd(c[-P + 1], c[P + 1]), c[-P - 1]), c[P - 1]);
+        const float sy = fsub(fsub(fadd(c[P - 1], c[P + 1]), c[-P - 1]), c[-P + 1]);
         const float dx = fmul(__fmaf_rn(sx, 3.0f, fmul(fsub(c[1], c[-1]), 10.0f)), w[ty][tx]);
-        const float dy = fmul(__fmaf_rn(sy, 3.0f, fmul(fsub(c[34], c[-34]), 10.0f)), w[ty][tx]);
+        const float dy = fmul(__fmaf_rn(sy, 3.0f, fmul(fsub(c[P], c[-P]), 10.0f)), w[ty][tx]);
         pv[ty][tx] = c[0];
         dxs[ty][tx] = dx;
         dys[ty][tx] = dy;
@@ -159,11 +164,17 @@ __global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V
       lk_stage_window<LK_WIN>(pJ, H, W, J.pitch, by, bx, jwin, LK_WPITCH, tid);
       __syncthreads();
       float b[2] = {0.0f, 0.0f};
+      LkAxis ax[4], ay[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        ax[t] = lk_axis(lx[t], bx, 1);
+        ay[t] = lk_axis(ly[t], by, LK_WPITCH);
+      }
 #pragma unroll
       for (int ty = 0; ty < 4; ++ty)
 #pragma unroll
         for (int tx = 0; tx < 4; ++tx) {
-          const float diff = fmul(fsub(lk_sample(jwin, bx, by, lx[tx], ly[ty]), pv[ty][tx]), w[ty][tx]);
+          const float diff = fmul(fsub(lk_sample(jwin, ax[tx], ay[ty]), pv[ty][tx]), w[ty][tx]);
           b[0] = __fmaf_rn(diff, dxs[ty][tx], b[0]);
           b[1] = __fmaf_rn(diff, dys[ty][tx], b[1]);
         }

@@ -17,7 +17,9 @@ import opticalflow_ri_b200 as ofri  # noqa: E402
 
 h = ofri.Handle(0)
 h.set_option("timing", 1)
-for n, batch in ((512, 16), (1024, 8)):
+REPS = int(os.environ.get("ADAPTER_REPS", "4"))
+SIZES = [(int(a), int(b)) for a, b in (x.split("x") for x in os.environ.get("ADAPTER_SIZES", "512x16,1024x8").split(","))]
+for n, batch in SIZES:
     pairs = [synthetic_piv_pair(n, n, s) for s in range(batch)]
     A = np.stack([p[0] for p in pairs])
     B = np.stack([p[1] for p in pairs])
@@ -26,7 +28,7 @@ for n, batch in ((512, 16), (1024, 8)):
     for name, algo, sigma in (("farneback", ofri.fb_algo(), 0.0), ("lucas_kanade", ofri.lk_algo(), 2.0)):
         p = ofri.make_params(algo, None, filter_sigma=sigma, pyramid_levels=1, k_levels=1, warping=False, final_scaling=False)
         best = None
-        for rep in range(4):
+        for rep in range(REPS):
             h.pyramidal_flow(A, B, p)
             ms = h.stage_timings().get(name, 0.0)
             best = ms if best is None else min(best, ms)
