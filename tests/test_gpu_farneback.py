@@ -131,3 +131,20 @@ def test_farneback_argument_errors(ofri, h, mods):
             h2.band_plan(64, 64, params, 0, 2)
     finally:
         h2.close()
+
+
+@pytest.mark.parametrize("shape", [(37, 45), (16, 20), (65, 40), (131, 34)])
+def test_small_and_odd_shapes(h, mods, shape):
+    """Frames smaller than the window / the polynomial support (the kernels' reflect rule wraps with a modulo guard), widths
+    that are not a multiple of 4, internal pyramid levels that stop at the 32-pixel limit (FB:483-489), batch of 2."""
+    FB = mods[0]
+    rng = np.random.default_rng(shape[0] * 100 + shape[1])
+    H, W = shape
+    A = rng.uniform(0, 255, (2, H, W)).astype(np.float32)
+    B = np.roll(A, 1, 2) + rng.uniform(-2, 2, (2, H, W)).astype(np.float32)
+    kw = dict(windowSize=13, Niters=2, polyN=5, polySigma=1.1, pyramidalLevels=3)
+    U, V = h.farneback_compute(A, B, None, None, FB.Farneback_PyCL(**kw).native_params())
+    for i in range(2):
+        z = np.zeros((H, W), np.float32)
+        uo, vo, _ = FBO.FBParams(**kw).compute(A[i], B[i], z, z)
+        assert np.array_equal(U[i], uo) and np.array_equal(V[i], vo), (shape, i)

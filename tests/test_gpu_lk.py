@@ -171,3 +171,17 @@ def test_reference_example_configurations(ofri, mods, bundled_pair, name):
     d = max(np.abs(U - Uo).max(), np.abs(V - Vo).max())
     print("%s: max|d| %.3g px, flow range U [%.3f, %.3f]" % (name, d, U.min(), U.max()))
     assert d <= 1e-4
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (19, 23), (33, 50), (5, 131)])
+def test_small_and_odd_shapes(ofri, h, shape):
+    """Frames smaller than the window, widths that are not a multiple of 4 (row pitch != W on the device), batch of 2."""
+    rng = np.random.default_rng(shape[0] * 100 + shape[1])
+    H, W = shape
+    A = rng.uniform(0, 255, (2, H, W)).astype(np.float32)
+    B = np.roll(A, 1, 2) + rng.uniform(-2, 2, (2, H, W)).astype(np.float32)
+    U0 = rng.uniform(-0.5, 0.5, (2, H, W)).astype(np.float32)
+    U, V = h.lk_compute(A, B, U0, -U0, ofri.lk_params(5, 13))
+    for i in range(2):
+        uo, vo = LKO.lk_compute(A[i], B[i], U0[i], -U0[i], 5, 13)
+        assert np.array_equal(U[i], uo) and np.array_equal(V[i], vo), (shape, i)
