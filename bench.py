@@ -352,8 +352,10 @@ def run_banded(args, torch, dist, ofri, h, rank, world, dev):
         out["efficiency_vs_n1_ms"] = n1["ms_per_pair"] / (world * ms)
     out["limiter"] = ("per rank and solve: 600/32 grouped ncclSend/ncclRecv ghost-row exchanges of 32 rows x W x (U,V) "
                       "overlapped with the interior tiles (the overlapped launches leave band_reserve_sms SMs to the NCCL "
-                      "kernel), 15 ncclAllReduce of the Liu-Shen residual sums per level (stream-ordered, one per fused block "
-                      "of 4 sweeps), 2 x ghost_rows redundant rows per band and level, fixed per-launch cost on bands 1/N as tall")
+                      "kernel), 15 all-reduces of the Liu-Shen residual sums per level (stream-ordered, one per fused block "
+                      "of 4 sweeps; %s), 2 x ghost_rows redundant rows per band and level, fixed per-launch cost on bands "
+                      "1/N as tall" % ("one 1-CTA kernel each over NVLink peer memory" if world > 1 and
+                                       h.get_option("comm_peer_allreduce") else "ncclAllReduce"))
     if world > 1:
         h.comm_destroy()
     return out
