@@ -185,3 +185,30 @@ def test_small_and_odd_shapes(ofri, h, shape):
     for i in range(2):
         uo, vo = LKO.lk_compute(A[i], B[i], U0[i], -U0[i], 5, 13)
         assert np.array_equal(U[i], uo) and np.array_equal(V[i], vo), (shape, i)
+
+
+def test_farneback_and_lk_as_optional_adapters(ofri, mods):
+    """The OpenCL adapters in the OPTIONAL slot (refining a Horn-Schunck main adapter), and both together (dense LK main,
+    Farneback optional): kinds OFRI_ALGO_FB / OFRI_ALGO_LK in ofri_params.opt_algo."""
+    import ofri_farneback_oracle as FBO
+    LK, G, LS = mods
+    sys.path.insert(0, ofri.SRC_DIR)
+    try:
+        import Farneback_PyCL as FB
+        import HornSchunck as HS
+    finally:
+        sys.path.remove(ofri.SRC_DIR)
+    a, b = piv_pair(31, 96, 112, shift=(1.2, 0.7))
+    fkw = dict(windowSize=13, Niters=2, polyN=5, polySigma=1.1)
+    cases = [(lambda: HS.HSOpticalFlowAlgoAdapter([8.0, 12.0], 40), lambda: O.HSParams([8.0, 12.0], 40),
+              lambda: FB.Farneback_PyCL(**fkw), lambda: FBO.FBParams(**fkw)),
+             (lambda: HS.HSOpticalFlowAlgoAdapter([8.0, 12.0], 40), lambda: O.HSParams([8.0, 12.0], 40),
+              lambda: LK.denseLucasKanade_PyCl(Niter=3, halfWindow=7), lambda: LKO.LKParams(3, 7)),
+             (lambda: LK.denseLucasKanade_PyCl(Niter=3, halfWindow=7), lambda: LKO.LKParams(3, 7),
+              lambda: FB.Farneback_PyCL(**fkw), lambda: FBO.FBParams(**fkw))]
+    for i, (m, mo, o, oo) in enumerate(cases):
+        Uo, Vo = O.pyramidal_flow(a, b, 2.0, mo(), 2, 1, 0.48, oo())[:2]
+        U, V = G.genericPyramidalOpticalFlow(a, b, 2.0, m(), 2, 1, 0.48, o())
+        d = max(np.abs(U - Uo).max(), np.abs(V - Vo).max())
+        print("optional-slot case %d: max|d| %.3g" % (i, d))
+        assert d <= 1e-4, (i, d)
