@@ -78,7 +78,15 @@ class Farneback_PyCL(object):
         return g[0, int(size / 2):].copy()
 
     def native_params(self):
-        """ofri_farneback_params of this adapter (tables for every internal pyramid level it may use)."""
+        """ofri_farneback_params of this adapter (tables for every internal pyramid level it may use); rebuilt only when
+        a constructor attribute has changed (the Decimal arithmetic of the window kernel takes milliseconds)."""
+        key = (self.windowSize, self.numIters, self.polyN, self.polySigma, bool(self.useGaussianFilter),
+               self.pyramidalLevels, self.pyrScale)
+        if getattr(self, '_params_key', None) != key:
+            self._params, self._params_key = self._build_native_params(), key
+        return self._params
+
+    def _build_native_params(self):
         n = self.polyN
         g, xg, xxg, ig11, ig03, ig33, ig55 = self.FarnebackPrepareGaussian()
         blur = []
