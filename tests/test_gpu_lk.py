@@ -2,6 +2,7 @@
 src/denseLucasKanade_PyCL.py) against oracle/ofri_lk_oracle.c on seeded inputs.  Oracle and kernel make the same three
 choices where the OpenCL original defers to the device (full-float32 bilinear sampler, fused mad, IEEE division) and add
 in the same order, so the stand-alone compute() is required to be BIT-IDENTICAL to the oracle."""
+import os
 import sys
 
 import numpy as np
@@ -212,3 +213,25 @@ def test_farneback_and_lk_as_optional_adapters(ofri, mods):
         d = max(np.abs(U - Uo).max(), np.abs(V - Vo).max())
         print("optional-slot case %d: max|d| %.3g" % (i, d))
         assert d <= 1e-4, (i, d)
+
+
+def test_benchmark_of_methods_table(ofri, bundled_pair):
+    """examples/run_benchmark_of_methods.py: the ten rows of the reference's benchmark_of_methods.py; its six dense-LK /
+    Farneback rows against the oracle driver on a crop of the bundled pair (the four HS rows have reference goldens:
+    test_gpu_parity.py::test_driver_bom_rows)."""
+    import importlib.util
+    import ofri_farneback_oracle as FBO
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bom_b200", os.path.join(root, "examples", "run_benchmark_of_methods.py"))
+    bom = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bom)
+    a = np.ascontiguousarray(bundled_pair[0][200:328, 180:324])
+    b = np.ascontiguousarray(bundled_pair[1][200:328, 180:324])
+    rows = [r for r in bom.ROWS if r[1] in ("lk", "fb")]
+    res = bom.run_benchmark(a, b, None, rows)
+    for name, family, sigma, levels, ls in rows:
+        theirs = O.LSParams(0.1) if ls else (LKO.LKParams(5, 13) if family == "lk" else FBO.FBParams())
+        Uo, Vo = O.pyramidal_flow(a, b, sigma, theirs, levels, 1)[:2]
+        d = max(np.abs(res[name]["U"] - Uo).max(), np.abs(res[name]["V"] - Vo).max())
+        print("BOM row %s: max|d| %.3g" % (name, d))
+        assert d <= 1e-4, (name, d)
