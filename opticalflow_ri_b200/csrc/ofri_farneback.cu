@@ -40,9 +40,16 @@ __global__ void fb_filter_v_kernel(const Img* __restrict__ src, const Img* __res
   float acc;
   if (MODE == 0) {
     acc = fmul(p[(long)y * s.pitch], t.k[0]);
-    for (int j = 1; j <= t.kh; ++j) {
-      const float a = p[(long)idx_low(y - j, s.H - 1) * s.pitch], c = p[(long)idx_high(y + j, s.H - 1) * s.pitch];
-      acc = fadd(acc, fmul(fadd(a, c), t.k[j]));
+    if (y - t.kh >= 0 && y + t.kh <= s.H - 1) {        // interior rows: no border mapping (its modulo guards cost more than the taps)
+      const float* lo = p + (long)(y - 1) * s.pitch;
+      const float* hi = p + (long)(y + 1) * s.pitch;
+#pragma unroll 4
+      for (int j = 1; j <= t.kh; ++j, lo -= s.pitch, hi += s.pitch) acc = fadd(acc, fmul(fadd(*lo, *hi), t.k[j]));
+    } else {
+      for (int j = 1; j <= t.kh; ++j) {
+        const float a = p[(long)idx_low(y - j, s.H - 1) * s.pitch], c = p[(long)idx_high(y + j, s.H - 1) * s.pitch];
+        acc = fadd(acc, fmul(fadd(a, c), t.k[j]));
+      }
     }
   } else {
     acc = p[(long)y * s.pitch];
@@ -66,8 +73,13 @@ __global__ void fb_filter_h_kernel(const Img* __restrict__ src, const Img* __res
   float acc;
   if (MODE == 0) {
     acc = fmul(p[x], t.k[0]);
-    for (int i = 1; i <= t.kh; ++i)
-      acc = fadd(acc, fmul(fadd(p[idx_refl(x - i, s.W - 1)], p[idx_refl(x + i, s.W - 1)]), t.k[i]));
+    if (x - t.kh >= 0 && x + t.kh <= s.W - 1) {        // interior columns
+#pragma unroll 4
+      for (int i = 1; i <= t.kh; ++i) acc = fadd(acc, fmul(fadd(p[x - i], p[x + i]), t.k[i]));
+    } else {
+      for (int i = 1; i <= t.kh; ++i)
+        acc = fadd(acc, fmul(fadd(p[idx_refl(x - i, s.W - 1)], p[idx_refl(x + i, s.W - 1)]), t.k[i]));
+    }
   } else {
     acc = p[x];
     for (int i = 1; i <= t.kh; ++i) {
