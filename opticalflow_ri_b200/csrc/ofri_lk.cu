@@ -15,6 +15,8 @@
 // rule applied while loading (row-coalesced reads instead of four scattered cache lines per warp and tap).  The three device-defined operations of the OpenCL original are fixed as in
 // oracle/ofri_lk_oracle.c (see its header): image sampler = OpenCL-specification bilinear filter in full float32 with
 // clamp-to-edge addressing, `mad` = fused multiply-add, IEEE division -- so the result is bit-identical to that oracle.
+#include <climits>
+
 #include "ofri_internal.h"
 #include "ofri_pixel.cuh"
 
@@ -59,8 +61,20 @@ __device__ __forceinline__ void lk_stage_window(const float* __restrict__ im, in
                                                 float* __restrict__ dst, int pitch_s, int tid) {
   static_assert(N > 32 && N <= 64, "two column loads per lane");
   const int lane = tid & 31, half = tid >> 5;
-  const int c0 = min(max(x0 + lane, 0), W - 1), c1 = min(max(x0 + 32 + lane, 0), W - 1);
   const bool second = lane < N - 32;
+  if (y0 >= 0 && x0 >= 0 && y0 + N <= H && x0 + N <= W) {      // CTA-uniform: window inside the image, no clamping; the
+    const float* src = im + (long)(y0 + half) * pitch + x0 + lane;   // row pointers advance by two rows per trip
+    float* d = dst + half * pitch_s + lane;
+    const long step = 2 * pitch;
+    const int dstep = 2 * pitch_s;
+#pragma unroll 3
+    for (int yy = half; yy < N; yy += 2, src += step, d += dstep) {
+      d[0] = __ldg(src);
+      if (second) d[32] = __ldg(src + 32);
+    }
+    return;
+  }
+  const int c0 = min(max(x0 + lane, 0), W - 1), c1 = min(max(x0 + 32 + lane, 0), W - 1);
 #pragma unroll 2
   for (int yy = half; yy < N; yy += 2) {
     const float* row = im + (long)min(max(y0 + yy, 0), H - 1) * pitch;
@@ -156,13 +170,19 @@ __global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V
       lx[t] = fadd(lx[t - 1], 8.0f);
       ly[t] = fadd(ly[t - 1], 8.0f);
     }
+    int bx = INT_MIN, by = INT_MIN;                      // window of frame 2 currently staged (none)
     for (int k = 0; k < iters; ++k) {
       if (ppx < -hw || ppx >= (float)W || ppy < -hw || ppy >= (float)H) break;
       // stage the window of frame 2 this step samples (all 64 x 16 positions lie in [ppx, ppx + 32] x [ppy, ppy + 32];
-      // the previous step's reads ended before the barriers of its work-group sum)
-      const int bx = (int)floorf(ppx) - 1, by = (int)floorf(ppy) - 1;
-      lk_stage_window<LK_WIN>(pJ, H, W, J.pitch, by, bx, jwin, LK_WPITCH, tid);
-      __syncthreads();
+      // the previous step's reads ended before the barriers of its work-group sum) -- unless the step moved the window
+      // origin by less than a texel and the staged window still covers it (CTA-uniform)
+      const int nbx = (int)floorf(ppx) - 1, nby = (int)floorf(ppy) - 1;
+      if (nbx != bx || nby != by) {
+        bx = nbx;
+        by = nby;
+        lk_stage_window<LK_WIN>(pJ, H, W, J.pitch, by, bx, jwin, LK_WPITCH, tid);
+        __syncthreads();
+      }
       float b[2] = {0.0f, 0.0f};
       LkAxis ax[4], ay[4];
 #pragma unroll
