@@ -91,6 +91,77 @@ __global__ void fb_filter_h_kernel(const Img* __restrict__ src, const Img* __res
   d.p[(long)b * d.stride + (long)y * d.pitch + x] = acc;
 }
 
+// Register sliding-window forms of the Gaussian passes for a compile-time half width KH: a thread produces RPT consecutive
+// outputs along the filter axis from RPT + 2 KH inputs it loads once (5 instead of 33 loads per output at KH = 16), each
+// output accumulated in exactly the order of the kernels above (-> the same bits).  Threads whose outputs need the border
+// mapping take the per-output path.
+template <int KH, int RPT>
+__global__ void __launch_bounds__(256) fb_filter_v_sw_kernel(const Img* __restrict__ src, const Img* __restrict__ dst,
+                                                             int nplanes, FbTaps t) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = (blockIdx.y * blockDim.y + threadIdx.y) * RPT;
+  const int pl = blockIdx.z % nplanes, b = blockIdx.z / nplanes;
+  const Img s = src[pl], d = dst[pl];
+  if (x >= s.W || y0 >= s.H) return;
+  const float* p = s.p + (long)b * s.stride + x;
+  float* o = d.p + (long)b * d.stride + x;
+  if (y0 - KH >= 0 && y0 + RPT - 1 + KH <= s.H - 1) {
+    float v[RPT + 2 * KH];
+    const float* q = p + (long)(y0 - KH) * s.pitch;
+#pragma unroll
+    for (int i = 0; i < RPT + 2 * KH; ++i, q += s.pitch) v[i] = *q;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      float acc = fmul(v[r + KH], t.k[0]);
+#pragma unroll
+      for (int j = 1; j <= KH; ++j) acc = fadd(acc, fmul(fadd(v[r + KH - j], v[r + KH + j]), t.k[j]));
+      o[(long)(y0 + r) * d.pitch] = acc;
+    }
+    return;
+  }
+  for (int r = 0; r < RPT && y0 + r < s.H; ++r) {
+    const int y = y0 + r;
+    float acc = fmul(p[(long)y * s.pitch], t.k[0]);
+    for (int j = 1; j <= KH; ++j) {
+      const float a = p[(long)idx_low(y - j, s.H - 1) * s.pitch], c = p[(long)idx_high(y + j, s.H - 1) * s.pitch];
+      acc = fadd(acc, fmul(fadd(a, c), t.k[j]));
+    }
+    o[(long)y * d.pitch] = acc;
+  }
+}
+// horizontal: a warp owns 32 RPT consecutive outputs of one row; the row segment is staged in shared memory (coalesced),
+// skewed by one float per 32 so that the lanes' RPT-strided windows fall into different banks
+template <int KH, int RPT>
+__global__ void __launch_bounds__(256) fb_filter_h_sw_kernel(const Img* __restrict__ src, const Img* __restrict__ dst,
+                                                             int nplanes, FbTaps t) {
+  constexpr int SEG = 32 * RPT, NIN = SEG + 2 * KH, NSK = NIN + NIN / 32 + 1;
+  __shared__ float sm[8][NSK];
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  const int xs = blockIdx.x * SEG, y = blockIdx.y * blockDim.y + wy;
+  const int pl = blockIdx.z % nplanes, b = blockIdx.z / nplanes;
+  const Img s = src[pl], d = dst[pl];
+  if (y >= s.H || xs >= s.W) return;                 // warp-uniform
+  const float* p = s.p + (long)b * s.stride + (long)y * s.pitch;
+  float* o = d.p + (long)b * d.stride + (long)y * d.pitch;
+  float* row = sm[wy];
+  for (int e = lane; e < NIN; e += 32) row[e + (e >> 5)] = p[idx_refl(xs - KH + e, s.W - 1)];
+  __syncwarp();
+  const int x0 = xs + lane * RPT;
+  if (x0 >= s.W) return;
+  float v[RPT + 2 * KH];
+#pragma unroll
+  for (int i = 0; i < RPT + 2 * KH; ++i) {
+    const int e = lane * RPT + i;
+    v[i] = row[e + (e >> 5)];
+  }
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    float acc = fmul(v[r + KH], t.k[0]);
+#pragma unroll
+    for (int j = 1; j <= KH; ++j) acc = fadd(acc, fmul(fadd(v[r + KH - j], v[r + KH + j]), t.k[j]));
+    if (x0 + r < s.W) o[x0 + r] = acc;
+  }
+}
+
 // ---- polynomial expansion (CL:72-132) ------------------------------------------------------------------------------------------
 // vertical pass: the three row-cache planes row[0], row[bdx], row[2 bdx]; rows clamped (replicate)
 __global__ void fb_poly_v_kernel(Img src, Img3 r, FbPoly c) {
@@ -235,6 +306,12 @@ static void fb_filter(const Img* src, const Img* tmp, const Img* dst, int n, con
     volatile float inv = 1.0f / area;
     fb_filter_v_kernel<1><<<g, b, 0, s>>>(d_imgs, d_imgs + n, n, t);
     fb_filter_h_kernel<1><<<g, b, 0, s>>>(d_imgs + n, d_imgs + 2 * n, n, t, inv);
+  } else if (kh == 16 && src[0].H > 2 * kh && src[0].W > 2 * kh) {   // the default 33-tap window: sliding-window forms
+    constexpr int RPT = 8;
+    dim3 gv((src[0].W + 31) / 32, (src[0].H + 8 * RPT - 1) / (8 * RPT), n * src[0].batch);
+    dim3 gh((src[0].W + 32 * RPT - 1) / (32 * RPT), (src[0].H + 7) / 8, n * src[0].batch);
+    fb_filter_v_sw_kernel<16, RPT><<<gv, b, 0, s>>>(d_imgs, d_imgs + n, n, t);
+    fb_filter_h_sw_kernel<16, RPT><<<gh, b, 0, s>>>(d_imgs + n, d_imgs + 2 * n, n, t);
   } else {
     fb_filter_v_kernel<0><<<g, b, 0, s>>>(d_imgs, d_imgs + n, n, t);
     fb_filter_h_kernel<0><<<g, b, 0, s>>>(d_imgs + n, d_imgs + 2 * n, n, t, 0.0f);
