@@ -174,9 +174,12 @@ ls_sweep_simple_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, 
     int src = (st[0] + k) & 1;
     if (src) { ui = u1; vi = v1; uo = u0; vo = v0; } else { ui = u0; vi = v0; uo = u1; vo = v1; }
   }
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  // mode 0 is launched with one block per 8 rows (the loop runs once); the replay launches, which almost always return
+  // above, use a few blocks per column strip and pair (262 144 empty blocks cost 88 us per launch at 64 pairs of 1024^2)
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
   double du2 = 0.0, dv2 = 0.0;
-  if (x < W && y < H) {
+  for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < H; y += gridDim.y * blockDim.y) {
+    if (x >= W) break;
     const float* U = ui.p + (long)b * ui.stride;
     const float* V = vi.p + (long)b * vi.stride;
     float uc[3][3], vc[3][3];
@@ -202,8 +205,8 @@ ls_sweep_simple_kernel(Img u0, Img v0, Img u1, Img v1, LsPlanes co, float hpar, 
     vo.p[(long)b * vo.stride + (long)y * vo.pitch + x] = vn;
     if (y >= band.own_lo && y < band.own_hi) {     // residual over the rows this band owns (all rows normally)
       float eu = fsub(un, uc[1][1]), ev = fsub(vn, vc[1][1]);
-      du2 = (double)eu * (double)eu;
-      dv2 = (double)ev * (double)ev;
+      du2 += (double)eu * (double)eu;
+      dv2 += (double)ev * (double)ev;
     }
   }
   if (mode == 0) block_atomic_add2(du2, dv2, errs + ((long)b * maxiter + k) * 2, sh);
@@ -510,8 +513,9 @@ void launch_ls_solve(const Img& ua, const Img& va, const Img& ub, const Img& vb,
   }
   ls_finalize_kernel<<<(batch + 127) / 128, 128, 0, s>>>(errs, state, batch, maxiter, tol, npix, T, nfull);
   lc.n += 1;
+  const dim3 gr(gs.x, gs.y < 8 ? gs.y : 8, gs.z);   // replay launches: their blocks loop over the rows (see the kernel)
   for (int j = 0; j < T - 1 && nfull > 0; ++j) {   // conditional replay of an overshot fused block
-    ls_sweep_simple_kernel<<<gs, bs, 0, s>>>(ua, va, ub, vb, coef, hpar, j, maxiter, tol, errs, state, 1, T, band);
+    ls_sweep_simple_kernel<<<gr, bs, 0, s>>>(ua, va, ub, vb, coef, hpar, j, maxiter, tol, errs, state, 1, T, band);
     lc.n += 1;
     if (hook) hook(-1, 0, 2);    // replay step: both buffers may have been written; refresh the ghost rows of both
   }
