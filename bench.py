@@ -18,6 +18,7 @@ Printed JSON line (rank 0):
   roofline      the dominant kernel, live (stage timers = CUDA events around the kernel family's launches); traffic from
                 the committed ncu captures (profiles/r2_traffic.json)
   configs       pairs/s of BASELINE configs 1 and 2 (Horn-Schunck only, 1 / 2 levels) on batched 512 x 512 pairs
+  adapters      ms per pair of the Farneback and dense Lucas-Kanade adapters at the reference examples' parameters
   banded        BASELINE configs[4]: ONE 16384 x 16384 pair split into row bands over the N ranks (NCCL ghost-row
                 exchange inside libofri.so); N = 1 runs the same entry point with one band.  Median ms per pair,
                 Gpix-sweeps/s, a bit-for-bit check against the single-GPU path at 4096^2, max |d| against the
@@ -575,6 +576,39 @@ def run_ours(args):
             configs[name] = {"pairs_per_s": world * Pc * 2 / (msc / 1e3),
                              "gpix_sweeps_per_s": world * Pc * 2 * px_it / (msc / 1e3) / 1e9}
         del dca, dcb, dcu, dcv
+    # ---- the reference's two other adapters at their example parameters, batched 512 x 512 pairs ---------------
+    adapters = None
+    if not args.no_adapters:
+        sys.path.insert(0, ofri.SRC_DIR)
+        try:
+            from Farneback_PyCL import Farneback_PyCL
+            from denseLucasKanade_PyCL import denseLucasKanade_PyCl
+        finally:
+            sys.path.remove(ofri.SRC_DIR)
+        h.set_stream(stream.cuda_stream)
+        Pa, Ha = 16, 512
+        aa, ab = make_inputs(Pa, Ha, Ha)
+        daa, dab = torch.from_numpy(aa).cuda(), torch.from_numpy(ab).cuda()
+        dau, dav = torch.empty_like(daa), torch.empty_like(daa)
+        h.set_farneback(Farneback_PyCL().native_params())
+        h.set_lk(denseLucasKanade_PyCl(Niter=5, halfWindow=13).native_params())
+        adapters = {"pairs": Pa, "H": Ha, "W": Ha, "unit": "ms per pair (device-resident, CUDA events, one-level driver call, "
+                                                          "adapter as main, best of 4)"}
+        for name, algo, sigma in (("farneback_w33_it5_poly7", ofri.fb_algo(), 0.0), ("dense_lk_hw13_it5", ofri.lk_algo(), 2.0)):
+            pr = ofri.make_params(algo, None, filter_sigma=sigma, pyramid_levels=1, k_levels=1, warping=False,
+                                  final_scaling=False)
+            best = None
+            for _ in range(4):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                h.pyramidal_flow_ptr(daa.data_ptr(), dab.data_ptr(), Pa, Ha, Ha, pr, dau.data_ptr(), dav.data_ptr(), None,
+                                     device=True)
+                a1.record(stream)
+                a1.synchronize()
+                ms = a0.elapsed_time(a1) / Pa
+                best = ms if best is None or ms < best else best
+            adapters[name] = {"ms_per_pair": best, "mpx_per_s": Ha * Ha / best / 1e3}
+        del daa, dab, dau, dav
     # ---- row-band mode (BASELINE configs[4]) ---------------------------------------------------------------------------------
     banded_out = None
     if not args.no_banded:
@@ -603,7 +637,7 @@ def run_ours(args):
                                  "host_memory": "pageable numpy arrays (library path %d: %s)"
                                  % (host_path, "pinned bounce ring + 2 host threads" if host_path == 2 else "direct copies"),
                                  "ratio_to_pinned": e2e_pageable / e2e_val, "result_check_max_abs_u": check_p},
-                "configs": configs, "banded": banded_out,
+                "configs": configs, "adapters": adapters, "banded": banded_out,
                 "gpu_launches": int(launches), "clocks": clocks,
                 "stage_ms_one_step": stage_ms}
         print(json.dumps(line))
@@ -629,6 +663,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-banded", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-adapters", action="store_true")
     ap.add_argument("--banded-size", type=int, default=BANDED_SIZE)
     ap.add_argument("--banded-check", type=int, default=BANDED_CHECK)
     ap.add_argument("--banded-reps", type=int, default=BANDED_REPS)
