@@ -586,7 +586,7 @@ def run_ours(args):
         finally:
             sys.path.remove(ofri.SRC_DIR)
         h.set_stream(stream.cuda_stream)
-        Pa, Ha = 16, 512
+        Pa, Ha = 64, 512
         aa, ab = make_inputs(Pa, Ha, Ha)
         daa, dab = torch.from_numpy(aa).cuda(), torch.from_numpy(ab).cuda()
         dau, dav = torch.empty_like(daa), torch.empty_like(daa)
