@@ -113,61 +113,28 @@ __device__ __forceinline__ void hs_tma_ghosts(const TmTile& tl, int W, int H, fl
   const bool left = tl.x0 < 0;                       // then x0 == -HX: global column 0 is tile column HX
   const int cw = (W - 1) - tl.x0;                    // tile column of global column W-1
   const bool right = cw + 1 < SW;
-  // Sources and destinations of a fix-up are disjoint column (row) sets, so every thread first loads all its values and
-  // then stores them: the loads are in flight together instead of one shared-memory round trip per element (the ghost
-  // columns of all rows and planes live in the same HX banks).
-  constexpr int NX = (5 * SH * HX + C::NT - 1) / C::NT;
-  auto x_pass = [&](bool is_left) {
-    float val[NX];
-#pragma unroll
-    for (int t = 0; t < NX; ++t) {
-      const int i = tid + t * C::NT;
-      const int k = 1 + i % HX, row = (i / HX) % SH, pl = i / (HX * SH);
-      const float* r = stage + pl * C::PLANE + row * SW;
-      val[t] = (i < 5 * SH * HX) ? (is_left ? r[HX + k] : r[cw - k]) : 0.0f;
-    }
-#pragma unroll
-    for (int t = 0; t < NX; ++t) {
-      const int i = tid + t * C::NT;
+  if (left || right) {
+    for (int i = tid; i < 5 * SH * HX; i += C::NT) {
       const int k = 1 + i % HX, row = (i / HX) % SH, pl = i / (HX * SH);
       float* r = stage + pl * C::PLANE + row * SW;
-      if (i < 5 * SH * HX) {
-        if (is_left) r[HX - k] = val[t];
-        else if (cw + k < SW) r[cw + k] = val[t];
-      }
+      if (left) r[HX - k] = r[HX + k];
+      if (right && cw + k < SW) r[cw + k] = r[cw - k];
     }
-  };
-  if (left) x_pass(true);
-  if (right) x_pass(false);
-  if (left || right) __syncthreads();
+    __syncthreads();
+  }
   const bool top = tl.y0 < 0;                        // then y0 == -T: global row 0 is tile row T
   const int rh = (H - 1) - tl.y0;                    // tile row of global row H-1
   const bool bottom = rh + 1 < SH;
-  constexpr int NY = (5 * T * (SW / 4) + C::NT - 1) / C::NT;
-  auto y_pass = [&](bool is_top) {
-    float4 val[NY];
-#pragma unroll
-    for (int t = 0; t < NY; ++t) {
-      const int i = tid + t * C::NT;
-      const int c4 = i % (SW / 4), k = 1 + (i / (SW / 4)) % T, pl = i / ((SW / 4) * T);
-      const float* p = stage + pl * C::PLANE + 4 * c4;
-      val[t] = (i < 5 * T * (SW / 4)) ? *reinterpret_cast<const float4*>(p + (is_top ? T + k : rh - k) * SW)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int t = 0; t < NY; ++t) {
-      const int i = tid + t * C::NT;
+  if (top || bottom) {
+    for (int i = tid; i < 5 * T * (SW / 4); i += C::NT) {
       const int c4 = i % (SW / 4), k = 1 + (i / (SW / 4)) % T, pl = i / ((SW / 4) * T);
       float* p = stage + pl * C::PLANE + 4 * c4;
-      if (i < 5 * T * (SW / 4)) {
-        if (is_top) *reinterpret_cast<float4*>(p + (T - k) * SW) = val[t];
-        else if (rh + k < SH) *reinterpret_cast<float4*>(p + (rh + k) * SW) = val[t];
-      }
+      if (top) *reinterpret_cast<float4*>(p + (T - k) * SW) = *reinterpret_cast<const float4*>(p + (T + k) * SW);
+      if (bottom && rh + k < SH)
+        *reinterpret_cast<float4*>(p + (rh + k) * SW) = *reinterpret_cast<const float4*>(p + (rh - k) * SW);
     }
-  };
-  if (top) y_pass(true);
-  if (bottom) y_pass(false);
-  if (top || bottom) __syncthreads();
+    __syncthreads();
+  }
 }
 
 template <int T, int R, int NRG>
