@@ -10,9 +10,10 @@
 // grid down to the window; per-work-item sums accumulate in that order by FMA, the 64 partial sums are added by the
 // fixed tree s[t] += s[t + 32], + 16, + 8, + 4, (s0 + s1) + (s2 + s3).  Here: one 64-thread CTA per pixel (persistent
 // grid, runs of 8 neighbouring pixels per CTA), the tree's first level through shared memory (warp 1 -> warp 0), the
-// rest by warp shuffles in the same operand order.  Frame 1's 34 x 34 patch and, per Gauss-Newton step, the 36 x 36
-// window of frame 2 that the step's 1024 bilinear samples fall into are staged in shared memory with the clamp-to-edge
-// rule applied while loading (row-coalesced reads instead of four scattered cache lines per warp and tap).  The three device-defined operations of the OpenCL original are fixed as in
+// rest by warp shuffles in the same operand order.  Frame 1's patch (and its Scharr derivatives) of a run of 8 pixels
+// and, per Gauss-Newton step, the 36 x 36 window of frame 2 that the step's 1024 bilinear samples fall into are staged
+// in shared memory with the clamp-to-edge rule applied while loading (row-coalesced reads instead of four scattered
+// cache lines per warp and tap).  The three device-defined operations of the OpenCL original are fixed as in
 // oracle/ofri_lk_oracle.c (see its header): image sampler = OpenCL-specification bilinear filter in full float32 with
 // clamp-to-edge addressing, `mad` = fused multiply-add, IEEE division -- so the result is bit-identical to that oracle.
 #include <climits>
@@ -32,7 +33,9 @@ struct LkWeights { float wx[8][4], wy[8][4]; };
 // once for each of its 4 sample columns and 4 sample rows (LkAxis) and combines them per sample -- the same float32
 // operations on the same operands as a direct image read, hence the same bits.  The index clamp into the window is a
 // memory-safety guard only (the window is one texel wider on every side than the positions can reach).
-constexpr int LK_WIN = 36, LK_WPITCH = 40;            // pitch 40: the 8 x 4 sample lattice of a warp hits 32 different banks
+// pitch 40 (72 for the 41 columns of a run's frame-1 patch): = 8 mod 32, so the 8 x 4 sample lattice of a warp hits 32
+// different banks
+constexpr int LK_WIN = 36, LK_WPITCH = 40, LK_PPITCH = 72;
 struct LkAxis { float a, oa; int off; };             // weight of the upper texel, of the lower texel, window offset
 __device__ __forceinline__ LkAxis lk_axis(float x, int base, int scale) {
   const float fx = fsub(x, 0.5f);
@@ -53,16 +56,16 @@ __device__ __forceinline__ float lk_sample(const float* __restrict__ win, const 
   return r;
 }
 
-// Stage an N x N window of `im` whose top-left texel is (y0, x0) into shared memory (row pitch `pitch_s`), clamp-to-edge
+// Stage an N x NC window of `im` whose top-left texel is (y0, x0) into shared memory (row pitch `pitch_s`), clamp-to-edge
 // applied while loading.  The two warps take alternate rows; a lane loads column `lane` and, for the first N - 32 lanes,
 // column 32 + lane: one clamped column offset per lane for the whole window, one clamped row pointer per row.
-template <int N>
+template <int N, int NC = N>
 __device__ __forceinline__ void lk_stage_window(const float* __restrict__ im, int H, int W, long pitch, int y0, int x0,
                                                 float* __restrict__ dst, int pitch_s, int tid) {
-  static_assert(N > 32 && N <= 64, "two column loads per lane");
+  static_assert(NC > 32 && NC <= 64, "two column loads per lane");
   const int lane = tid & 31, half = tid >> 5;
-  const bool second = lane < N - 32;
-  if (y0 >= 0 && x0 >= 0 && y0 + N <= H && x0 + N <= W) {      // CTA-uniform: window inside the image, no clamping; the
+  const bool second = lane < NC - 32;
+  if (y0 >= 0 && x0 >= 0 && y0 + N <= H && x0 + NC <= W) {      // CTA-uniform: window inside the image, no clamping; the
     const float* src = im + (long)(y0 + half) * pitch + x0 + lane;   // row pointers advance by two rows per trip
     float* d = dst + half * pitch_s + lane;
     const long step = 2 * pitch;
@@ -110,12 +113,12 @@ __device__ __forceinline__ void lk_group_sum(float (&val)[N], float* sm, int tid
 }
 
 __global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V, int iters, float hw, LkWeights wt) {
-  __shared__ float patch[34 * LK_WPITCH];
+  __shared__ float patch[34 * LK_PPITCH];             // frame 1 around the run: rows py-1 .. py+32, 41 columns
+  __shared__ float ddx[32 * LK_WPITCH], ddy[32 * LK_WPITCH];   // its (unweighted) Scharr derivatives, 32 x 39
   __shared__ float jwin[LK_WIN * LK_WPITCH];
   __shared__ float red[3 * 33];
   const int tid = threadIdx.x, xid = tid & 7, yid = tid >> 3;
   const int H = I.H, W = I.W;
-  const long npix = (long)H * W;
   const float* __restrict__ pI = I.at(blockIdx.y);
   const float* __restrict__ pJ = J.at(blockIdx.y);
   float* pU = U.at(blockIdx.y);
@@ -126,27 +129,40 @@ __global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V
 #pragma unroll
     for (int tx = 0; tx < 4; ++tx) w[ty][tx] = fmul(wt.wy[yid][ty], wt.wx[xid][tx]);
   const int ihw = (int)hw;
-  // pixels in runs of 8 consecutive indices per CTA (round-robin over the runs): the windows of a run overlap almost
-  // entirely, so its image reads stay in L1
-  for (long gid = (long)blockIdx.x * 8; gid < npix; gid = ((gid & 7) == 7) ? gid - 7 + (long)gridDim.x * 8 : gid + 1) {
-    const int i = (int)(gid / W), j = (int)(gid - (long)i * W);
-    const int px = j - ihw, py = i - ihw;
-    __syncthreads();                                   // the previous pixel's patch is no longer read
-    lk_stage_window<34>(pI, H, W, I.pitch, py - 1, px - 1, patch, LK_WPITCH, tid);
+  // Pixels in RUNS of 8 neighbours of one image row per CTA (round-robin over the runs).  The windows of a run overlap in
+  // all but 7 columns, so frame 1 is staged once per run (34 x 41 texels) and its Scharr derivatives are formed once per
+  // run (32 x 39) into shared memory; a pixel then only reads its 16 samples per work-item and applies its 0/1 weights
+  // -- the same products in the same order as a per-pixel evaluation.
+  const int runs_per_row = (W + 7) / 8;
+  const long nruns = (long)H * runs_per_row;
+  for (long run = blockIdx.x; run < nruns; run += gridDim.x) {
+    const int i = (int)(run / runs_per_row), j0 = 8 * (int)(run - (long)i * runs_per_row);
+    const int py = i - ihw;
+    __syncthreads();                                   // the previous run's patch / derivatives are no longer read
+    lk_stage_window<34, 41>(pI, H, W, I.pitch, py - 1, j0 - ihw - 1, patch, LK_PPITCH, tid);
     __syncthreads();
+    for (int e = tid; e < 32 * 39; e += 64) {
+      const int y = e / 39, x = e - y * 39;
+      constexpr int P = LK_PPITCH;
+      const float* c = patch + (y + 1) * P + (x + 1);
+      const float sx = fsub(fsub(fadd(c[-P + 1], c[P + 1]), c[-P - 1]), c[P - 1]);
+      const float sy = fsub(fsub(fadd(c[P - 1], c[P + 1]), c[-P - 1]), c[-P + 1]);
+      ddx[y * LK_WPITCH + x] = __fmaf_rn(sx, 3.0f, fmul(fsub(c[1], c[-1]), 10.0f));
+      ddy[y * LK_WPITCH + x] = __fmaf_rn(sy, 3.0f, fmul(fsub(c[P], c[-P]), 10.0f));
+    }
+    __syncthreads();
+   for (int kp = 0; kp < 8 && j0 + kp < W; ++kp) {
+    const int j = j0 + kp;
     float pv[4][4], dxs[4][4], dys[4][4];
     float acc[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int ty = 0; ty < 4; ++ty)
 #pragma unroll
       for (int tx = 0; tx < 4; ++tx) {
-        constexpr int P = LK_WPITCH;
-        const float* c = patch + (ty * 8 + yid + 1) * P + (tx * 8 + xid + 1);
-        const float sx = fsub(fsub(fadd(c[-P + 1], c[P + 1]), c[-P - 1]), c[P - 1]);
-        const float sy = fsub(fsub(fadd(c[P - 1], c[P + 1]), c[-P - 1]), c[-P + 1]);
-        const float dx = fmul(__fmaf_rn(sx, 3.0f, fmul(fsub(c[1], c[-1]), 10.0f)), w[ty][tx]);
-        const float dy = fmul(__fmaf_rn(sy, 3.0f, fmul(fsub(c[P], c[-P]), 10.0f)), w[ty][tx]);
-        pv[ty][tx] = c[0];
+        const int y = ty * 8 + yid, x = tx * 8 + xid + kp;
+        const float dx = fmul(ddx[y * LK_WPITCH + x], w[ty][tx]);
+        const float dy = fmul(ddy[y * LK_WPITCH + x], w[ty][tx]);
+        pv[ty][tx] = patch[(y + 1) * LK_PPITCH + x + 1];
         dxs[ty][tx] = dx;
         dys[ty][tx] = dy;
         acc[0] = __fmaf_rn(dx, dx, acc[0]);
@@ -214,6 +230,7 @@ __global__ void __launch_bounds__(64) lk_dense_kernel(Img I, Img J, Img U, Img V
       pU[(long)i * U.pitch + j] = fsub(fadd(ppx, hw), (float)j);
       pV[(long)i * V.pitch + j] = fsub(fadd(ppy, hw), (float)i);
     }
+   }
   }
 }
 
@@ -243,7 +260,6 @@ int launch_lk(const Img& im1, const Img& im2, const Img& u_io, const Img& v_io, 
     axis_weights(id, win, lp->asym[0], lp->asym[1], wt.wx[id]);
     axis_weights(id, win, lp->asym[2], lp->asym[3], wt.wy[id]);
   }
-  const long npix = (long)im1.H * im1.W;
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -253,7 +269,7 @@ int launch_lk(const Img& im1, const Img& im2, const Img& u_io, const Img& v_io, 
   }
   const long want = (long)num_sms * 8;                  // 8 resident 64-thread CTAs per SM (128 registers per thread; 12 CTAs at 80
                                                         // registers measured 4 % slower: the kernel is issue-bound)
-  const long runs = (npix + 7) / 8;
+  const long runs = (long)im1.H * ((im1.W + 7) / 8);
   dim3 grid((unsigned)(runs < want ? runs : want), (unsigned)im1.batch);
   lk_dense_kernel<<<grid, 64, 0, s>>>(im1, im2, u_io, v_io, lp->n_iters, (float)((win - 1) >> 1), wt);
   ++lc.n;
