@@ -9,8 +9,8 @@ PARITY PINNING: the reference's own implementation of this adapter needs an Open
 does not have, so its outputs cannot be generated here: **parity unpinned** against the reference itself.  What the tests
 do instead: (1) every coefficient table against the reference's pure-Python generators (FarnebackPrepareGaussian is
 restated; getGaussianKernelBitExact is shared with the pinned oracle), (2) the whole compute() against OpenCV's CPU
-implementation of the same algorithm (cv2.calcOpticalFlowFarneback, which the reference's kernels port; agreement in the
-image interior, tests/test_farneback_cpu.py), (3) the CUDA path against this file on seeded inputs.
+implementation of the same algorithm (cv2.calcOpticalFlowFarneback, which the reference's kernels port; agreement to
+< 3e-6 px at the fixed point of the iteration in the image interior, tests/test_farneback_cpu.py), (3) the CUDA path against this file on seeded inputs.
 """
 import numpy as np
 
