@@ -145,6 +145,37 @@ def test_oracle_matches_opencv_at_the_fixed_point(case):
     assert abs(np.median(U[m:-m, m:-m]) - 1.3) < 0.15 and abs(np.median(V[m:-m, m:-m]) + 0.7) < 0.15
 
 
+@pytest.mark.parametrize("case", [(13, 6, 5, 1.1), (21, 8, 7, 1.5)])
+def test_oracle_gaussian_window_path_matches_opencv(case, monkeypatch):
+    """The Gaussian-window code path (gaussianBlur5) against OpenCV's OPTFLOW_FARNEBACK_GAUSSIAN at the fixed point, with
+    OpenCV's window kernel (sigma = 0.3 * (window / 2), float32 taps normalised once) substituted for the reference's:
+    the reference builds its window with getGaussianKernelBitExact, whose values (pinned on the reference's own generator,
+    test_oracle_tables_match_reference) are a different Gaussian, so only the PATH can be compared with OpenCV.
+    Measured: max 1.3e-6 / 2.5e-6 px."""
+    cv2 = pytest.importorskip("cv2")
+    win, iters, poly_n, poly_sigma = case
+    orig = FBO.blur_kernel_half
+
+    def opencv_window(ksize, sigma):
+        if ksize <= 3:                      # the level-0 pre-blur kernel: leave it alone
+            return orig(ksize, sigma)
+        m = ksize // 2
+        s = m * 0.3
+        k = np.exp(-np.arange(-m, m + 1, dtype=np.float64) ** 2 / (2 * s * s)).astype(np.float32)
+        k = (k * np.float32(1.0 / float(np.sum(k, dtype=np.float64)))).astype(np.float32)
+        return k[m:].copy()
+
+    monkeypatch.setattr(FBO, "blur_kernel_half", opencv_window)
+    a, b = piv_pair(11, 96, 112)
+    z = np.zeros_like(a)
+    fb = FBO.FBParams(windowSize=win, Niters=iters, polyN=poly_n, polySigma=poly_sigma, useGaussian=True, pyramidalLevels=1)
+    U, V, _ = fb.compute(a, b, z, z)
+    flow = cv2.calcOpticalFlowFarneback(a, b, None, 0.5, 1, win, iters, poly_n, poly_sigma, cv2.OPTFLOW_FARNEBACK_GAUSSIAN)
+    m = win // 2 + 8
+    d = np.abs(np.dstack([U, V]) - flow)[m:-m, m:-m]
+    assert d.max() < 2e-5, d.max()
+
+
 def test_oracle_internal_pyramid_recovers_the_shift():
     a, b = piv_pair(11, 96, 112)
     z = np.zeros_like(a)
